@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Headline benchmark: observed-entry MM updates/s (M*N*iters/s) of the NBMF-MM fit loop.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (B200 kernels)
+  python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the reference
+
+A "step" is one MM iteration (H half-step + loss/stop rule + W half-step, reference
+_solver.py:143-175) over the whole matrix.  Workload = BASELINE.json configs[3]: synthetic
+bit-packed binary 1,000,000 x 100,000, K=32, 90 % observed, beta-dir, normalize, FP32,
+row-sharded over the N GPUs (fixed total size: strong scaling) with one NCCL allreduce of the
+K x N H-partials per iteration.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "oracle"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+METRIC = "observed-entry MM updates/s (M*N*iters/s)"
+UNIT = "updates/s"
+SEED = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--cols", type=int, default=100_000)
+    ap.add_argument("--k", type=int, default=32)
+    ap.add_argument("--obs", type=float, default=0.9)
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    cfg = {
+        "workload": f"configs[3]: synthetic bit-packed binary {a.rows}x{a.cols}, K={a.k}, {int(a.obs * 100)}% observed, "
+                    f"beta-dir, normalize, alpha=beta=1.2, row-sharded with NCCL allreduce of H partials",
+        "rows": a.rows, "cols": a.cols, "k": a.k, "observed_fraction": a.obs,
+        "orientation": "beta-dir", "projection_method": "normalize", "mask_semantics": "reference",
+        "l2": "inputs (bit planes, 2 x rows x cols / 8 bytes per pass) are far larger than the 126 MB L2; no flush needed",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_port_run(a, steps, warmup, rows=None, cols=None):
+    """Time the oracle port of the reference (NumPy + BLAS, all host threads) on a bounded sample of
+    the workload: a `rows x cols` block with the same K, mask fraction and generative recipe."""
+    import nbmf_oracle as orc
+    total = max(1, steps + warmup)
+    if rows is None:
+        rows = a.cpu_rows or (4096 if total <= 6 else 2048)
+    cols = cols or 4096
+    rows, cols = min(rows, a.rows), min(cols, a.cols)
+    rng = np.random.default_rng(SEED)
+    Wst = rng.dirichlet(np.ones(a.k), size=rows)
+    Hst = rng.random((a.k, cols)) * 0.2
+    Y = (rng.random((rows, cols)) < Wst @ Hst).astype(np.float64)
+    mask = (rng.random((rows, cols)) < a.obs).astype(np.float64)
+    rs = np.random.RandomState(0)
+    W = rs.uniform(0.1, 0.9, (rows, a.k)).T
+    W = W / W.sum(axis=0, keepdims=True)
+    H = rs.uniform(0.1, 0.9, (a.k, cols))
+    for _ in range(warmup):
+        W, H = orc.mm_step(Y, W, H, mask, 1.2, 1.2)
+        orc.map_objective(Y, W, H, mask, 1.2, 1.2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        W, H = orc.mm_step(Y, W, H, mask, 1.2, 1.2)            # one reference iteration ...
+        orc.map_objective(Y, W, H, mask, 1.2, 1.2)             # ... including its per-iteration loss
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([d.get("num_threads", 1) for d in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = os.cpu_count() or 1
+    return {
+        "value": rows * cols * steps / dt, "unit": UNIT, "cores": int(blas_threads), "kind": "port",
+        "sample": f"{rows}x{cols} block of the workload (same K={a.k}, {int(a.obs * 100)}% mask), {steps} iterations, "
+                  f"{dt / max(steps, 1):.2f} s/iter; oracle/nbmf_oracle.py (NumPy fp64 + BLAS, {blas_threads} threads, "
+                  f"{os.cpu_count()} host cpus)",
+    }, dt
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, dt = cpu_port_run(a, a.steps, a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / max(a.steps, 1) * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, {"note": "reference arm: CPU oracle port timed on a bounded sample, see cpu_baseline.sample"}),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from nbmf_mm_b200 import BitMatrix, _lib, nbmf_mm_solver
+    from nbmf_mm_b200.device import DeviceProblem, synth_bits_device
+    from nbmf_mm_b200.solver import _row_shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a GPU: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != a.gpus and rank == 0:
+        print(f"# note: --gpus {a.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    lib = _lib.load()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    M_rows, N, K = a.rows, a.cols, a.k
+    r0, r1 = _row_shard(M_rows, rank, world)
+    m_local = r1 - r0
+    hstar = (np.random.default_rng(SEED).random((K if K <= 32 else 32, N)) * 0.2).astype(np.float32)
+    P, Mk = synth_bits_device(SEED, r0, m_local, N, hstar, a.obs, dev)
+    n_obs_local = float(Mk.count())
+    n_obs = n_obs_local
+    if world > 1:
+        t = torch.tensor([n_obs_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        n_obs = float(t.item())
+
+    steps, warmup = a.steps, a.warmup
+    prob = DeviceProblem(m_local, N, K, dtype=a.dtype, vkind="bits", has_mask=True, alpha=1.2, beta=1.2, eps=1e-8,
+                         n_obs=n_obs, max_iter_cap=steps + warmup + 2, device=dev)
+    prob.set_bits(P, Mk)
+    if world > 1:
+        prob.init_comm()
+    tdt = torch.float32 if a.dtype == "float32" else torch.float64
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    W0 = torch.rand((m_local, K), generator=g, device=dev, dtype=tdt) * 0.8 + 0.1
+    H0 = torch.from_numpy(np.random.RandomState(0).uniform(0.1, 0.9, (K, N))).to(dev, tdt)
+    prob.set_factors(W0, H0, normalize_w=True)
+
+    # ---- device-resident timing: W warm-up iterations, then exactly K timed iterations
+    prob.fit_begin(steps + warmup + 1, 0.0)
+    prob.fit_enqueue(warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    prob.profile(True)
+    lib.nbmf_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    prob.fit_enqueue(steps)
+    ev1.record()
+    barrier()
+    sampler.stop_flag = True
+    launches = int(lib.nbmf_launch_count(0))
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    h_ms, h_cnt, w_ms, w_cnt = prob.profile_read()
+    prob.profile(False)
+    done, n_hist = prob.fit_poll(wait=True)
+    hist, _ = prob.fit_history(n_hist)
+    sampler.join(timeout=2)
+    value = M_rows * N * steps / (ms_total * 1e-3)
+    plan = prob.plan_info()
+
+    # ---- FMA-pipe peak (roofline denominator), measured on this GPU right after the timed region
+    scratch = torch.zeros(16, dtype=torch.float32, device=dev)
+    peak = C_double()
+    _lib.check(lib.nbmf_fma_peak(0 if a.dtype == "float32" else 1, 4000, scratch.data_ptr(),
+                                 torch.cuda.current_stream(dev).cuda_stream, peak.ref()), "nbmf_fma_peak")
+    peak_tf = peak.value
+    h_avg_ms = h_ms / max(h_cnt, 1)
+    w_avg_ms = w_ms / max(w_cnt, 1)
+    entries_local = float(m_local) * N
+    h_flop = 6.0 * K * entries_local          # Theta dot 2K + C and D accumulations 4K flop per entry
+    w_flop = 4.0 * K * entries_local          # Theta' dot 2K + one accumulation of H'(p-q) 2K
+    h_ach = h_flop / (h_avg_ms * 1e-3) * 1e-12 if h_cnt else None
+    w_ach = w_flop / (w_avg_ms * 1e-3) * 1e-12 if w_cnt else None
+    nominal = 2 * 128 * 148 * (sampler.max_mhz or 1965) * 1e6 * 1e-12
+    roofline = {
+        "bound": "fp32" if a.dtype == "float32" else "fp64", "kernel": "h_pass_kernel (H half-step + fused NLL)",
+        "achieved": h_ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (h_ach / peak_tf) if h_ach else None,
+        "peak_source": "measured in this run: nbmf_fma_peak (packed FFMA2 chains, 148x8 CTAs); MEASURED_PEAKS.json has no FP32 entry",
+        "nominal_peak": nominal, "frac_of_nominal": (h_ach / nominal) if h_ach else None,
+        "traffic": None,
+        "algorithmic_flop_per_entry": {"h_pass": 6 * K, "w_pass": 4 * K, "iteration": 10 * K},
+        "avg_launch_ms": h_avg_ms, "launches_timed": h_cnt, "share_of_step": h_ms / ms_total if ms_total else None,
+        "w_pass": {"achieved": w_ach, "frac": (w_ach / peak_tf) if w_ach else None, "avg_launch_ms": w_avg_ms,
+                   "share_of_step": w_ms / ms_total if ms_total else None},
+        "iteration_frac": (10.0 * K * entries_local * steps / (ms_total * 1e-3) * 1e-12 / peak_tf),
+        "hbm_context": {"algorithmic_bytes_per_entry_iteration": 0.375, "hbm_gbs_used": 0.375 * value / world * 1e-9,
+                        "hbm_peak_gbs": measured_peaks().get("hbm_gbs")},
+    }
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), H2D/D2H inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        Ph = torch.empty(P.words.shape, dtype=torch.int32, pin_memory=True).copy_(P.words)
+        Mh = torch.empty(Mk.words.shape, dtype=torch.int32, pin_memory=True).copy_(Mk.words)
+        prob.close()
+        del P, Mk, W0, H0
+        torch.cuda.empty_cache()
+        stats = {}
+        barrier()
+        t0 = time.perf_counter()
+        out = nbmf_mm_solver(BitMatrix(Ph, (m_local, N)), K, max_iter=steps, tol=0.0, alpha=1.2, beta=1.2,
+                             mask=BitMatrix(Mh, (m_local, N)), random_state=0, dtype=a.dtype, device=dev,
+                             distributed=True, shard=(r0, M_rows), stats=stats)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        assert out[4] == steps
+        e2e = {"value": M_rows * N * steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": stats["h2d_bytes"] / steps, "d2h_bytes_per_step": stats["d2h_bytes"] / steps,
+               "seconds": dt, "api": "nbmf_mm_b200.nbmf_mm_solver(BitMatrix(pinned host), mask=BitMatrix(pinned host), "
+                                    "max_iter=steps, tol=0, dtype=float32): H2D of both bit planes and the inits, "
+                                    "the fit loop, D2H of W, H and the loss history",
+               "final_loss": float(out[2][-1])}
+    else:
+        prob.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cpu, _ = cpu_port_run(a, 2, 1, rows=a.cpu_rows or 4096)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if a.dtype == "float32" else "f64", "data": "synthetic",
+            "config": workload_config(a, {"rows_per_gpu": m_local, "launch_plan": plan, "n_obs": n_obs,
+                                          "loss_first_last": [float(hist[0]), float(hist[-1])] if len(hist) else None}),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+class C_double:
+    def __init__(self):
+        import ctypes
+        self._c = ctypes.c_double(0.0)
+        self._ctypes = ctypes
+
+    def ref(self):
+        return self._ctypes.byref(self._c)
+
+    @property
+    def value(self):
+        return float(self._c.value)
+
+
+def measured_peaks():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        return {}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)

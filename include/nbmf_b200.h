@@ -1,0 +1,153 @@
+/* nbmf_b200.h -- C-ABI of libnbmf_b200.so: the B200 (sm_100a) implementation of the
+ * NBMF-MM fit loop (mean-parameterised Bernoulli NMF, Magron & Fevotte 2022).
+ *
+ * This is the drop-in boundary for ONE path of siddC/nbmf_mm: what sits below
+ * `NBMFMM.fit` (reference src/nbmf_mm/_base.py:98-111), i.e. `nbmf_mm_solver`
+ * (src/nbmf_mm/_solver.py:61-216), its one-step function `nbmf_mm_update_beta_dir`
+ * (_solver.py:5-59) and the fixed-H W-solver inlined in `NBMFMM.transform`
+ * (_base.py:178-198).  The reference has no FFI of its own (pure NumPy); each entry point
+ * below names the reference code it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer named *_dev is a DEVICE pointer on the current CUDA device; the caller
+ *    owns all memory (the library never allocates device memory: the caller sizes a
+ *    workspace with nbmf_workspace_bytes and passes it to nbmf_create);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, only the calls
+ *    documented as synchronising wait for it;
+ *  - matrices are in the solver's INTERNAL orientation (dir-beta callers pass the packed
+ *    transpose, as _solver.py:113-123 does): V is m x n, W is m x k row-major, H is k x n
+ *    row-major; `dtype` 0 = float32, 1 = float64 selects the arithmetic type of the path;
+ *  - bit planes are uint32 words, bit (j % 32) of word (j / 32) of row i, rows padded to
+ *    nbmf_words_per_row(n) words (a multiple of 32 words = 1024 columns), padding bits zero;
+ *  - return value 0 = ok, negative = error; nbmf_last_error() gives the message.  There is
+ *    no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef NBMF_B200_H
+#define NBMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBMF_OK 0
+#define NBMF_ERR_ARG (-1)
+#define NBMF_ERR_CUDA (-2)
+#define NBMF_ERR_UNSUPPORTED (-3)
+#define NBMF_ERR_NCCL (-4)
+
+#define NBMF_F32 0
+#define NBMF_F64 1
+#define NBMF_U8 2
+
+#define NBMF_V_BITS 0   /* binary V: planes P = V & mask and M = mask, 1 bit per entry each */
+#define NBMF_V_DENSE 1  /* probabilistic V in [0,1]: dense V*mask in `dtype` + mask bit plane */
+
+#define NBMF_MASK_REFERENCE 0 /* H step / loss treat unobserved entries as observed zeros (_solver.py:43,153-154) */
+#define NBMF_MASK_STRICT 1    /* only observed entries contribute (README / paper); unpinned */
+
+#define NBMF_PROJ_NORMALIZE 0 /* multiplicative step, /n, L1 renormalisation (_solver.py:53-57) */
+#define NBMF_PROJ_DUCHI 1     /* multiplicative step / n_obs(row), Euclidean simplex projection; unpinned */
+
+typedef struct nbmf_ctx nbmf_ctx;
+
+/* Problem description; replaces the keyword arguments of nbmf_mm_solver (_solver.py:61-75). */
+typedef struct nbmf_config {
+  int64_t m;             /* local rows of this shard (internal orientation) */
+  int64_t n;             /* columns */
+  int32_t k;             /* n_components, 1..64 */
+  int32_t dtype;         /* NBMF_F32 | NBMF_F64 */
+  int32_t vkind;         /* NBMF_V_BITS | NBMF_V_DENSE */
+  int32_t mask_semantics;
+  int32_t projection;
+  int32_t has_mask;      /* 0: everything observed (mask=None) */
+  double alpha, beta;    /* Beta prior of H (_solver.py:35-36) */
+  double eps;            /* 1e-8 in the reference */
+  double n_obs;          /* loss denominator: Y.size or count_nonzero(mask) over ALL shards (_solver.py:151,155) */
+  int32_t max_iter_cap;  /* capacity of the on-device loss history */
+  int32_t reserved;
+} nbmf_config;
+
+int nbmf_version(void);
+const char* nbmf_last_error(void);
+int64_t nbmf_words_per_row(int64_t n);          /* uint32 words per bit-plane row (multiple of 32) */
+int64_t nbmf_padded_cols(int64_t n);            /* leading dimension of dense V*mask rows (= 32 * words) */
+
+/* ---- data layer (replaces the per-iteration Y*mask / transposes of _solver.py:21-32) ---- */
+/* dense X (x_dtype F32|F64|U8, leading dim ldx) [+ mask] -> bit planes P (= X!=0 & mask) and M (nullable) */
+int nbmf_pack_bits(const void* x_dev, int x_dtype, int64_t ldx, const void* mask_dev, int mask_dtype, int64_t ldm,
+                   int64_t m, int64_t n, uint32_t* p_bits_dev, uint32_t* m_bits_dev, void* stream);
+/* dense X [+ mask] -> V*mask in out_dtype with leading dimension nbmf_padded_cols(n), zero padded */
+int nbmf_pack_dense(const void* x_dev, int x_dtype, int64_t ldx, const void* mask_dev, int mask_dtype, int64_t ldm,
+                    int64_t m, int64_t n, int out_dtype, void* vm_dev, void* stream);
+/* bit-plane transpose (m x n bits -> n x m bits): dir-beta runs as beta-dir on V^T (_solver.py:113-123) */
+int nbmf_transpose_bits(const uint32_t* src_dev, int64_t m, int64_t n, uint32_t* dst_dev, void* stream);
+/* number of set bits of a plane (count_nonzero(mask), _solver.py:155); synchronises the stream */
+int nbmf_popcount_bits(const uint32_t* bits_dev, int64_t m, int64_t n, uint64_t* scratch_dev, uint64_t* count_host,
+                       void* stream);
+/* counter-based synthetic generator keyed on (seed, global row, column): V ~ Bernoulli(W*H*) with
+ * Dirichlet(1) rows W* (derived from the key) and the given H* (kstar x n, float32), mask ~ Bernoulli(obs_frac) */
+int nbmf_synth_bits(uint64_t seed, int64_t row0, int64_t m, int64_t n, const float* hstar_dev, int32_t kstar,
+                    float obs_frac, uint32_t* p_bits_dev, uint32_t* m_bits_dev, void* stream);
+
+/* ---- fit context ---- */
+int64_t nbmf_workspace_bytes(const nbmf_config* cfg);
+int nbmf_create(const nbmf_config* cfg, void* workspace_dev, int64_t workspace_bytes, void* stream, nbmf_ctx** out);
+int nbmf_destroy(nbmf_ctx* ctx);
+/* borrow the data planes (must outlive the context) */
+int nbmf_set_data_bits(nbmf_ctx* ctx, const uint32_t* p_bits_dev, const uint32_t* m_bits_dev);
+int nbmf_set_data_dense(nbmf_ctx* ctx, const void* vm_dev, const uint32_t* m_bits_dev);
+/* W_init (m x k) / H_init (k x n) in cfg.dtype; normalize_w != 0 divides every W row by its sum
+ * (_solver.py:132-136).  Either pointer may be NULL to keep the current factor.  Resets the loop state. */
+int nbmf_set_factors(nbmf_ctx* ctx, const void* w_dev, const void* h_dev, int normalize_w);
+int nbmf_get_factors(nbmf_ctx* ctx, void* w_dev, void* h_dev);
+
+/* ---- single steps (replace nbmf_mm_update_beta_dir, _solver.py:5-59) ---- */
+int nbmf_h_half_step(nbmf_ctx* ctx);            /* H <- H' (_solver.py:39-47) */
+int nbmf_w_half_step(nbmf_ctx* ctx);            /* W <- W' with the current H (_solver.py:50-57) */
+/* MAP objective of the current factors (_solver.py:148-162); synchronises the stream */
+int nbmf_objective(nbmf_ctx* ctx, double* loss_host);
+
+/* ---- the fit loop (replaces the loop of nbmf_mm_solver, _solver.py:143-175) ----
+ * Runs up to max_iter MM iterations entirely on the stream; the loss of every iteration, the
+ * relative-change stop rule and n_iter are evaluated on the device.  Synchronises at the end and
+ * copies the loss history (n_iter doubles) and n_iter to the host. */
+int nbmf_fit(nbmf_ctx* ctx, int32_t max_iter, double tol, double* history_host, int32_t* n_iter_host,
+             int32_t* converged_host);
+/* same loop, asynchronous: enqueue `n_iters` more iterations (plus the trailing loss pass when the
+ * budget max_iter is reached) and return without waiting */
+int nbmf_fit_begin(nbmf_ctx* ctx, int32_t max_iter, double tol);
+int nbmf_fit_enqueue(nbmf_ctx* ctx, int32_t n_iters);
+/* non-blocking unless wait != 0: fetch (done, n_iter) of the work enqueued so far */
+int nbmf_fit_poll(nbmf_ctx* ctx, int wait, int32_t* done_host, int32_t* n_iter_host);
+int nbmf_fit_history(nbmf_ctx* ctx, double* history_host, int32_t count, int32_t* converged_host);
+
+/* ---- transform (replaces the 50 fixed-H W steps of NBMFMM.transform, _base.py:178-198) ----
+ * n_steps W half-steps with the current H from the current W, then clip to [1e-8, 1] and row-normalise. */
+int nbmf_transform(nbmf_ctx* ctx, int32_t n_steps);
+
+/* ---- multi-GPU: rows are sharded, the K x N partials of the H step are summed with one
+ * ncclAllReduce per iteration (no reference analogue) ---- */
+int nbmf_comm_unique_id(void* id128_host);                          /* rank 0; 128 bytes */
+int nbmf_comm_init(nbmf_ctx* ctx, const void* id128_host, int32_t rank, int32_t world);
+int nbmf_comm_world(nbmf_ctx* ctx);
+
+/* ---- measurement helpers ---- */
+/* sustained FMA-pipe throughput (TFLOP/s) of packed FFMA2 (dtype F32) or DFMA (F64); synchronises */
+int nbmf_fma_peak(int dtype, int32_t iters, void* scratch_dev, void* stream, double* tflops_host);
+/* per-launch CUDA-event timing of the two pass kernels (H pass, W pass) on the context's stream:
+ * enable clears the record; read synchronises and returns total milliseconds and launch counts */
+int nbmf_profile_enable(nbmf_ctx* ctx, int enable);
+int nbmf_profile_read(nbmf_ctx* ctx, double* h_ms_host, int32_t* h_count_host, double* w_ms_host, int32_t* w_count_host);
+/* launch geometry chosen for this context: H pass = column blocks x row splits, W pass = row blocks x column splits */
+int nbmf_plan_info(nbmf_ctx* ctx, int32_t* h_col_blocks, int32_t* h_row_splits, int32_t* w_row_blocks, int32_t* w_col_splits);
+/* number of kernels this library launched since the last reset */
+int64_t nbmf_launch_count(int reset);
+/* tiling of the pass kernels chosen for (dtype, vkind, k): columns per H-pass CTA, rows per W-pass CTA, padded K */
+int nbmf_variant_info(int dtype, int vkind, int k, int32_t* h_cols_per_cta, int32_t* w_rows_per_cta, int32_t* k_padded);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBMF_B200_H */

@@ -1,0 +1,655 @@
+// C-ABI of libnbmf_b200.so (declared in include/nbmf_b200.h): variant dispatch, workspace
+// planning, the device-resident fit loop and the NCCL row-shard reduction.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/nbmf_b200.h"
+#include "internal.h"
+
+namespace nbmf {
+bool lookup_f32_bits(int strict, int k, PassLaunch* out);
+bool lookup_f32_dense(int strict, int k, PassLaunch* out);
+bool lookup_f64_bits(int strict, int k, PassLaunch* out);
+bool lookup_f64_dense(int strict, int k, PassLaunch* out);
+
+bool lookup_pass(int dtype, int dense, int strict, int k, PassLaunch* out) {
+  if (k < 1) return false;
+  if (dtype == 0) return dense ? lookup_f32_dense(strict, k, out) : lookup_f32_bits(strict, k, out);
+  if (dtype == 1) return dense ? lookup_f64_dense(strict, k, out) : lookup_f64_bits(strict, k, out);
+  return false;
+}
+}  // namespace nbmf
+
+using namespace nbmf;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  return fail(NBMF_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(expr)                                         \
+  do {                                                         \
+    cudaError_t e__ = (expr);                                  \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #expr);      \
+  } while (0)
+#define CHECK_LAUNCH(n)                                        \
+  do {                                                         \
+    g_launches += (n);                                         \
+    cudaError_t e__ = cudaPeekAtLastError();                   \
+    if (e__ != cudaSuccess) return cuda_fail(e__, __func__);   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ NCCL (dlopen'd)
+struct NcclId { char internal[128]; };
+typedef int (*pfn_ncclGetUniqueId)(NcclId*);
+typedef int (*pfn_ncclCommInitRank)(void**, int, NcclId, int);
+typedef int (*pfn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*pfn_ncclCommDestroy)(void*);
+typedef const char* (*pfn_ncclGetErrorString)(int);
+typedef int (*pfn_ncclGroup)(void);
+static struct {
+  void* lib = nullptr;
+  pfn_ncclGetUniqueId GetUniqueId = nullptr;
+  pfn_ncclCommInitRank CommInitRank = nullptr;
+  pfn_ncclAllReduce AllReduce = nullptr;
+  pfn_ncclCommDestroy CommDestroy = nullptr;
+  pfn_ncclGetErrorString GetErrorString = nullptr;
+  pfn_ncclGroup GroupStart = nullptr, GroupEnd = nullptr;
+} g_nccl;
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+
+static int load_nccl() {
+  if (g_nccl.AllReduce) return NBMF_OK;
+  void* lib = nullptr;
+  if (const char* p = getenv("NBMF_NCCL_LIB")) lib = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy torch already mapped
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(NBMF_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+  g_nccl.lib = lib;
+  g_nccl.GetUniqueId = (pfn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (pfn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (pfn_ncclAllReduce)dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (pfn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (pfn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
+  g_nccl.GroupStart = (pfn_ncclGroup)dlsym(lib, "ncclGroupStart");
+  g_nccl.GroupEnd = (pfn_ncclGroup)dlsym(lib, "ncclGroupEnd");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+    g_nccl.AllReduce = nullptr;
+    return fail(NBMF_ERR_NCCL, "libnccl.so.2 lacks required symbols");
+  }
+  return NBMF_OK;
+}
+static int nccl_fail(int rc, const char* where) {
+  return fail(NBMF_ERR_NCCL, std::string(where) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error"));
+}
+
+// ------------------------------------------------------------------------------------ context
+struct Plan {
+  PassLaunch pl;
+  int64_t ldh, wpr;
+  int h_ncb, h_nsplit, w_nsplit, n_prior;
+  int64_t h_rows_per_split, w_cols_per_split;
+  size_t sz;   // sizeof(Real)
+  // workspace offsets
+  size_t oW, oH, oHt, oCDpart, oCDsum, oLLpart, oLLsum, oPrior, oG, oQ, oRowcount, oHist, oState, oLoss, total;
+};
+
+struct nbmf_ctx {
+  nbmf_config cfg;
+  Plan p;
+  cudaStream_t st;
+  unsigned char* ws;
+  const uint32_t* P = nullptr;
+  const uint32_t* M = nullptr;
+  const void* Vm = nullptr;
+  bool rowcount_ready = false;
+  // loop
+  int max_iter = 0;
+  double tol = 0.0;
+  int enqueued = 0;
+  bool tail_enqueued = false;
+  FitState* host_state = nullptr;   // pinned
+  cudaEvent_t poll_ev = nullptr;
+  bool poll_pending = false;
+  // comm
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+  // optional per-launch timing of the two pass kernels (bench.py roofline)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_h, prof_w;      // (start, stop) pairs
+
+  template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
+  void* W() const { return ws + p.oW; }
+  void* H() const { return ws + p.oH; }
+  void* Ht() const { return ws + p.oHt; }
+  FitState* state() const { return at<FitState>(p.oState); }
+};
+
+static void prof_clear(std::vector<cudaEvent_t>& v);
+
+static int choose_split(int64_t blocks, int64_t max_split) {
+  if (max_split < 1) max_split = 1;
+  const double sms = 148.0;
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= max_split; ++s) {
+    const double ctas = (double)blocks * s, waves = ctas / sms;
+    double score = waves / ceil(waves) * std::min(1.0, ctas / sms) - 0.01 * s;
+    if (score > best_score + 1e-9) { best = s; best_score = score; }
+  }
+  return best;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int make_plan(const nbmf_config& c, Plan* p) {
+  if (c.m < 1 || c.n < 1) return fail(NBMF_ERR_ARG, "m and n must be positive");
+  if (c.k < 1 || c.k > 64) return fail(NBMF_ERR_UNSUPPORTED, "n_components must be in 1..64");
+  if (c.dtype != NBMF_F32 && c.dtype != NBMF_F64) return fail(NBMF_ERR_ARG, "dtype must be NBMF_F32 or NBMF_F64");
+  if (c.vkind != NBMF_V_BITS && c.vkind != NBMF_V_DENSE) return fail(NBMF_ERR_ARG, "bad vkind");
+  if (c.mask_semantics == NBMF_MASK_STRICT && !c.has_mask) { /* strict == reference when everything is observed */ }
+  const int strict = (c.mask_semantics == NBMF_MASK_STRICT && c.has_mask) ? 1 : 0;
+  if (!lookup_pass(c.dtype, c.vkind == NBMF_V_DENSE, strict, c.k, &p->pl))
+    return fail(NBMF_ERR_UNSUPPORTED, "no kernel variant for this (dtype, vkind, k)");
+  p->sz = c.dtype == NBMF_F32 ? 4 : 8;
+  p->wpr = nbmf_words_per_row(c.n);
+  p->ldh = p->wpr * 32;
+  const int kp = p->pl.kp;
+  // H pass: column blocks x row splits
+  p->h_ncb = (int)((c.n + p->pl.h_bn - 1) / p->pl.h_bn);
+  int64_t max_split = std::min<int64_t>(64, (c.m + 127) / 128);
+  const size_t cd_one = (size_t)2 * kp * p->ldh * p->sz;
+  while (max_split > 1 && cd_one * (size_t)max_split > ((size_t)2 << 30)) --max_split;
+  p->h_nsplit = choose_split(p->h_ncb, max_split);
+  p->h_rows_per_split = ((c.m + p->h_nsplit - 1) / p->h_nsplit + 31) / 32 * 32;
+  p->h_nsplit = (int)((c.m + p->h_rows_per_split - 1) / p->h_rows_per_split);
+  // W pass: row blocks x column splits
+  const int64_t nrb = (c.m + p->pl.w_bmr - 1) / p->pl.w_bmr;
+  p->w_nsplit = choose_split(nrb, std::min<int64_t>(32, (c.n + 127) / 128));
+  p->w_cols_per_split = ((c.n + p->w_nsplit - 1) / p->w_nsplit + 127) / 128 * 128;
+  p->w_nsplit = (int)((c.n + p->w_cols_per_split - 1) / p->w_cols_per_split);
+  p->n_prior = h_epilogue_blocks(c.n, kp);
+
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  p->oW = take((size_t)c.m * kp * p->sz);
+  p->oH = take((size_t)kp * p->ldh * p->sz);
+  p->oHt = take((size_t)p->ldh * kp * p->sz);
+  p->oCDpart = take(cd_one * p->h_nsplit);
+  p->oCDsum = take(cd_one);
+  p->oLLpart = take((size_t)p->h_nsplit * p->h_ncb * 8);
+  p->oLLsum = take(64);
+  p->oPrior = take((size_t)p->n_prior * 16);
+  p->oG = take((size_t)p->w_nsplit * c.m * kp * p->sz);
+  p->oQ = take((size_t)p->w_nsplit * c.m * p->sz);
+  p->oRowcount = take((size_t)c.m * p->sz);
+  p->oHist = take((size_t)(std::max(c.max_iter_cap, 1) + 2) * 8);
+  p->oState = take(sizeof(FitState));
+  p->oLoss = take(64);
+  p->total = o;
+  return NBMF_OK;
+}
+
+// ------------------------------------------------------------------------------------ small API
+extern "C" int nbmf_version(void) { return 100; }
+extern "C" const char* nbmf_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t nbmf_words_per_row(int64_t n) { return (n + 1023) / 1024 * 32; }
+extern "C" int64_t nbmf_padded_cols(int64_t n) { return nbmf_words_per_row(n) * 32; }
+extern "C" int64_t nbmf_launch_count(int reset) {
+  const long long v = g_launches.load();
+  if (reset) g_launches = 0;
+  return v;
+}
+extern "C" int nbmf_variant_info(int dtype, int vkind, int k, int32_t* h_cols, int32_t* w_rows, int32_t* kp) {
+  PassLaunch pl;
+  if (!lookup_pass(dtype, vkind == NBMF_V_DENSE, 0, k, &pl)) return fail(NBMF_ERR_UNSUPPORTED, "no variant");
+  if (h_cols) *h_cols = pl.h_bn;
+  if (w_rows) *w_rows = pl.w_bmr;
+  if (kp) *kp = pl.kp;
+  return NBMF_OK;
+}
+
+// ------------------------------------------------------------------------------------ data layer
+extern "C" int nbmf_pack_bits(const void* x, int xdt, int64_t ldx, const void* mask, int mdt, int64_t ldm, int64_t m,
+                              int64_t n, uint32_t* P, uint32_t* M, void* stream) {
+  if (!x || !P || m < 1 || n < 1) return fail(NBMF_ERR_ARG, "nbmf_pack_bits: bad arguments");
+  launch_pack_bits(xdt, x, ldx, mask, mdt, ldm, m, n, nbmf_words_per_row(n), P, M, (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+extern "C" int nbmf_pack_dense(const void* x, int xdt, int64_t ldx, const void* mask, int mdt, int64_t ldm, int64_t m,
+                               int64_t n, int out_dtype, void* vm, void* stream) {
+  if (!x || !vm || m < 1 || n < 1) return fail(NBMF_ERR_ARG, "nbmf_pack_dense: bad arguments");
+  launch_pack_dense(xdt, x, ldx, mask, mdt, ldm, m, n, out_dtype, nbmf_padded_cols(n), vm, (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+extern "C" int nbmf_transpose_bits(const uint32_t* src, int64_t m, int64_t n, uint32_t* dst, void* stream) {
+  if (!src || !dst || m < 1 || n < 1) return fail(NBMF_ERR_ARG, "nbmf_transpose_bits: bad arguments");
+  launch_transpose_bits(src, m, n, nbmf_words_per_row(n), dst, nbmf_words_per_row(m), (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+extern "C" int nbmf_popcount_bits(const uint32_t* bits, int64_t m, int64_t n, uint64_t* scratch, uint64_t* count_host,
+                                  void* stream) {
+  if (!bits || !scratch || !count_host) return fail(NBMF_ERR_ARG, "nbmf_popcount_bits: bad arguments");
+  launch_popcount(bits, m, nbmf_words_per_row(n), (unsigned long long*)scratch, (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  CUDA_TRY(cudaMemcpyAsync(count_host, scratch, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return NBMF_OK;
+}
+extern "C" int nbmf_synth_bits(uint64_t seed, int64_t row0, int64_t m, int64_t n, const float* hstar, int32_t kstar,
+                               float obs_frac, uint32_t* P, uint32_t* M, void* stream) {
+  if (!hstar || !P || kstar < 1 || kstar > 32) return fail(NBMF_ERR_ARG, "nbmf_synth_bits: bad arguments (kstar in 1..32)");
+  launch_synth_bits(seed, row0, m, n, nbmf_words_per_row(n), nullptr, hstar, kstar, obs_frac, P, M, (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+
+// ------------------------------------------------------------------------------------ context
+extern "C" int64_t nbmf_workspace_bytes(const nbmf_config* cfg) {
+  Plan p;
+  if (!cfg) { fail(NBMF_ERR_ARG, "null config"); return -1; }
+  if (make_plan(*cfg, &p) != NBMF_OK) return -1;
+  return (int64_t)p.total;
+}
+
+__global__ void reset_state_kernel(FitState* s) {
+  s->done = 0; s->it = 0; s->n_hist = 0; s->converged = 0;
+  s->prev_loss = INFINITY; s->prior_a = 0.0; s->prior_b = 0.0;
+}
+
+extern "C" int nbmf_create(const nbmf_config* cfg, void* ws, int64_t ws_bytes, void* stream, nbmf_ctx** out) {
+  if (!cfg || !ws || !out) return fail(NBMF_ERR_ARG, "nbmf_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(NBMF_ERR_CUDA, "no CUDA device: libnbmf_b200 has no CPU fallback");
+  nbmf_ctx* c = new nbmf_ctx();
+  c->cfg = *cfg;
+  int rc = make_plan(*cfg, &c->p);
+  if (rc != NBMF_OK) { delete c; return rc; }
+  if ((size_t)ws_bytes < c->p.total) { delete c; return fail(NBMF_ERR_ARG, "workspace too small"); }
+  if ((uintptr_t)ws % 256) { delete c; return fail(NBMF_ERR_ARG, "workspace must be 256-byte aligned"); }
+  c->ws = (unsigned char*)ws;
+  c->st = (cudaStream_t)stream;
+  cudaError_t e = cudaMallocHost((void**)&c->host_state, sizeof(FitState));
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMallocHost"); }
+  e = cudaEventCreateWithFlags(&c->poll_ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) { cudaFreeHost(c->host_state); delete c; return cuda_fail(e, "cudaEventCreate"); }
+  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state());
+  g_launches += 1;
+  *out = c;
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_destroy(nbmf_ctx* c) {
+  if (!c) return NBMF_OK;
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  prof_clear(c->prof_h);
+  prof_clear(c->prof_w);
+  if (c->poll_ev) cudaEventDestroy(c->poll_ev);
+  if (c->host_state) cudaFreeHost(c->host_state);
+  delete c;
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t* M) {
+  if (!c || !P) return fail(NBMF_ERR_ARG, "nbmf_set_data_bits: null argument");
+  if (c->cfg.vkind != NBMF_V_BITS) return fail(NBMF_ERR_ARG, "context was created for dense V");
+  if (c->cfg.has_mask && !M) return fail(NBMF_ERR_ARG, "has_mask is set but no mask plane given");
+  c->P = P;
+  c->M = c->cfg.has_mask ? M : nullptr;
+  c->rowcount_ready = false;
+  return NBMF_OK;
+}
+extern "C" int nbmf_set_data_dense(nbmf_ctx* c, const void* Vm, const uint32_t* M) {
+  if (!c || !Vm) return fail(NBMF_ERR_ARG, "nbmf_set_data_dense: null argument");
+  if (c->cfg.vkind != NBMF_V_DENSE) return fail(NBMF_ERR_ARG, "context was created for bit-packed V");
+  if (c->cfg.has_mask && !M) return fail(NBMF_ERR_ARG, "has_mask is set but no mask plane given");
+  c->Vm = Vm;
+  c->M = c->cfg.has_mask ? M : nullptr;
+  c->rowcount_ready = false;
+  return NBMF_OK;
+}
+
+static int require_data(nbmf_ctx* c) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  if (c->cfg.vkind == NBMF_V_BITS ? !c->P : !c->Vm) return fail(NBMF_ERR_ARG, "no data planes set");
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_set_factors(nbmf_ctx* c, const void* w, const void* h, int normalize_w) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  launch_init_factors(c->cfg.dtype, w, h, c->cfg.m, c->cfg.n, c->cfg.k, c->p.pl.kp, c->p.ldh, c->W(), c->H(), c->Ht(),
+                      normalize_w, c->st);
+  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state());
+  CHECK_LAUNCH((w ? 1 : 0) + (h ? 1 : 0) + 1);
+  c->enqueued = 0;
+  c->tail_enqueued = false;
+  return NBMF_OK;
+}
+extern "C" int nbmf_get_factors(nbmf_ctx* c, void* w, void* h) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  launch_export_factors(c->cfg.dtype, c->W(), c->H(), c->cfg.m, c->cfg.n, c->cfg.k, c->p.pl.kp, c->p.ldh, w, h, c->st);
+  CHECK_LAUNCH((w ? 1 : 0) + (h ? 1 : 0));
+  return NBMF_OK;
+}
+
+// ------------------------------------------------------------------------------------ steps
+static int allreduce(nbmf_ctx* c, bool with_cd) {
+  if (c->world <= 1) return NBMF_OK;
+  const size_t count = (size_t)2 * c->p.pl.kp * c->p.ldh;
+  int rc = g_nccl.GroupStart();
+  if (rc) return nccl_fail(rc, "ncclGroupStart");
+  if (with_cd) {
+    void* cd = c->ws + c->p.oCDsum;
+    rc = g_nccl.AllReduce(cd, cd, count, c->cfg.dtype == NBMF_F32 ? kNcclFloat32 : kNcclFloat64, kNcclSum, c->comm, c->st);
+    if (rc) return nccl_fail(rc, "ncclAllReduce(C|D)");
+  }
+  void* ll = c->ws + c->p.oLLsum;
+  rc = g_nccl.AllReduce(ll, ll, 1, kNcclFloat64, kNcclSum, c->comm, c->st);
+  if (rc) return nccl_fail(rc, "ncclAllReduce(LL)");
+  rc = g_nccl.GroupEnd();
+  if (rc) return nccl_fail(rc, "ncclGroupEnd");
+  return NBMF_OK;
+}
+
+static void prof_mark(nbmf_ctx* c, std::vector<cudaEvent_t>& v) {
+  if (!c->profile) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, c->st);
+  v.push_back(e);
+}
+
+static int enqueue_h_pass(nbmf_ctx* c, int compute_cd) {
+  const Plan& p = c->p;
+  HPassArgs a;
+  a.W = c->W(); a.H = c->H(); a.P = c->P; a.M = c->M; a.Vm = c->Vm; a.ldv = p.ldh;
+  a.m = c->cfg.m; a.n = c->cfg.n; a.ldh = p.ldh; a.wpr = p.wpr;
+  a.rows_per_split = p.h_rows_per_split;
+  a.CD = c->ws + p.oCDpart; a.LL = c->at<double>(p.oLLpart);
+  a.eps = c->cfg.eps; a.done = &c->state()->done; a.compute_cd = compute_cd;
+  prof_mark(c, c->prof_h);
+  p.pl.h_launch(a, p.h_nsplit, c->st);
+  prof_mark(c, c->prof_h);
+  const int64_t count = compute_cd ? (int64_t)2 * p.pl.kp * p.ldh : 0;
+  launch_h_reduce(c->cfg.dtype, c->ws + p.oCDpart, p.h_nsplit, count, c->ws + p.oCDsum, c->at<double>(p.oLLpart),
+                  (int64_t)p.h_nsplit * p.h_ncb, c->at<double>(p.oLLsum), c->state(), c->st);
+  CHECK_LAUNCH(2);
+  return allreduce(c, compute_cd != 0);
+}
+
+static int enqueue_h_epilogue(nbmf_ctx* c) {
+  const Plan& p = c->p;
+  launch_h_epilogue(c->cfg.dtype, c->ws + p.oCDsum, c->cfg.n, c->cfg.k, p.pl.kp, p.ldh, c->cfg.alpha, c->cfg.beta,
+                    c->cfg.eps, c->H(), c->Ht(), c->at<double>(p.oPrior), c->state(), c->st);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+
+static int enqueue_w_step(nbmf_ctx* c) {
+  const Plan& p = c->p;
+  if (c->cfg.projection == NBMF_PROJ_DUCHI && c->M && !c->rowcount_ready) {
+    launch_rowcount(c->cfg.dtype, c->M, c->cfg.m, c->cfg.n, p.wpr, c->ws + p.oRowcount, c->st);
+    CHECK_LAUNCH(1);
+    c->rowcount_ready = true;
+  }
+  WPassArgs a;
+  a.W = c->W(); a.Ht = c->Ht(); a.P = c->P; a.M = c->M; a.Vm = c->Vm; a.ldv = p.ldh;
+  a.m = c->cfg.m; a.n = c->cfg.n; a.ldh = p.ldh; a.wpr = p.wpr;
+  a.cols_per_split = p.w_cols_per_split;
+  a.G = c->ws + p.oG; a.Q = c->ws + p.oQ; a.eps = c->cfg.eps; a.done = &c->state()->done;
+  prof_mark(c, c->prof_w);
+  p.pl.w_launch(a, p.w_nsplit, c->st);
+  prof_mark(c, c->prof_w);
+  const void* rowcount = (c->cfg.projection == NBMF_PROJ_DUCHI && c->M) ? (const void*)(c->ws + p.oRowcount) : nullptr;
+  launch_w_epilogue(c->cfg.dtype, c->ws + p.oG, c->ws + p.oQ, p.w_nsplit, c->cfg.m, c->cfg.n, c->cfg.k, p.pl.kp,
+                    c->cfg.projection, rowcount, c->W(), c->state(), c->st);
+  CHECK_LAUNCH(2);
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_h_half_step(nbmf_ctx* c) {
+  int rc = require_data(c);
+  if (rc) return rc;
+  if ((rc = enqueue_h_pass(c, 1))) return rc;
+  return enqueue_h_epilogue(c);
+}
+extern "C" int nbmf_w_half_step(nbmf_ctx* c) {
+  int rc = require_data(c);
+  if (rc) return rc;
+  return enqueue_w_step(c);
+}
+
+__global__ void objective_kernel(const double* __restrict__ LLsum, const double* __restrict__ prior_part, int n_part,
+                                 double alpha, double beta, double n_obs, double* __restrict__ out) {
+  double pa = 0.0, pb = 0.0;
+  for (int i = threadIdx.x; i < n_part; i += 32) { pa += prior_part[2 * i]; pb += prior_part[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pa += __shfl_xor_sync(0xffffffffu, pa, o);
+    pb += __shfl_xor_sync(0xffffffffu, pb, o);
+  }
+  if (threadIdx.x == 0) out[0] = -(LLsum[0] + (alpha - 1.0) * pa + (beta - 1.0) * pb) / n_obs;
+}
+
+extern "C" int nbmf_objective(nbmf_ctx* c, double* loss_host) {
+  int rc = require_data(c);
+  if (rc) return rc;
+  if (!loss_host) return fail(NBMF_ERR_ARG, "null output");
+  const Plan& p = c->p;
+  if ((rc = enqueue_h_pass(c, 0))) return rc;
+  launch_prior_sums(c->cfg.dtype, c->H(), c->cfg.n, c->cfg.k, p.pl.kp, p.ldh, c->cfg.eps, c->at<double>(p.oPrior), c->st);
+  objective_kernel<<<1, 32, 0, c->st>>>(c->at<double>(p.oLLsum), c->at<double>(p.oPrior), p.n_prior, c->cfg.alpha,
+                                        c->cfg.beta, c->cfg.n_obs, c->at<double>(p.oLoss));
+  CHECK_LAUNCH(2);
+  CUDA_TRY(cudaMemcpyAsync(loss_host, c->at<double>(p.oLoss), 8, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  return NBMF_OK;
+}
+
+// ------------------------------------------------------------------------------------ fit loop
+extern "C" int nbmf_fit_begin(nbmf_ctx* c, int32_t max_iter, double tol) {
+  int rc = require_data(c);
+  if (rc) return rc;
+  if (max_iter < 1) return fail(NBMF_ERR_ARG, "max_iter must be >= 1");
+  if (max_iter > c->cfg.max_iter_cap) return fail(NBMF_ERR_ARG, "max_iter exceeds cfg.max_iter_cap");
+  c->max_iter = max_iter;
+  c->tol = tol;
+  c->enqueued = 0;
+  c->tail_enqueued = false;
+  c->poll_pending = false;
+  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state());
+  // prior sums of the initial H are not needed for any recorded loss, but keep the buffer defined
+  launch_prior_sums(c->cfg.dtype, c->H(), c->cfg.n, c->cfg.k, c->p.pl.kp, c->p.ldh, c->cfg.eps,
+                    c->at<double>(c->p.oPrior), c->st);
+  CHECK_LAUNCH(2);
+  return NBMF_OK;
+}
+
+static int enqueue_finalize(nbmf_ctx* c) {
+  const Plan& p = c->p;
+  launch_finalize(c->state(), c->at<double>(p.oLLsum), c->at<double>(p.oPrior), p.n_prior, c->cfg.alpha, c->cfg.beta,
+                  c->cfg.n_obs, c->tol, c->max_iter, c->at<double>(p.oHist), c->st);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_fit_enqueue(nbmf_ctx* c, int32_t n_iters) {
+  if (!c || c->max_iter < 1) return fail(NBMF_ERR_ARG, "nbmf_fit_begin was not called");
+  int rc;
+  for (int i = 0; i < n_iters && c->enqueued < c->max_iter; ++i) {
+    // H pass on (W_t, H_t): partial C, D and the log-likelihood of iteration t-1's factors
+    if ((rc = enqueue_h_pass(c, 1))) return rc;
+    if ((rc = enqueue_finalize(c))) return rc;        // loss_{t-1}, stop rule; may set done
+    if ((rc = enqueue_h_epilogue(c))) return rc;      // H_{t+1}
+    if ((rc = enqueue_w_step(c))) return rc;          // W_{t+1} from H_{t+1}
+    c->enqueued += 1;
+  }
+  if (c->enqueued >= c->max_iter && !c->tail_enqueued) {
+    // loss of the last iteration: one loss-only pass
+    if ((rc = enqueue_h_pass(c, 0))) return rc;
+    if ((rc = enqueue_finalize(c))) return rc;
+    c->tail_enqueued = true;
+  }
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_fit_poll(nbmf_ctx* c, int wait, int32_t* done_host, int32_t* n_iter_host) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  if (!c->poll_pending) {
+    CUDA_TRY(cudaMemcpyAsync(c->host_state, c->state(), sizeof(FitState), cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(cudaEventRecord(c->poll_ev, c->st));
+    c->poll_pending = true;
+  }
+  if (wait) {
+    CUDA_TRY(cudaEventSynchronize(c->poll_ev));
+  } else {
+    cudaError_t e = cudaEventQuery(c->poll_ev);
+    if (e == cudaErrorNotReady) {
+      if (done_host) *done_host = -1;            // snapshot not ready yet
+      return NBMF_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventQuery");
+  }
+  c->poll_pending = false;
+  if (done_host) *done_host = c->host_state->done;
+  if (n_iter_host) *n_iter_host = c->host_state->n_hist;
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_fit_history(nbmf_ctx* c, double* history_host, int32_t count, int32_t* converged_host) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  if (count > 0 && history_host)
+    CUDA_TRY(cudaMemcpyAsync(history_host, c->at<double>(c->p.oHist), (size_t)count * 8, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaMemcpyAsync(c->host_state, c->state(), sizeof(FitState), cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  if (converged_host) *converged_host = c->host_state->converged;
+  return NBMF_OK;
+}
+
+extern "C" int nbmf_fit(nbmf_ctx* c, int32_t max_iter, double tol, double* history_host, int32_t* n_iter_host,
+                        int32_t* converged_host) {
+  int rc = nbmf_fit_begin(c, max_iter, tol);
+  if (rc) return rc;
+  int chunk = 8;
+  int32_t done = 0, n_iter = 0;
+  // keep one chunk in flight beyond the one being waited on; converged iterations are no-ops
+  if ((rc = nbmf_fit_enqueue(c, chunk))) return rc;
+  while (true) {
+    CUDA_TRY(cudaMemcpyAsync(c->host_state, c->state(), sizeof(FitState), cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(cudaEventRecord(c->poll_ev, c->st));
+    const bool all_enqueued = c->tail_enqueued;
+    if (!all_enqueued) {
+      chunk = std::min(chunk * 2, 64);
+      if ((rc = nbmf_fit_enqueue(c, chunk))) return rc;
+    }
+    CUDA_TRY(cudaEventSynchronize(c->poll_ev));
+    done = c->host_state->done;
+    n_iter = c->host_state->n_hist;
+    if (done || all_enqueued) break;
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  CUDA_TRY(cudaMemcpy(c->host_state, c->state(), sizeof(FitState), cudaMemcpyDeviceToHost));
+  n_iter = c->host_state->n_hist;
+  if (n_iter_host) *n_iter_host = n_iter;
+  return nbmf_fit_history(c, history_host, n_iter, converged_host);
+}
+
+// ------------------------------------------------------------------------------------ transform
+extern "C" int nbmf_transform(nbmf_ctx* c, int32_t n_steps) {
+  int rc = require_data(c);
+  if (rc) return rc;
+  for (int i = 0; i < n_steps; ++i)
+    if ((rc = enqueue_w_step(c))) return rc;
+  launch_clip_rows(c->cfg.dtype, c->W(), c->cfg.m, c->cfg.k, c->p.pl.kp, 1e-8, 1.0, c->st);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+
+// ------------------------------------------------------------------------------------ comm
+extern "C" int nbmf_comm_unique_id(void* id128) {
+  if (!id128) return fail(NBMF_ERR_ARG, "null id buffer");
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclId id;
+  rc = g_nccl.GetUniqueId(&id);
+  if (rc) return nccl_fail(rc, "ncclGetUniqueId");
+  memcpy(id128, &id, 128);
+  return NBMF_OK;
+}
+extern "C" int nbmf_comm_init(nbmf_ctx* c, const void* id128, int32_t rank, int32_t world) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(NBMF_ERR_ARG, "nbmf_comm_init: bad arguments");
+  if (world == 1) { c->world = 1; c->rank = 0; return NBMF_OK; }
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclId id;
+  memcpy(&id, id128, 128);
+  rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
+  if (rc) return nccl_fail(rc, "ncclCommInitRank");
+  c->world = world;
+  c->rank = rank;
+  return NBMF_OK;
+}
+extern "C" int nbmf_comm_world(nbmf_ctx* c) { return c ? c->world : 0; }
+
+// ------------------------------------------------------------------------------------ measurement
+static void prof_clear(std::vector<cudaEvent_t>& v) {
+  for (cudaEvent_t e : v) cudaEventDestroy(e);
+  v.clear();
+}
+static void prof_sum(std::vector<cudaEvent_t>& v, double* ms, int32_t* count) {
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, v[i], v[i + 1]) == cudaSuccess) { tot += t; ++n; }
+  }
+  if (ms) *ms = tot;
+  if (count) *count = n;
+}
+extern "C" int nbmf_profile_enable(nbmf_ctx* c, int enable) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  prof_clear(c->prof_h);
+  prof_clear(c->prof_w);
+  c->profile = enable != 0;
+  return NBMF_OK;
+}
+extern "C" int nbmf_profile_read(nbmf_ctx* c, double* h_ms, int32_t* h_count, double* w_ms, int32_t* w_count) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  prof_sum(c->prof_h, h_ms, h_count);
+  prof_sum(c->prof_w, w_ms, w_count);
+  return NBMF_OK;
+}
+extern "C" int nbmf_plan_info(nbmf_ctx* c, int32_t* h_col_blocks, int32_t* h_row_splits, int32_t* w_row_blocks,
+                              int32_t* w_col_splits) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  if (h_col_blocks) *h_col_blocks = c->p.h_ncb;
+  if (h_row_splits) *h_row_splits = c->p.h_nsplit;
+  if (w_row_blocks) *w_row_blocks = (int32_t)((c->cfg.m + c->p.pl.w_bmr - 1) / c->p.pl.w_bmr);
+  if (w_col_splits) *w_col_splits = c->p.w_nsplit;
+  return NBMF_OK;
+}
+extern "C" int nbmf_fma_peak(int dtype, int32_t iters, void* scratch, void* stream, double* tflops_host) {
+  if (!scratch || !tflops_host || iters < 1) return fail(NBMF_ERR_ARG, "nbmf_fma_peak: bad arguments");
+  *tflops_host = run_fma_peak(dtype, iters, (cudaStream_t)stream, (float*)scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "nbmf_fma_peak");
+  return NBMF_OK;
+}

@@ -1,0 +1,59 @@
+// Internal C++ interface between the C-ABI (capi.cu), the pass instantiations and the
+// small epilogue / data-layer kernels.  Nothing here is exported.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "args.h"
+
+namespace nbmf {
+
+// ---- per-fit device state (one struct in device memory; read by every kernel)
+struct FitState {
+  int done;            // 1 = stop (converged or max_iter reached); kernels become no-ops
+  int it;              // number of H passes finalised so far == MM iterations started
+  int n_hist;          // number of losses recorded (== n_iter_ when done)
+  int converged;       // 1 = stopped by the tolerance rule
+  double prev_loss;    // loss of the previous iteration (inf before the first)
+  double prior_a;      // sum log(H + eps) of the current H
+  double prior_b;      // sum log((1 - H) + eps) of the current H
+};
+
+// ---- variant lookup: dtype 0 = f32, 1 = f64; returns false if K is unsupported
+bool lookup_pass(int dtype, int dense, int strict, int k, PassLaunch* out);
+
+// ---- epilogues and small reductions (misc_kernels.cu); dtype as above
+void launch_init_factors(int dtype, const void* W_in, const void* H_in, int64_t m, int64_t n, int k, int kp,
+                         int64_t ldh, void* W, void* H, void* Ht, int normalize_w, cudaStream_t st);
+void launch_export_factors(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, int kp,
+                           int64_t ldh, void* W_out, void* H_out, cudaStream_t st);
+void launch_h_reduce(int dtype, const void* CDpart, int nsplit, int64_t count, void* CDsum,
+                     const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, cudaStream_t st);
+void launch_finalize(FitState* state, const double* LLsum, const double* prior_part, int n_prior_part,
+                     double alpha, double beta, double n_obs, double tol, int max_iter, double* history,
+                     cudaStream_t st);
+int  h_epilogue_blocks(int64_t n, int kp);
+void launch_h_epilogue(int dtype, const void* CDsum, int64_t n, int k, int kp, int64_t ldh, double alpha,
+                       double beta, double eps, void* H, void* Ht, double* prior_part, const FitState* state,
+                       cudaStream_t st);
+void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64_t ldh, double eps,
+                       double* prior_part, cudaStream_t st);
+void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nsplit, int64_t m, int64_t n,
+                       int k, int kp, int projection, const void* rowcount, void* W, const FitState* state,
+                       cudaStream_t st);
+void launch_clip_rows(int dtype, void* W, int64_t m, int k, int kp, double lo, double hi, cudaStream_t st);
+
+// ---- data layer
+void launch_pack_bits(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
+                      int64_t m, int64_t n, int64_t wpr, uint32_t* P, uint32_t* M, cudaStream_t st);
+void launch_pack_dense(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
+                       int64_t m, int64_t n, int out_dtype, int64_t ldv, void* Vm, cudaStream_t st);
+void launch_transpose_bits(const uint32_t* src, int64_t m, int64_t n, int64_t wpr_src, uint32_t* dst,
+                           int64_t wpr_dst, cudaStream_t st);
+void launch_rowcount(int dtype, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, void* out, cudaStream_t st);
+void launch_popcount(const uint32_t* B, int64_t m, int64_t wpr, unsigned long long* out, cudaStream_t st);
+void launch_synth_bits(uint64_t seed, int64_t row0, int64_t m, int64_t n, int64_t wpr, const float* Wstar,
+                       const float* Hstar, int kstar, float obs_frac, uint32_t* P, uint32_t* M, cudaStream_t st);
+double run_fma_peak(int dtype, int iters, cudaStream_t st, float* scratch);
+
+}  // namespace nbmf

@@ -1,0 +1,521 @@
+// Epilogue, reduction and data-layer kernels around the two pass kernels.
+// Reference arithmetic: src/nbmf_mm/_solver.py (line numbers cited per kernel).
+#include <math.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace nbmf {
+
+// ------------------------------------------------------------------------------------
+// factor import / export (host layout: W (m x k) row-major, H (k x n) row-major)
+// ------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void init_w_kernel(const Real* __restrict__ Win, int64_t m, int k, int kp, Real* __restrict__ W,
+                              int normalize) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  Real s = Real(0);
+  for (int kk = 0; kk < k; ++kk) s += Win[row * k + kk];           // _solver.py:136  W / W.sum(axis=0)
+  for (int kk = 0; kk < kp; ++kk) {
+    Real v = Real(0);
+    if (kk < k) v = normalize ? Win[row * k + kk] / s : Win[row * k + kk];
+    W[row * kp + kk] = v;
+  }
+}
+
+template <typename Real>
+__global__ void init_h_kernel(const Real* __restrict__ Hin, int64_t n, int k, int kp, int64_t ldh,
+                              Real* __restrict__ H, Real* __restrict__ Ht) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kk = blockIdx.y;
+  if (j >= ldh) return;
+  const Real v = (kk < k && j < n) ? Hin[(int64_t)kk * n + j] : Real(0.5);
+  H[(int64_t)kk * ldh + j] = v;
+  Ht[j * kp + kk] = v;
+}
+
+template <typename Real>
+__global__ void export_w_kernel(const Real* __restrict__ W, int64_t m, int k, int kp, Real* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m * k) return;
+  out[e] = W[(e / k) * kp + (e % k)];
+}
+template <typename Real>
+__global__ void export_h_kernel(const Real* __restrict__ H, int64_t n, int k, int64_t ldh, Real* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * k) return;
+  out[e] = H[(e / n) * ldh + (e % n)];
+}
+
+void launch_init_factors(int dtype, const void* W_in, const void* H_in, int64_t m, int64_t n, int k, int kp,
+                         int64_t ldh, void* W, void* H, void* Ht, int normalize_w, cudaStream_t st) {
+  const unsigned gw = (unsigned)((m + 255) / 256);
+  dim3 gh((unsigned)((ldh + 255) / 256), (unsigned)kp);
+  if (dtype == 0) {
+    if (W_in) init_w_kernel<float><<<gw, 256, 0, st>>>((const float*)W_in, m, k, kp, (float*)W, normalize_w);
+    if (H_in) init_h_kernel<float><<<gh, 256, 0, st>>>((const float*)H_in, n, k, kp, ldh, (float*)H, (float*)Ht);
+  } else {
+    if (W_in) init_w_kernel<double><<<gw, 256, 0, st>>>((const double*)W_in, m, k, kp, (double*)W, normalize_w);
+    if (H_in) init_h_kernel<double><<<gh, 256, 0, st>>>((const double*)H_in, n, k, kp, ldh, (double*)H, (double*)Ht);
+  }
+}
+
+void launch_export_factors(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, int kp,
+                           int64_t ldh, void* W_out, void* H_out, cudaStream_t st) {
+  const unsigned gw = (unsigned)((m * k + 255) / 256), gh = (unsigned)((n * k + 255) / 256);
+  if (dtype == 0) {
+    if (W_out) export_w_kernel<float><<<gw, 256, 0, st>>>((const float*)W, m, k, kp, (float*)W_out);
+    if (H_out) export_h_kernel<float><<<gh, 256, 0, st>>>((const float*)H, n, k, ldh, (float*)H_out);
+  } else {
+    if (W_out) export_w_kernel<double><<<gw, 256, 0, st>>>((const double*)W, m, k, kp, (double*)W_out);
+    if (H_out) export_h_kernel<double><<<gh, 256, 0, st>>>((const double*)H, n, k, ldh, (double*)H_out);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// deterministic reduction of the row-split partials of the H pass (fixed split order)
+// ------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void h_reduce_kernel(const Real* __restrict__ part, int nsplit, int64_t count, Real* __restrict__ sum,
+                                const double* __restrict__ LLpart, int64_t n_ll, double* __restrict__ LLsum,
+                                const FitState* __restrict__ state) {
+  if (state->done) return;
+  if (blockIdx.x == gridDim.x - 1) {            // last block: the log-likelihood partials
+    if (threadIdx.x < 32) {
+      double v = 0.0;
+      for (int64_t i = threadIdx.x; i < n_ll; i += 32) v += LLpart[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) LLsum[0] = v;
+    }
+    return;
+  }
+  const int64_t stride = (int64_t)(gridDim.x - 1) * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
+    Real v = part[e];
+    for (int s = 1; s < nsplit; ++s) v += part[(int64_t)s * count + e];
+    sum[e] = v;
+  }
+}
+
+void launch_h_reduce(int dtype, const void* CDpart, int nsplit, int64_t count, void* CDsum,
+                     const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, cudaStream_t st) {
+  int64_t nb = (count + 1023) / 1024;
+  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb < 1) nb = 1;
+  const unsigned grid = (unsigned)nb + 1;
+  if (dtype == 0)
+    h_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)CDpart, nsplit, count, (float*)CDsum, LLpart, n_ll, LLsum, state);
+  else
+    h_reduce_kernel<double><<<grid, 256, 0, st>>>((const double*)CDpart, nsplit, count, (double*)CDsum, LLpart, n_ll, LLsum, state);
+}
+
+// ------------------------------------------------------------------------------------
+// loss of the previous iteration + stop rule, on the device (_solver.py:158-175).
+// The H pass of iteration `it` sees (W_it, H_it), i.e. the factors PRODUCED by iteration
+// it-1, so its log-likelihood is the loss of iteration it-1.
+// ------------------------------------------------------------------------------------
+__global__ void finalize_kernel(FitState* state, const double* __restrict__ LLsum,
+                                const double* __restrict__ prior_part, int n_prior_part, double alpha, double beta,
+                                double n_obs, double tol, int max_iter, double* __restrict__ history) {
+  if (state->done) return;
+  double pa = 0.0, pb = 0.0;
+  for (int i = threadIdx.x; i < n_prior_part; i += 32) {
+    pa += prior_part[2 * i];
+    pb += prior_part[2 * i + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pa += __shfl_xor_sync(0xffffffffu, pa, o);
+    pb += __shfl_xor_sync(0xffffffffu, pb, o);
+  }
+  if (threadIdx.x != 0) return;
+  const int it = state->it;
+  int done = 0;
+  if (it >= 1) {
+    const double loss = -(LLsum[0] + (alpha - 1.0) * pa + (beta - 1.0) * pb) / n_obs;
+    history[it - 1] = loss;
+    state->n_hist = it;
+    if (it >= 2) {
+      const double prev = state->prev_loss;
+      const double rel = fabs(prev - loss) / fabs(prev);
+      if (rel < tol) { done = 1; state->converged = 1; }
+    }
+    state->prev_loss = loss;
+    if (it >= max_iter) done = 1;
+  }
+  state->prior_a = pa;
+  state->prior_b = pb;
+  if (done) state->done = 1;
+  else state->it = it + 1;
+}
+
+void launch_finalize(FitState* state, const double* LLsum, const double* prior_part, int n_prior_part,
+                     double alpha, double beta, double n_obs, double tol, int max_iter, double* history,
+                     cudaStream_t st) {
+  finalize_kernel<<<1, 32, 0, st>>>(state, LLsum, prior_part, n_prior_part, alpha, beta, n_obs, tol, max_iter, history);
+}
+
+// ------------------------------------------------------------------------------------
+// H epilogue: Beta-prior ratio + clip (_solver.py:42-47), writes H, Ht and the per-block
+// partial sums of log(H+eps), log((1-H)+eps) for the loss prior term (_solver.py:158-159).
+// ------------------------------------------------------------------------------------
+constexpr int HEPI_NT = 256;
+int h_epilogue_blocks(int64_t n, int kp) { return (int)((n + HEPI_NT - 1) / HEPI_NT) * kp; }
+
+template <typename Real, bool UPDATE>
+__global__ void h_epilogue_kernel(const Real* __restrict__ CD, int64_t n, int k, int kp, int64_t ldh, double alpha,
+                                  double beta, double eps_d, Real* __restrict__ H, Real* __restrict__ Ht,
+                                  double* __restrict__ prior_part, const FitState* __restrict__ state) {
+  __shared__ double scratch[HEPI_NT / 32];
+  if (UPDATE && state->done) return;
+  const int64_t j = (int64_t)blockIdx.x * HEPI_NT + threadIdx.x;
+  const int kk = blockIdx.y;
+  double la = 0.0, lb = 0.0;
+  if (kk < k && j < n) {
+    const int64_t o = (int64_t)kk * ldh + j;
+    Real hn = H[o];
+    if (UPDATE) {
+      const Real eps = (Real)eps_d;
+      const Real h = hn;
+      const Real num = h * CD[o] + (Real)(alpha - 1.0);
+      const Real den = (Real(1) - h) * CD[(int64_t)kp * ldh + o] + (Real)(beta - 1.0);
+      hn = num / (num + den + eps);
+      hn = fmin(fmax(hn, eps), Real(1) - eps);
+      H[o] = hn;
+      Ht[j * kp + kk] = hn;
+    }
+    la = log((double)(hn + (Real)eps_d));
+    lb = log((double)((Real(1) - hn) + (Real)eps_d));
+  }
+  const double sa = block_sum<HEPI_NT>(la, scratch);
+  const double sb = block_sum<HEPI_NT>(lb, scratch);
+  if (threadIdx.x == 0) {
+    const int64_t b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    prior_part[2 * b] = sa;
+    prior_part[2 * b + 1] = sb;
+  }
+}
+
+void launch_h_epilogue(int dtype, const void* CDsum, int64_t n, int k, int kp, int64_t ldh, double alpha,
+                       double beta, double eps, void* H, void* Ht, double* prior_part, const FitState* state,
+                       cudaStream_t st) {
+  dim3 grid((unsigned)((n + HEPI_NT - 1) / HEPI_NT), (unsigned)kp);
+  if (dtype == 0)
+    h_epilogue_kernel<float, true><<<grid, HEPI_NT, 0, st>>>((const float*)CDsum, n, k, kp, ldh, alpha, beta, eps, (float*)H, (float*)Ht, prior_part, state);
+  else
+    h_epilogue_kernel<double, true><<<grid, HEPI_NT, 0, st>>>((const double*)CDsum, n, k, kp, ldh, alpha, beta, eps, (double*)H, (double*)Ht, prior_part, state);
+}
+
+void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64_t ldh, double eps,
+                       double* prior_part, cudaStream_t st) {
+  dim3 grid((unsigned)((n + HEPI_NT - 1) / HEPI_NT), (unsigned)kp);
+  if (dtype == 0)
+    h_epilogue_kernel<float, false><<<grid, HEPI_NT, 0, st>>>(nullptr, n, k, kp, ldh, 1.0, 1.0, eps, (float*)H, nullptr, prior_part, nullptr);
+  else
+    h_epilogue_kernel<double, false><<<grid, HEPI_NT, 0, st>>>(nullptr, n, k, kp, ldh, 1.0, 1.0, eps, (double*)H, nullptr, prior_part, nullptr);
+}
+
+// ------------------------------------------------------------------------------------
+// W epilogue: multiplicative step + simplex projection (_solver.py:53-57), row-local.
+// projection 0 = "normalize": (W*G)/n then L1 renormalisation;  1 = "duchi": (W*G)/n_obs(row)
+// then Euclidean projection onto the simplex (Duchi et al. 2008 sort/threshold; unpinned).
+// ------------------------------------------------------------------------------------
+constexpr int MAX_K = 64;
+
+template <typename Real>
+__global__ void w_epilogue_kernel(const Real* __restrict__ Gpart, const Real* __restrict__ Qpart, int nsplit,
+                                  int64_t m, int64_t n, int k, int kp, int projection,
+                                  const Real* __restrict__ rowcount, Real* __restrict__ W,
+                                  const FitState* __restrict__ state) {
+  if (state->done) return;
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  Real q = Qpart[row];
+  for (int s = 1; s < nsplit; ++s) q += Qpart[(int64_t)s * m + row];
+  Real v[MAX_K];
+  const Real denom = (projection == 0) ? (Real)n : (rowcount ? rowcount[row] : (Real)n);
+  Real sum = Real(0);
+  for (int kk = 0; kk < k; ++kk) {
+    Real gs = Gpart[row * kp + kk];
+    for (int s = 1; s < nsplit; ++s) gs += Gpart[((int64_t)s * m + row) * kp + kk];
+    const Real x = (W[row * kp + kk] * (gs + q)) / denom;
+    v[kk] = x;
+    sum += x;
+  }
+  if (projection == 0) {
+    for (int kk = 0; kk < k; ++kk) W[row * kp + kk] = v[kk] / sum;
+    return;
+  }
+  // Duchi: sort descending (insertion sort, k <= 64), find rho and the threshold
+  Real u[MAX_K];
+  for (int a = 0; a < k; ++a) {
+    const Real x = v[a];
+    int b = a;
+    while (b > 0 && u[b - 1] < x) { u[b] = u[b - 1]; --b; }
+    u[b] = x;
+  }
+  Real css = Real(0), theta = Real(0);
+  for (int a = 0; a < k; ++a) {
+    css += u[a];
+    const Real t = (css - Real(1)) / (Real)(a + 1);
+    if (u[a] - t > Real(0)) theta = t;
+  }
+  for (int kk = 0; kk < k; ++kk) W[row * kp + kk] = fmax(v[kk] - theta, Real(0));
+}
+
+void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nsplit, int64_t m, int64_t n,
+                       int k, int kp, int projection, const void* rowcount, void* W, const FitState* state,
+                       cudaStream_t st) {
+  const unsigned grid = (unsigned)((m + 127) / 128);
+  if (dtype == 0)
+    w_epilogue_kernel<float><<<grid, 128, 0, st>>>((const float*)Gpart, (const float*)Qpart, nsplit, m, n, k, kp, projection, (const float*)rowcount, (float*)W, state);
+  else
+    w_epilogue_kernel<double><<<grid, 128, 0, st>>>((const double*)Gpart, (const double*)Qpart, nsplit, m, n, k, kp, projection, (const double*)rowcount, (double*)W, state);
+}
+
+// transform() tail: clip to [lo, hi] then row renormalisation (_base.py:196-198)
+template <typename Real>
+__global__ void clip_rows_kernel(Real* __restrict__ W, int64_t m, int k, int kp, Real lo, Real hi) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  Real s = Real(0);
+  for (int kk = 0; kk < k; ++kk) {
+    const Real x = fmin(fmax(W[row * kp + kk], lo), hi);
+    W[row * kp + kk] = x;
+    s += x;
+  }
+  for (int kk = 0; kk < k; ++kk) W[row * kp + kk] /= s;
+}
+void launch_clip_rows(int dtype, void* W, int64_t m, int k, int kp, double lo, double hi, cudaStream_t st) {
+  const unsigned grid = (unsigned)((m + 127) / 128);
+  if (dtype == 0) clip_rows_kernel<float><<<grid, 128, 0, st>>>((float*)W, m, k, kp, (float)lo, (float)hi);
+  else clip_rows_kernel<double><<<grid, 128, 0, st>>>((double*)W, m, k, kp, lo, hi);
+}
+
+// ------------------------------------------------------------------------------------
+// data layer: 1 bit per entry planes, dense V*mask, packed transpose, counts
+// element dtypes: 0 = f32, 1 = f64, 2 = u8
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double load_elem(const void* p, int dtype, int64_t idx) {
+  if (dtype == 0) return (double)reinterpret_cast<const float*>(p)[idx];
+  if (dtype == 1) return reinterpret_cast<const double*>(p)[idx];
+  return (double)reinterpret_cast<const unsigned char*>(p)[idx];
+}
+
+__global__ void pack_bits_kernel(const void* __restrict__ X, int xdt, int64_t ldx, const void* __restrict__ mask,
+                                 int mdt, int64_t ldm, int64_t m, int64_t n, int64_t wpr, uint32_t* __restrict__ P,
+                                 uint32_t* __restrict__ M) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t total = m * wpr;
+  for (int64_t wi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < total; wi += nwarps) {
+    const int64_t row = wi / wpr, w = wi % wpr;
+    const int64_t col = w * 32 + lane;
+    bool ob = col < n, pb = false;
+    if (ob) {
+      if (mask) ob = load_elem(mask, mdt, row * ldm + col) != 0.0;
+      pb = ob && (load_elem(X, xdt, row * ldx + col) != 0.0);
+    }
+    const uint32_t pw = __ballot_sync(0xffffffffu, pb), mw = __ballot_sync(0xffffffffu, ob);
+    if (lane == 0) {
+      P[wi] = pw;
+      if (M) M[wi] = mw;
+    }
+  }
+}
+
+void launch_pack_bits(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
+                      int64_t m, int64_t n, int64_t wpr, uint32_t* P, uint32_t* M, cudaStream_t st) {
+  int64_t nb = (m * wpr + 7) / 8;
+  if (nb > 148 * 32) nb = 148 * 32;
+  if (nb < 1) nb = 1;
+  pack_bits_kernel<<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, wpr, P, M);
+}
+
+template <typename Real>
+__global__ void pack_dense_kernel(const void* __restrict__ X, int xdt, int64_t ldx, const void* __restrict__ mask,
+                                  int mdt, int64_t ldm, int64_t m, int64_t n, int64_t ldv, Real* __restrict__ Vm) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m * ldv; e += stride) {
+    const int64_t row = e / ldv, col = e % ldv;
+    double v = 0.0;
+    if (col < n) {
+      v = load_elem(X, xdt, row * ldx + col);
+      if (mask) v *= load_elem(mask, mdt, row * ldm + col);      // Y * mask, _solver.py:30
+    }
+    Vm[e] = (Real)v;
+  }
+}
+
+void launch_pack_dense(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
+                       int64_t m, int64_t n, int out_dtype, int64_t ldv, void* Vm, cudaStream_t st) {
+  int64_t nb = (m * ldv + 255) / 256;
+  if (nb > 148 * 32) nb = 148 * 32;
+  if (nb < 1) nb = 1;
+  if (out_dtype == 0)
+    pack_dense_kernel<float><<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, ldv, (float*)Vm);
+  else
+    pack_dense_kernel<double><<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, ldv, (double*)Vm);
+}
+
+// 32x32 bit-block transpose with warp ballots: dst[col][row/32] bit (row%32) = src[row][col/32] bit (col%32)
+__global__ void transpose_bits_kernel(const uint32_t* __restrict__ src, int64_t m, int64_t n, int64_t wpr_src,
+                                      uint32_t* __restrict__ dst, int64_t wpr_dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rblocks = (m + 31) / 32, cblocks = (n + 31) / 32;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t bi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bi < rblocks * cblocks; bi += nwarps) {
+    const int64_t rb = bi / cblocks, cb = bi % cblocks;
+    const int64_t row = rb * 32 + lane;
+    const uint32_t w = row < m ? src[row * wpr_src + cb] : 0u;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t t = __ballot_sync(0xffffffffu, (w >> b) & 1u);
+      if (lane == b) mine = t;
+    }
+    const int64_t orow = cb * 32 + lane;
+    if (orow < n) dst[orow * wpr_dst + rb] = mine;
+  }
+}
+
+void launch_transpose_bits(const uint32_t* src, int64_t m, int64_t n, int64_t wpr_src, uint32_t* dst,
+                           int64_t wpr_dst, cudaStream_t st) {
+  cudaMemsetAsync(dst, 0, (size_t)n * wpr_dst * 4, st);
+  int64_t nb = (((m + 31) / 32) * ((n + 31) / 32) + 7) / 8;
+  if (nb > 148 * 32) nb = 148 * 32;
+  if (nb < 1) nb = 1;
+  transpose_bits_kernel<<<(unsigned)nb, 256, 0, st>>>(src, m, n, wpr_src, dst, wpr_dst);
+}
+
+template <typename Real>
+__global__ void rowcount_kernel(const uint32_t* __restrict__ M, int64_t m, int64_t wpr, Real* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= m) return;
+  const int lane = threadIdx.x & 31;
+  int c = 0;
+  for (int64_t w = lane; w < wpr; w += 32) c += __popc(M[row * wpr + w]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) out[row] = (Real)c;
+}
+void launch_rowcount(int dtype, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, void* out, cudaStream_t st) {
+  (void)n;
+  const unsigned grid = (unsigned)((m + 7) / 8);
+  if (dtype == 0) rowcount_kernel<float><<<grid, 256, 0, st>>>(M, m, wpr, (float*)out);
+  else rowcount_kernel<double><<<grid, 256, 0, st>>>(M, m, wpr, (double*)out);
+}
+
+__global__ void popcount_kernel(const uint32_t* __restrict__ B, int64_t total, unsigned long long* out) {
+  unsigned long long c = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) c += __popc(B[e]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);           // integer atomics: order-independent
+}
+void launch_popcount(const uint32_t* B, int64_t m, int64_t wpr, unsigned long long* out, cudaStream_t st) {
+  cudaMemsetAsync(out, 0, sizeof(unsigned long long), st);
+  int64_t nb = (m * wpr + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  popcount_kernel<<<(unsigned)nb, 256, 0, st>>>(B, m * wpr, out);
+}
+
+// ------------------------------------------------------------------------------------
+// counter-based synthetic generator (config 4): V ~ Bernoulli(W* H*), mask ~ Bernoulli(obs)
+// keyed on (seed, global row, column) so any row block can be regenerated independently.
+// W* rows are Dirichlet(1) (normalised exponentials of hashed uniforms), H* is supplied.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t key) { return (float)(mix64(key) >> 40) * (1.0f / 16777216.0f); }
+
+__global__ void synth_bits_kernel(uint64_t seed, int64_t row0, int64_t m, int64_t n, int64_t wpr,
+                                  const float* __restrict__ Hstar, int kstar, float obs_frac,
+                                  uint32_t* __restrict__ P, uint32_t* __restrict__ M) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x;
+  if (row >= m) return;
+  const uint64_t grow = (uint64_t)(row0 + row);
+  // Dirichlet(1) weights of this row, lane k holds w_k
+  float e = 0.f;
+  if (lane < kstar) e = -__logf(fmaxf(u01(seed * 0x100000001B3ull + (grow << 8) + (uint64_t)lane + 0x5151ull), 1e-7f));
+  float s = e;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float wk = e / s;
+  for (int64_t w = threadIdx.x >> 5; w < wpr; w += (blockDim.x >> 5)) {
+    const int64_t col = w * 32 + lane;
+    float theta = 0.f;
+    for (int kk = 0; kk < kstar; ++kk) {
+      const float wv = __shfl_sync(0xffffffffu, wk, kk);
+      if (col < n) theta = fmaf(wv, Hstar[(int64_t)kk * n + col], theta);
+    }
+    const uint64_t key = (seed << 1) ^ (grow * (uint64_t)n + (uint64_t)col);
+    const bool ob = col < n && u01(key * 2 + 1) < obs_frac;
+    const bool vb = col < n && u01(key * 2) < theta;
+    const uint32_t pw = __ballot_sync(0xffffffffu, vb && ob), mw = __ballot_sync(0xffffffffu, ob);
+    if (lane == 0) {
+      P[row * wpr + w] = pw;
+      if (M) M[row * wpr + w] = mw;
+    }
+  }
+}
+
+void launch_synth_bits(uint64_t seed, int64_t row0, int64_t m, int64_t n, int64_t wpr, const float* Wstar,
+                       const float* Hstar, int kstar, float obs_frac, uint32_t* P, uint32_t* M, cudaStream_t st) {
+  (void)Wstar;
+  synth_bits_kernel<<<(unsigned)m, 256, 0, st>>>(seed, row0, m, n, wpr, Hstar, kstar, obs_frac, P, M);
+}
+
+// ------------------------------------------------------------------------------------
+// FP32 / FP64 FMA-pipe peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has
+// no FP32 entry).  fp32 uses the same packed FFMA2 the pass kernels issue.
+// ------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float* out) {
+  using V2 = typename Vec2<Real>::type;
+  V2 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make2((Real)(threadIdx.x * 1e-3 + i), (Real)(i * 0.5));
+  const V2 a = make2((Real)0.999, (Real)1.001), b = make2((Real)1e-3, (Real)-1e-3);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fma2(acc[i], a, b);
+  }
+  Real s = Real(0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i].x + acc[i].y;
+  if (s == (Real)123456.789) out[0] = (float)s;                 // keep the chain alive
+}
+
+double run_fma_peak(int dtype, int iters, cudaStream_t st, float* scratch) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = 148 * 8;
+  for (int rep = 0; rep < 2; ++rep) {
+    if (rep == 1) cudaEventRecord(e0, st);
+    if (dtype == 0) fma_peak_kernel<float><<<grid, 256, 0, st>>>(iters, scratch);
+    else fma_peak_kernel<double><<<grid, 256, 0, st>>>(iters, scratch);
+  }
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flop = 2.0 * 2.0 * 64.0 * (double)iters * 256.0 * grid;   // 64 fma2 per iter, 2 FMA each
+  return flop / (ms * 1e-3) * 1e-12;
+}
+
+}  // namespace nbmf

@@ -1,0 +1,479 @@
+// The two fused pass kernels of one MM iteration (reference: src/nbmf_mm/_solver.py:5-59
+// for the update, :148-162 for the loss that rides on the H pass).
+//
+// Both are structured like attention with fp32/fp64 SIMT math: the Theta = W.H tile is
+// formed on the fly from a factor tile staged in shared memory and a factor slice held
+// in registers, the masked ratios are computed in registers, and the second contraction
+// is accumulated in registers.  Theta, the ratios and the weights never touch HBM.
+//
+// Register tiling.  A warp is split into G = 32/S "groups" of S lanes.  A group owns C
+// output vectors (columns j for the H pass, rows i for the W pass); inside a group the K
+// axis is split S ways (lane kp owns k in [kp*KH, (kp+1)*KH), KH = KP/S).  Theta partial
+// dot products are combined with log2(S) xor-shuffles.  Accumulators are (k, k+1) pairs so
+// that fp32 issues packed FFMA2 (one issue slot per two FMAs).
+#pragma once
+#include "args.h"
+#include "common.cuh"
+
+namespace nbmf {
+
+template <typename Real, int KH>
+__device__ __forceinline__ void load_pairs(const Real* __restrict__ src, typename Vec2<Real>::type (&dst)[KH / 2]) {
+  using V2 = typename Vec2<Real>::type;
+  if constexpr (sizeof(Real) == 4 && (KH % 4) == 0) {
+#pragma unroll
+    for (int q = 0; q < KH / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(src + 4 * q);
+      dst[2 * q] = make2(v.x, v.y);
+      dst[2 * q + 1] = make2(v.z, v.w);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < KH / 2; ++q) dst[q] = *reinterpret_cast<const V2*>(src + 2 * q);
+  }
+}
+
+// =====================================================================================
+// H pass:  C[k][j] = sum_i W[i][k] * pos[i][j] / (Theta[i][j] + eps)
+//          D[k][j] = sum_i W[i][k] * neg[i][j] / ((1 - Theta[i][j]) + eps)
+//          LL      = sum_ij pos*log(Theta+eps) + neg*log((1-Theta)+eps)      (_solver.py:39-43,150-154)
+// pos = V&mask; neg = 1 - pos (reference quirk) or mask - pos (STRICT).
+// A thread owns C contiguous columns x KH values of k; rows stream through shared memory.
+// =====================================================================================
+template <typename Real_, int KP_, int S_, int C_, int NW_, int MINB_, bool DENSE_, bool STRICT_>
+struct HCfg {
+  using Real = Real_;
+  static constexpr int KP = KP_, S = S_, C = C_, NW = NW_, MINB = MINB_;
+  static constexpr bool DENSE = DENSE_, STRICT = STRICT_;
+  static constexpr int KH = KP / S;
+  static constexpr int G = 32 / S;
+  static constexpr int CW = G * C;          // columns per warp
+  static constexpr int BN = NW * CW;        // columns per CTA
+  static constexpr int WPT = BN / 32;       // bit words per tile row
+  static constexpr int BM = 32;             // rows per stage
+  static constexpr int NSTAGE = 3;
+  static constexpr int NT = NW * 32;
+  static constexpr int W_BYTES = BM * KP * (int)sizeof(Real);
+  static constexpr int P_BYTES = DENSE ? 0 : BM * WPT * 4;
+  static constexpr int M_BYTES = STRICT ? BM * WPT * 4 : 0;
+  static constexpr int STAGE_BYTES = W_BYTES + P_BYTES + M_BYTES;
+  static constexpr int SMEM = NSTAGE * STAGE_BYTES;
+  static_assert(KP % S == 0 && KH % 2 == 0, "K slice per lane must be even");
+  static_assert((KP * sizeof(Real)) % 16 == 0, "W rows must be 16-byte multiples");
+  static_assert(BN % 128 == 0 && 1024 % BN == 0, "column tile must divide the 1024-column pitch");
+  static_assert(32 % C == 0, "a thread's bits must not straddle a word");
+};
+
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassArgs a) {
+  using Real = typename Cfg::Real;
+  using V2 = typename Vec2<Real>::type;
+  constexpr int KP = Cfg::KP, S = Cfg::S, C = Cfg::C, KH = Cfg::KH, NT = Cfg::NT;
+  constexpr int BM = Cfg::BM, WPT = Cfg::WPT, NSTAGE = Cfg::NSTAGE;
+  constexpr bool DENSE = Cfg::DENSE, STRICT = Cfg::STRICT;
+  if (*a.done) return;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_scratch[NT / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane / S, kp = lane % S;
+  const int jw = warp * Cfg::CW + g * C;                        // column offset inside the CTA tile
+  const int64_t j0 = (int64_t)blockIdx.x * Cfg::BN + jw;         // first owned column
+  const int split = blockIdx.y;
+  const int64_t r0 = (int64_t)split * a.rows_per_split;
+  const int64_t r1 = min(a.m, r0 + a.rows_per_split);
+  const Real eps = (Real)a.eps;
+
+  // ---- H slice -> registers (padded columns hold 0.5, always in bounds)
+  V2 hp[C][KH / 2];
+  {
+    const Real* __restrict__ Hg = reinterpret_cast<const Real*>(a.H);
+#pragma unroll
+    for (int q = 0; q < KH / 2; ++q)
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc)
+        hp[cc][q] = make2(Hg[(int64_t)(kp * KH + 2 * q) * a.ldh + j0 + cc],
+                          Hg[(int64_t)(kp * KH + 2 * q + 1) * a.ldh + j0 + cc]);
+  }
+  V2 cacc[C][KH / 2], dacc[C][KH / 2];
+#pragma unroll
+  for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+    for (int q = 0; q < KH / 2; ++q) cacc[cc][q] = dacc[cc][q] = make2(Real(0), Real(0));
+  double lld[C];
+#pragma unroll
+  for (int cc = 0; cc < C; ++cc) lld[cc] = 0.0;
+
+  const unsigned char* __restrict__ Wg = reinterpret_cast<const unsigned char*>(a.W);
+  const Real* __restrict__ Vg = reinterpret_cast<const Real*>(a.Vm);
+  const int64_t ntiles = (r1 > r0) ? (r1 - r0 + BM - 1) / BM : 0;
+
+  auto issue_tile = [&](int64_t t) {
+    unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;
+    const int64_t rb = r0 + t * BM;
+    const int nrows = (int)min((int64_t)BM, r1 - rb);
+    const int wchunks = nrows * (KP * (int)sizeof(Real) / 16);
+    const unsigned char* wsrc = Wg + (size_t)rb * KP * sizeof(Real);
+    for (int c = tid; c < wchunks; c += NT) cp_async16(st + 16 * c, wsrc + 16 * (size_t)c);
+    if constexpr (!DENSE) {
+      constexpr int CPR = WPT / 4;                               // 16-byte chunks per tile row
+      const int bchunks = nrows * CPR;
+      for (int c = tid; c < bchunks; c += NT) {
+        const int r = c / CPR, q = c % CPR;
+        cp_async16(st + Cfg::W_BYTES + 16 * c,
+                   a.P + (size_t)(rb + r) * a.wpr + (size_t)blockIdx.x * WPT + 4 * q);
+      }
+    }
+    if constexpr (STRICT) {
+      constexpr int CPR = WPT / 4;
+      const int bchunks = nrows * CPR;
+      for (int c = tid; c < bchunks; c += NT) {
+        const int r = c / CPR, q = c % CPR;
+        cp_async16(st + Cfg::W_BYTES + Cfg::P_BYTES + 16 * c,
+                   a.M + (size_t)(rb + r) * a.wpr + (size_t)blockIdx.x * WPT + 4 * q);
+      }
+    }
+  };
+
+#pragma unroll
+  for (int t = 0; t < NSTAGE - 1; ++t) {
+    if (t < ntiles) issue_tile(t);
+    cp_async_commit();
+  }
+
+  for (int64_t t = 0; t < ntiles; ++t) {
+    if (t + NSTAGE - 1 < ntiles) issue_tile(t + NSTAGE - 1);
+    cp_async_commit();
+    cp_async_wait<NSTAGE - 1>();
+    __syncthreads();
+
+    const unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;
+    const Real* Wt = reinterpret_cast<const Real*>(st);
+    const uint32_t* Pb = reinterpret_cast<const uint32_t*>(st + Cfg::W_BYTES);
+    const uint32_t* Mb = reinterpret_cast<const uint32_t*>(st + Cfg::W_BYTES + Cfg::P_BYTES);
+    const int64_t rb = r0 + t * BM;
+    const int nrows = (int)min((int64_t)BM, r1 - rb);
+
+    Real ll[C];
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) ll[cc] = Real(0);
+    Real vnext[C];
+    if constexpr (DENSE) {
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) vnext[cc] = Vg[(size_t)rb * a.ldv + j0 + cc];
+    }
+
+#pragma unroll 2
+    for (int r = 0; r < nrows; ++r) {
+      V2 wp[KH / 2];
+      load_pairs<Real, KH>(Wt + r * KP + kp * KH, wp);
+
+      // ---- Theta[i][j] for the C owned columns
+      V2 th[C];
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) th[cc] = make2(Real(0), Real(0));
+#pragma unroll
+      for (int q = 0; q < KH / 2; ++q)
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) th[cc] = fma2(wp[q], hp[cc][q], th[cc]);
+      Real theta[C];
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        theta[cc] = th[cc].x + th[cc].y;
+#pragma unroll
+        for (int o = 1; o < S; o <<= 1) theta[cc] += __shfl_xor_sync(0xffffffffu, theta[cc], o);
+      }
+
+      uint32_t pb = 0, mb = 0xffffffffu;
+      if constexpr (!DENSE) pb = Pb[r * WPT + (jw >> 5)] >> (jw & 31);
+      if constexpr (STRICT) mb = Mb[r * WPT + (jw >> 5)] >> (jw & 31);
+      Real vcur[C];
+      if constexpr (DENSE) {
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) vcur[cc] = vnext[cc];
+        const int64_t rn = min(rb + r + 1, a.m - 1);
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) vnext[cc] = Vg[(size_t)rn * a.ldv + j0 + cc];
+      }
+
+      // ---- masked ratios in registers, loss term, second contraction
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        Real rp, rn_;
+        if constexpr (!DENSE) {
+          const bool p = (pb >> cc) & 1u;
+          const Real x = (p ? theta[cc] : (Real(1) - theta[cc])) + eps;
+          Real r_ = rcp_(x);
+          Real lg = logu_(x);
+          if constexpr (STRICT) {
+            const bool o = (mb >> cc) & 1u;
+            r_ = o ? r_ : Real(0);
+            lg = o ? lg : Real(0);
+          }
+          ll[cc] += lg;
+          rp = p ? r_ : Real(0);
+          rn_ = p ? Real(0) : r_;
+        } else {
+          const Real v = vcur[cc];
+          const Real xp = theta[cc] + eps;
+          const Real xn = (Real(1) - theta[cc]) + eps;
+          Real neg;
+          if constexpr (STRICT) neg = (((mb >> cc) & 1u) ? Real(1) : Real(0)) - v;
+          else neg = Real(1) - v;
+          rp = div_(v, xp);
+          rn_ = div_(neg, xn);
+          ll[cc] += v * logu_(xp) + neg * logu_(xn);
+        }
+        if (a.compute_cd) {
+          const V2 rp2 = make2(rp, rp), rn2 = make2(rn_, rn_);
+#pragma unroll
+          for (int q = 0; q < KH / 2; ++q) {
+            cacc[cc][q] = fma2(wp[q], rp2, cacc[cc][q]);
+            dacc[cc][q] = fma2(wp[q], rn2, dacc[cc][q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) lld[cc] += (double)ll[cc];
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  // ---- partial C, D for this row split
+  if (a.compute_cd) {
+    Real* __restrict__ Cg = reinterpret_cast<Real*>(a.CD) + (size_t)(split * 2 + 0) * KP * a.ldh;
+    Real* __restrict__ Dg = reinterpret_cast<Real*>(a.CD) + (size_t)(split * 2 + 1) * KP * a.ldh;
+#pragma unroll
+    for (int q = 0; q < KH / 2; ++q) {
+      const size_t o0 = (size_t)(kp * KH + 2 * q) * a.ldh + j0;
+      const size_t o1 = o0 + a.ldh;
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        Cg[o0 + cc] = cacc[cc][q].x;
+        Cg[o1 + cc] = cacc[cc][q].y;
+        Dg[o0 + cc] = dacc[cc][q].x;
+        Dg[o1 + cc] = dacc[cc][q].y;
+      }
+    }
+  }
+  // ---- partial log-likelihood: one lane per group counts, padded columns excluded
+  double mine = 0.0;
+  if (kp == 0) {
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc)
+      if (j0 + cc < a.n) mine += lld[cc];
+  }
+  const double tot = block_sum<NT>(mine, red_scratch);
+  if (tid == 0) a.LL[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<Real>();
+}
+
+template <typename Cfg>
+void launch_h_pass(const HPassArgs& a, int nsplit, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(h_pass_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a.n + Cfg::BN - 1) / Cfg::BN), (unsigned)nsplit);
+  h_pass_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(a);
+}
+
+// =====================================================================================
+// W pass:  Gs[i][k] = sum_j H[k][j] * (p_ij - q_ij),   Qs[i] = sum_j q_ij
+//   p = posW/(Theta+eps), q = negW/((1-Theta)+eps)  with posW = V&mask, negW = mask&~V
+//   (_solver.py:50-53, always properly masked), so that
+//   G[i][k] = sum_j H[k][j] p + (1-H[k][j]) q = Gs[i][k] + Qs[i].
+// For binary V exactly one of p, q is non-zero, so p - q is exact.
+// A thread owns C rows x KH values of k; columns stream through shared memory (Ht tiles).
+// =====================================================================================
+template <typename Real_, int KP_, int S_, int C_, int NW_, int MINB_, bool DENSE_>
+struct WCfg {
+  using Real = Real_;
+  static constexpr int KP = KP_, S = S_, C = C_, NW = NW_, MINB = MINB_;
+  static constexpr bool DENSE = DENSE_;
+  static constexpr int KH = KP / S;
+  static constexpr int G = 32 / S;
+  static constexpr int RW = G * C;          // rows per warp
+  static constexpr int BMR = NW * RW;       // rows per CTA
+  static constexpr int BNT = 128;           // columns per stage
+  static constexpr int NWORD = BNT / 32;
+  static constexpr int NSTAGE = 2;
+  static constexpr int NT = NW * 32;
+  static constexpr int HT_BYTES = BNT * KP * (int)sizeof(Real);
+  static constexpr int P_BYTES = DENSE ? 0 : BMR * NWORD * 4;
+  static constexpr int M_BYTES = BMR * NWORD * 4;
+  static constexpr int STAGE_BYTES = HT_BYTES + P_BYTES + M_BYTES;
+  static constexpr int SMEM = NSTAGE * STAGE_BYTES;
+  static_assert(KP % S == 0 && KH % 2 == 0, "K slice per lane must be even");
+  static_assert((KP * sizeof(Real)) % 16 == 0, "Ht rows must be 16-byte multiples");
+};
+
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassArgs a) {
+  using Real = typename Cfg::Real;
+  using V2 = typename Vec2<Real>::type;
+  constexpr int KP = Cfg::KP, S = Cfg::S, C = Cfg::C, KH = Cfg::KH, NT = Cfg::NT;
+  constexpr int BNT = Cfg::BNT, NWORD = Cfg::NWORD, NSTAGE = Cfg::NSTAGE, BMR = Cfg::BMR;
+  constexpr bool DENSE = Cfg::DENSE;
+  if (*a.done) return;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane / S, kp = lane % S;
+  const int il = warp * Cfg::RW + g * C;                          // first owned row inside the CTA tile
+  const int64_t ib = (int64_t)blockIdx.x * BMR;
+  const int split = blockIdx.y;
+  const int64_t c0 = (int64_t)split * a.cols_per_split;
+  const int64_t c1 = min(a.n, c0 + a.cols_per_split);
+  const bool has_mask = (a.M != nullptr);
+  const Real eps = (Real)a.eps;
+
+  // ---- W slice -> registers (rows past m are clamped; their results are not stored)
+  V2 wp[C][KH / 2];
+  {
+    const Real* __restrict__ Wg = reinterpret_cast<const Real*>(a.W);
+#pragma unroll
+    for (int rr = 0; rr < C; ++rr) {
+      const int64_t row = min(ib + il + rr, a.m - 1);
+      load_pairs<Real, KH>(Wg + (size_t)row * KP + kp * KH, wp[rr]);
+    }
+  }
+  V2 gacc[C][KH / 2];
+  Real qacc[C];
+#pragma unroll
+  for (int rr = 0; rr < C; ++rr) {
+    qacc[rr] = Real(0);
+#pragma unroll
+    for (int q = 0; q < KH / 2; ++q) gacc[rr][q] = make2(Real(0), Real(0));
+  }
+
+  const unsigned char* __restrict__ Htg = reinterpret_cast<const unsigned char*>(a.Ht);
+  const Real* __restrict__ Vg = reinterpret_cast<const Real*>(a.Vm);
+  const int64_t ntiles = (c1 > c0) ? (c1 - c0 + BNT - 1) / BNT : 0;
+
+  auto issue_tile = [&](int64_t t) {
+    unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;
+    const int64_t cb = c0 + t * BNT;
+    constexpr int HCH = Cfg::HT_BYTES / 16;
+    const unsigned char* hsrc = Htg + (size_t)cb * KP * sizeof(Real);
+    for (int c = tid; c < HCH; c += NT) cp_async16(st + 16 * c, hsrc + 16 * (size_t)c);
+    const int64_t wb = cb >> 5;                                   // first bit word of this tile
+    for (int r = tid; r < BMR; r += NT) {
+      const int64_t row = min(ib + r, a.m - 1);
+      if constexpr (!DENSE) cp_async16(st + Cfg::HT_BYTES + 16 * r, a.P + (size_t)row * a.wpr + wb);
+      if (has_mask) cp_async16(st + Cfg::HT_BYTES + Cfg::P_BYTES + 16 * r, a.M + (size_t)row * a.wpr + wb);
+    }
+  };
+
+  if (ntiles > 0) issue_tile(0);
+  cp_async_commit();
+
+  for (int64_t t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) issue_tile(t + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    const unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;
+    const Real* Hts = reinterpret_cast<const Real*>(st);
+    const uint32_t* Pb = reinterpret_cast<const uint32_t*>(st + Cfg::HT_BYTES);
+    const uint32_t* Mb = reinterpret_cast<const uint32_t*>(st + Cfg::HT_BYTES + Cfg::P_BYTES);
+    const int64_t cb = c0 + t * BNT;
+
+#pragma unroll 1
+    for (int w = 0; w < NWORD; ++w) {
+      const int64_t colw = cb + 32 * w;
+      if (colw >= c1) break;
+      // columns past n (or past this split) contribute nothing
+      const int64_t rem = c1 - colw;
+      const uint32_t valid = rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
+      uint32_t pw[C], mw[C];
+#pragma unroll
+      for (int rr = 0; rr < C; ++rr) {
+        pw[rr] = DENSE ? 0u : Pb[(il + rr) * NWORD + w];
+        mw[rr] = (has_mask ? Mb[(il + rr) * NWORD + w] : 0xffffffffu) & valid;
+      }
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        Real vv[C][8];
+        if constexpr (DENSE) {
+#pragma unroll
+          for (int rr = 0; rr < C; ++rr) {
+            const int64_t row = min(ib + il + rr, a.m - 1);
+            const Real* src = Vg + (size_t)row * a.ldv + colw + 8 * u;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) vv[rr][e] = src[e];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int jj = 8 * u + e;
+          V2 hq[KH / 2];
+          load_pairs<Real, KH>(Hts + (32 * w + jj) * KP + kp * KH, hq);
+          V2 th[C];
+#pragma unroll
+          for (int rr = 0; rr < C; ++rr) th[rr] = make2(Real(0), Real(0));
+#pragma unroll
+          for (int q = 0; q < KH / 2; ++q)
+#pragma unroll
+            for (int rr = 0; rr < C; ++rr) th[rr] = fma2(wp[rr][q], hq[q], th[rr]);
+#pragma unroll
+          for (int rr = 0; rr < C; ++rr) {
+            Real theta = th[rr].x + th[rr].y;
+#pragma unroll
+            for (int o = 1; o < S; o <<= 1) theta += __shfl_xor_sync(0xffffffffu, theta, o);
+            const bool ob = (mw[rr] >> jj) & 1u;
+            Real s;
+            if constexpr (!DENSE) {
+              const bool p = (pw[rr] >> jj) & 1u;
+              const Real x = (p ? theta : (Real(1) - theta)) + eps;
+              Real r_ = rcp_(x);
+              r_ = ob ? r_ : Real(0);
+              s = p ? r_ : -r_;
+              qacc[rr] += p ? Real(0) : r_;
+            } else {
+              const Real v = vv[rr][e];
+              const Real pa = div_(v, theta + eps);
+              const Real qb = div_((ob ? Real(1) : Real(0)) - v, (Real(1) - theta) + eps);
+              s = pa - qb;
+              qacc[rr] += qb;
+            }
+            const V2 s2 = make2(s, s);
+#pragma unroll
+            for (int q = 0; q < KH / 2; ++q) gacc[rr][q] = fma2(hq[q], s2, gacc[rr][q]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  Real* __restrict__ Gg = reinterpret_cast<Real*>(a.G) + (size_t)split * a.m * KP;
+  Real* __restrict__ Qg = reinterpret_cast<Real*>(a.Q) + (size_t)split * a.m;
+#pragma unroll
+  for (int rr = 0; rr < C; ++rr) {
+    const int64_t row = ib + il + rr;
+    if (row < a.m) {
+#pragma unroll
+      for (int q = 0; q < KH / 2; ++q)
+        *reinterpret_cast<V2*>(Gg + (size_t)row * KP + kp * KH + 2 * q) = gacc[rr][q];
+      if (kp == 0) Qg[row] = qacc[rr];
+    }
+  }
+}
+
+template <typename Cfg>
+void launch_w_pass(const WPassArgs& a, int nsplit, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(w_pass_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a.m + Cfg::BMR - 1) / Cfg::BMR), (unsigned)nsplit);
+  w_pass_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(a);
+}
+
+}  // namespace nbmf

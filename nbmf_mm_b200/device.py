@@ -1,0 +1,325 @@
+"""Device-side plumbing between the Python host and the C-ABI (``include/nbmf_b200.h``).
+
+PyTorch is used for what it is good at here -- device memory, streams and
+``torch.distributed`` -- while all arithmetic of the hot path runs in the hand-written
+sm_100a kernels of ``libnbmf_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .bits import BitMatrix, words_per_row
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("nbmf_mm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(_torch().cuda.current_stream(dev).cuda_stream)
+
+
+_TORCH_DT = {"float32": "float32", "float64": "float64"}
+
+
+def dtype_code(dtype) -> int:
+    name = np.dtype(dtype).name
+    if name == "float32":
+        return _lib.NBMF_F32
+    if name == "float64":
+        return _lib.NBMF_F64
+    raise ValueError(f"dtype must be float32 or float64, got {dtype!r}")
+
+
+def _elem_code(t) -> int:
+    torch = _torch()
+    if t.dtype == torch.float32:
+        return _lib.NBMF_F32
+    if t.dtype == torch.float64:
+        return _lib.NBMF_F64
+    if t.dtype in (torch.uint8, torch.bool):
+        return _lib.NBMF_U8
+    raise ValueError(f"unsupported element type {t.dtype}")
+
+
+# ----------------------------------------------------------------------------- data layer
+def pack_bits_device(X_dev, mask_dev=None, want_mask_plane=True):
+    """Dense device matrix (+ optional dense mask) -> (P = X!=0 & mask, M = mask) bit planes."""
+    torch = _torch()
+    lib = _lib.load()
+    m, n = X_dev.shape
+    wpr = words_per_row(n)
+    dev = X_dev.device
+    X_dev = X_dev.contiguous()
+    P = torch.empty((m, wpr), dtype=torch.int32, device=dev)
+    M = None
+    if mask_dev is not None:
+        mask_dev = mask_dev.contiguous()
+        if want_mask_plane:
+            M = torch.empty((m, wpr), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nbmf_pack_bits(_ptr(X_dev), _elem_code(X_dev), n, _ptr(mask_dev),
+                                      _elem_code(mask_dev) if mask_dev is not None else 0, n,
+                                      m, n, _ptr(P), _ptr(M), _stream(dev)), "nbmf_pack_bits")
+    return BitMatrix(P, (m, n)), (BitMatrix(M, (m, n)) if M is not None else None)
+
+
+def pack_dense_device(X_dev, mask_dev, dtype):
+    """Dense device matrix (+ mask) -> V*mask in ``dtype`` with the padded leading dimension."""
+    torch = _torch()
+    lib = _lib.load()
+    m, n = X_dev.shape
+    ldv = words_per_row(n) * 32
+    dev = X_dev.device
+    X_dev = X_dev.contiguous()
+    if mask_dev is not None:
+        mask_dev = mask_dev.contiguous()
+    Vm = torch.empty((m, ldv), dtype=getattr(torch, np.dtype(dtype).name), device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nbmf_pack_dense(_ptr(X_dev), _elem_code(X_dev), n, _ptr(mask_dev),
+                                       _elem_code(mask_dev) if mask_dev is not None else 0, n,
+                                       m, n, dtype_code(dtype), _ptr(Vm), _stream(dev)), "nbmf_pack_dense")
+    return Vm
+
+
+def transpose_device(B: BitMatrix) -> BitMatrix:
+    torch = _torch()
+    lib = _lib.load()
+    m, n = B.shape
+    dev = B.words.device
+    out = torch.empty((n, words_per_row(m)), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nbmf_transpose_bits(_ptr(B.words), m, n, _ptr(out), _stream(dev)), "nbmf_transpose_bits")
+    return BitMatrix(out, (n, m))
+
+
+def popcount_device(B: BitMatrix) -> int:
+    torch = _torch()
+    lib = _lib.load()
+    dev = B.words.device
+    scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+    out = C.c_uint64(0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nbmf_popcount_bits(_ptr(B.words), B.shape[0], B.shape[1], _ptr(scratch), C.byref(out),
+                                          _stream(dev)), "nbmf_popcount_bits")
+    return int(out.value)
+
+
+def synth_bits_device(seed, row0, m, n, hstar, obs_frac, device, with_mask=True):
+    """Counter-based generator of config 4: returns (P, M) planes on ``device``."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = require_cuda(device)
+    hs = torch.as_tensor(np.ascontiguousarray(hstar, dtype=np.float32), device=dev)
+    wpr = words_per_row(n)
+    P = torch.empty((m, wpr), dtype=torch.int32, device=dev)
+    M = torch.empty((m, wpr), dtype=torch.int32, device=dev) if with_mask else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.nbmf_synth_bits(int(seed), int(row0), int(m), int(n), _ptr(hs), int(hs.shape[0]),
+                                       float(obs_frac), _ptr(P), _ptr(M), _stream(dev)), "nbmf_synth_bits")
+    return BitMatrix(P, (m, n)), (BitMatrix(M, (m, n)) if with_mask else None)
+
+
+# ----------------------------------------------------------------------------- fit context
+class DeviceProblem:
+    """One NBMF-MM problem (or one row shard of it) resident on one GPU.
+
+    Thin owner of an ``nbmf_ctx``: the workspace and the data planes are torch tensors,
+    every method is one C-ABI call.  Internal orientation: V is ``m x n``, W ``m x k``,
+    H ``k x n`` (``_solver.py:113-136``).
+    """
+
+    def __init__(self, m, n, k, *, dtype="float64", vkind="bits", has_mask=False, alpha=1.2, beta=1.2,
+                 eps=1e-8, n_obs=None, mask_semantics="reference", projection="normalize",
+                 max_iter_cap=2000, device=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.dev = require_cuda(device)
+        self.m, self.n, self.k = int(m), int(n), int(k)
+        self.np_dtype = np.dtype(dtype)
+        self.t_dtype = getattr(torch, self.np_dtype.name)
+        if mask_semantics not in ("reference", "strict"):
+            raise ValueError(f"mask_semantics must be 'reference' or 'strict', got {mask_semantics!r}")
+        if projection not in ("normalize", "duchi"):
+            raise ValueError(f"projection_method must be 'normalize' or 'duchi', got {projection!r}")
+        cfg = _lib.NbmfConfig()
+        cfg.m, cfg.n, cfg.k = self.m, self.n, self.k
+        cfg.dtype = dtype_code(dtype)
+        cfg.vkind = _lib.NBMF_V_BITS if vkind == "bits" else _lib.NBMF_V_DENSE
+        cfg.mask_semantics = _lib.NBMF_MASK_STRICT if mask_semantics == "strict" else _lib.NBMF_MASK_REFERENCE
+        cfg.projection = _lib.NBMF_PROJ_DUCHI if projection == "duchi" else _lib.NBMF_PROJ_NORMALIZE
+        cfg.has_mask = 1 if has_mask else 0
+        cfg.alpha, cfg.beta, cfg.eps = float(alpha), float(beta), float(eps)
+        cfg.n_obs = float(self.m * self.n if n_obs is None else n_obs)
+        cfg.max_iter_cap = int(max_iter_cap)
+        self.cfg = cfg
+        nbytes = self.lib.nbmf_workspace_bytes(C.byref(cfg))
+        if nbytes < 0:
+            _lib.check(-1, "nbmf_workspace_bytes")
+        self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+        self._ctx = C.c_void_p(0)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.nbmf_create(C.byref(cfg), _ptr(self.workspace), nbytes, _stream(self.dev),
+                                            C.byref(self._ctx)), "nbmf_create")
+        self._keep = []          # tensors the context borrows
+        self.world = 1
+
+    # -- lifetime
+    def close(self):
+        if self._ctx:
+            _torch().cuda.synchronize(self.dev)
+            self.lib.nbmf_destroy(self._ctx)
+            self._ctx = C.c_void_p(0)
+            self._keep = []
+            self.workspace = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _call(self, name, *args):
+        with _torch().cuda.device(self.dev):
+            _lib.check(getattr(self.lib, name)(self._ctx, *args), name)
+
+    # -- data
+    def set_bits(self, P: BitMatrix, M: BitMatrix | None = None):
+        if P.shape != (self.m, self.n):
+            raise ValueError(f"P has shape {P.shape}, expected {(self.m, self.n)}")
+        P = P if P.is_device else P.to_device(self.dev)
+        if M is not None:
+            M = M if M.is_device else M.to_device(self.dev)
+        self._keep = [P.words, None if M is None else M.words]
+        self._call("nbmf_set_data_bits", _ptr(P.words), _ptr(None if M is None else M.words))
+
+    def set_dense(self, Vm, M: BitMatrix | None = None):
+        if M is not None:
+            M = M if M.is_device else M.to_device(self.dev)
+        self._keep = [Vm, None if M is None else M.words]
+        self._call("nbmf_set_data_dense", _ptr(Vm), _ptr(None if M is None else M.words))
+
+    # -- factors
+    def _to_dev(self, A, shape):
+        torch = _torch()
+        if A is None:
+            return None
+        if not isinstance(A, torch.Tensor):
+            A = torch.from_numpy(np.ascontiguousarray(A, dtype=self.np_dtype))
+        A = A.to(device=self.dev, dtype=self.t_dtype).contiguous()
+        if tuple(A.shape) != shape:
+            raise ValueError(f"factor has shape {tuple(A.shape)}, expected {shape}")
+        return A
+
+    def set_factors(self, W=None, H=None, normalize_w=True):
+        Wd = self._to_dev(W, (self.m, self.k))
+        Hd = self._to_dev(H, (self.k, self.n))
+        self._call("nbmf_set_factors", _ptr(Wd), _ptr(Hd), 1 if normalize_w else 0)
+
+    def get_factors_device(self):
+        torch = _torch()
+        W = torch.empty((self.m, self.k), dtype=self.t_dtype, device=self.dev)
+        H = torch.empty((self.k, self.n), dtype=self.t_dtype, device=self.dev)
+        self._call("nbmf_get_factors", _ptr(W), _ptr(H))
+        return W, H
+
+    def get_factors(self):
+        W, H = self.get_factors_device()
+        return W.cpu().numpy().astype(np.float64), H.cpu().numpy().astype(np.float64)
+
+    # -- steps
+    def h_half_step(self):
+        self._call("nbmf_h_half_step")
+
+    def w_half_step(self):
+        self._call("nbmf_w_half_step")
+
+    def objective(self) -> float:
+        out = C.c_double(0.0)
+        self._call("nbmf_objective", C.byref(out))
+        return float(out.value)
+
+    # -- loop
+    def fit(self, max_iter, tol):
+        """Run the device-resident loop; returns (losses ndarray, n_iter, converged)."""
+        hist = np.zeros(int(max_iter) + 2, dtype=np.float64)
+        n_iter = C.c_int32(0)
+        conv = C.c_int32(0)
+        self._call("nbmf_fit", int(max_iter), float(tol), hist.ctypes.data_as(C.POINTER(C.c_double)),
+                   C.byref(n_iter), C.byref(conv))
+        return hist[: n_iter.value].copy(), int(n_iter.value), bool(conv.value)
+
+    def fit_begin(self, max_iter, tol):
+        self._call("nbmf_fit_begin", int(max_iter), float(tol))
+
+    def fit_enqueue(self, n_iters):
+        self._call("nbmf_fit_enqueue", int(n_iters))
+
+    def fit_poll(self, wait=False):
+        done, n_iter = C.c_int32(0), C.c_int32(0)
+        self._call("nbmf_fit_poll", 1 if wait else 0, C.byref(done), C.byref(n_iter))
+        return int(done.value), int(n_iter.value)
+
+    def fit_history(self, count):
+        hist = np.zeros(max(int(count), 1), dtype=np.float64)
+        conv = C.c_int32(0)
+        self._call("nbmf_fit_history", hist.ctypes.data_as(C.POINTER(C.c_double)), int(count), C.byref(conv))
+        return hist[: int(count)].copy(), bool(conv.value)
+
+    def transform(self, n_steps=50):
+        self._call("nbmf_transform", int(n_steps))
+
+    # -- measurement
+    def profile(self, enable=True):
+        self._call("nbmf_profile_enable", 1 if enable else 0)
+
+    def profile_read(self):
+        """(H-pass total ms, launches, W-pass total ms, launches) since profile(True)."""
+        hm, wm, hc, wc = C.c_double(0), C.c_double(0), C.c_int32(0), C.c_int32(0)
+        self._call("nbmf_profile_read", C.byref(hm), C.byref(hc), C.byref(wm), C.byref(wc))
+        return hm.value, hc.value, wm.value, wc.value
+
+    def plan_info(self):
+        a, b, c_, d = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._call("nbmf_plan_info", C.byref(a), C.byref(b), C.byref(c_), C.byref(d))
+        return dict(h_col_blocks=a.value, h_row_splits=b.value, w_row_blocks=c_.value, w_col_splits=d.value)
+
+    # -- multi-GPU
+    def init_comm(self, group=None):
+        """Join the row-shard communicator: rank 0 creates an NCCL unique id, torch.distributed
+        (any backend) carries it to the other ranks, every rank calls ncclCommInitRank."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        if world == 1:
+            return
+        _lib.nccl_library_hint()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(self.lib.nbmf_comm_unique_id(buf), "nbmf_comm_unique_id")
+        payload = [bytes(buf)]
+        dist.broadcast_object_list(payload, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = (C.c_ubyte * 128).from_buffer_copy(payload[0])
+        self._call("nbmf_comm_init", raw, rank, world)
+        self.world = world

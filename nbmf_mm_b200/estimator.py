@@ -1,0 +1,192 @@
+"""scikit-learn style estimator, drop-in for ``nbmf_mm.NBMFMM`` / ``nbmf_mm.NBMF``
+(reference ``src/nbmf_mm/_base.py``), backed by the B200 kernels.
+
+Same constructor arguments, attributes, error messages and RNG side effects as the
+reference, plus the keyword arguments its README advertises but its code lacks
+(``projection_method``, ``n_init``; README.md:124-144) and the device knobs
+(``dtype``, ``mask_semantics``, ``device``, ``distributed``).
+"""
+from __future__ import annotations
+
+import numpy as np
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.utils import check_array
+
+from ._utils import check_is_fitted
+from .bits import BitMatrix
+from .solver import make_problem, nbmf_mm_solver, prepare_data
+
+# exact-key alias table of the reference (_base.py:127-137); keys are NOT case-folded
+_ORIENTATION_ALIASES = {
+    "beta-dir": "beta-dir",
+    "dir-beta": "dir-beta",
+    "Beta-Dir": "beta-dir",
+    "Dir-Beta": "dir-beta",
+    "Dir Beta": "dir-beta",
+    "binary ICA": "beta-dir",
+    "Binary ICA": "beta-dir",
+    "bICA": "beta-dir",
+    "Aspect Bernoulli": "dir-beta",
+}
+
+
+class NBMFMM(BaseEstimator, TransformerMixin):
+    """Non-negative Binary Matrix Factorization via Majorization-Minimization on B200.
+
+    Parameters (reference ``_base.py:63-66`` first, extensions after ``orientation``)
+    ----------
+    n_components, alpha, beta, max_iter, tol, W_init, H_init, init, random_state, verbose,
+    orientation : as in the reference (``init`` is accepted and ignored there too).
+    projection_method : {"normalize", "duchi"}, default "normalize"
+        Simplex step of the W update: multiplicative + L1 renormalisation (the reference's
+        only behaviour) or Euclidean projection (Duchi et al. 2008; README-only, unpinned).
+    n_init : int, default 1
+        Random restarts; restart r uses ``random_state + r`` and the lowest final loss wins.
+    dtype : {"float64", "float32"}, default "float64"
+        Arithmetic type of the device path.  float64 reproduces the reference to ~1e-12;
+        float32 is the throughput mode (packed FFMA2).
+    mask_semantics : {"reference", "strict"}, default "reference"
+        "reference" reproduces the reference's H-step/loss treatment of unobserved entries as
+        observed zeros (``_solver.py:43,153-154``); "strict" is the README/paper behaviour.
+    device : torch device or None;  distributed : bool, row-shard over torch.distributed.
+    """
+
+    def __init__(self, n_components=10, alpha=1.2, beta=1.2, max_iter=2000, tol=1e-5,
+                 W_init=None, H_init=None, init=None, random_state=None, verbose=0,
+                 orientation="beta-dir", projection_method="normalize", n_init=1,
+                 dtype="float64", mask_semantics="reference", device=None, distributed=False):
+        self.n_components = n_components
+        self.alpha = alpha
+        self.beta = beta
+        self.max_iter = max_iter
+        self.tol = tol
+        self.W_init = W_init
+        self.H_init = H_init
+        self.init = init
+        self.random_state = random_state
+        self.verbose = verbose
+        self.orientation = orientation
+        self.projection_method = projection_method
+        self.n_init = n_init
+        self.dtype = dtype
+        self.mask_semantics = mask_semantics
+        self.device = device
+        self.distributed = distributed
+
+    # ------------------------------------------------------------------ helpers
+    def _normalize_orientation(self, orientation):
+        if orientation in _ORIENTATION_ALIASES:
+            return _ORIENTATION_ALIASES[orientation]
+        raise ValueError(f"Unknown orientation: {orientation}. "
+                         f"Must be one of {list(_ORIENTATION_ALIASES.keys())}")
+
+    @staticmethod
+    def _validate_X(X):
+        if isinstance(X, BitMatrix):
+            return X
+        X = check_array(X, accept_sparse="csr", dtype=np.float64)     # _base.py:83
+        if hasattr(X, "toarray"):
+            X = X.toarray()
+        return X
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, X, y=None, mask=None):
+        """Fit the model to binary (or [0,1]-valued) data ``X`` (``_base.py:80-122``)."""
+        X = self._validate_X(X)
+        if not isinstance(X, BitMatrix) and not np.all((X >= 0) & (X <= 1)):
+            raise ValueError("X must be binary")                       # _base.py:90-91
+        orientation = self._normalize_orientation(self.orientation)
+        self.orientation = orientation                                 # reference mutates it too (_base.py:95)
+        if self.projection_method not in ("normalize", "duchi"):
+            raise ValueError(f"projection_method must be 'normalize' or 'duchi', got {self.projection_method!r}")
+        n_init = int(self.n_init)
+        if n_init < 1:
+            raise ValueError("n_init must be >= 1")
+
+        best = None
+        for r in range(n_init):
+            seed = self.random_state if (self.random_state is None or n_init == 1) else self.random_state + r
+            stats = {}
+            out = nbmf_mm_solver(
+                Y=X, n_components=self.n_components, max_iter=self.max_iter, tol=self.tol,
+                alpha=self.alpha, beta=self.beta, W_init=self.W_init, H_init=self.H_init, mask=mask,
+                random_state=seed, verbose=self.verbose, orientation=orientation,
+                projection_method=self.projection_method, mask_semantics=self.mask_semantics,
+                dtype=self.dtype, device=self.device, distributed=self.distributed, stats=stats)
+            if best is None or out[2][-1] < best[0][2][-1]:
+                best = (out, stats, r)
+        (W, H, losses, _, n_iter), stats, best_r = best
+
+        self.W_ = W
+        self.components_ = H
+        self.loss_curve_ = losses
+        self.objective_history_ = losses
+        self.loss_ = losses[-1] if losses else np.inf
+        self.n_iter_ = n_iter
+        self.reconstruction_err_ = float(losses[-1]) if losses else np.inf
+        self.best_init_ = best_r
+        self.transfer_stats_ = stats
+        return self
+
+    def fit_transform(self, X, y=None):
+        self.fit(X)
+        return self.W_
+
+    # ------------------------------------------------------------------ transform & co
+    def _fixed_h_problem(self, X, mask, n_obs=None):
+        data = prepare_data(X, mask, transpose=False, dtype=self.dtype, device=self.device)
+        if data.n != self.components_.shape[1]:
+            raise ValueError(f"X has {data.n} features, the model was fitted with {self.components_.shape[1]}")
+        prob = make_problem(data, self.n_components, dtype=self.dtype, alpha=1.0, beta=1.0, eps=1e-8,
+                            mask_semantics="reference", projection="normalize", max_iter_cap=1,
+                            device=self.device, n_obs=n_obs)
+        return data, prob
+
+    def _transform_device(self, X, mask):
+        """50 fixed-H W half-steps from W ~ U(0.1, 0.9) drawn from the global NumPy RNG, then clip
+        and row-normalise -- ``_base.py:162-199``.  Always the beta-dir W step, whatever the
+        orientation, exactly like the reference."""
+        data, prob = self._fixed_h_problem(X, mask)
+        try:
+            W0 = np.random.uniform(0.1, 0.9, (data.m, self.n_components))      # _base.py:175
+            prob.set_factors(W0, self.components_, normalize_w=False)
+            prob.transform(50)
+            W, _ = prob.get_factors()
+        finally:
+            prob.close()
+        return W
+
+    def transform(self, X, mask=None):
+        check_is_fitted(self, ["components_"])
+        X = self._validate_X(X)
+        return self._transform_device(X, mask)
+
+    def inverse_transform(self, W):
+        """``clip(W @ components_, 0, 1)`` (``_base.py:201-210``); dense M x N by contract."""
+        check_is_fitted(self, ["components_"])
+        W = check_array(W, dtype=np.float64)
+        return np.clip(W @ self.components_, 0.0, 1.0)
+
+    def score(self, X, mask=None):
+        """Average log-likelihood per observed entry (``_base.py:212-247``).
+
+        As in the reference, ``transform`` is called WITHOUT the mask (``_base.py:235``) and the
+        log-likelihood treats unobserved entries as observed zeros while dividing by the number of
+        observed ones.  Theta = W.components_ is evaluated on the device and never materialised
+        (the reference's clip to [0,1] is a no-op for simplex W and H in (0,1))."""
+        check_is_fitted(self, ["components_"])
+        X = self._validate_X(X)
+        W = self._transform_device(X, None)
+        data, prob = self._fixed_h_problem(X, mask)
+        try:
+            prob.set_factors(W, self.components_, normalize_w=False)
+            loss = prob.objective()
+        finally:
+            prob.close()
+        return float(-loss)
+
+    def perplexity(self, X, mask=None):
+        return float(np.exp(-self.score(X, mask)))
+
+
+NBMF = NBMFMM

@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference solver interface, running on the B200 kernels.
+
+``nbmf_mm_solver`` and ``nbmf_mm_update_beta_dir`` keep the reference's names, argument
+meaning, return tuple and side effects (``src/nbmf_mm/_solver.py:5-13,61-75``); everything
+between input validation and the returned NumPy arrays happens on the device through the
+C-ABI.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .bits import BitMatrix
+from .device import DeviceProblem, pack_bits_device, pack_dense_device, require_cuda
+
+_CANON = ("beta-dir", "dir-beta")
+
+
+@dataclass
+class PreparedData:
+    """Device-resident data planes of one problem in INTERNAL orientation."""
+    m: int
+    n: int
+    vkind: str                 # "bits" | "dense"
+    P: Optional[BitMatrix]     # V & mask             (bits)
+    M: Optional[BitMatrix]     # mask or None
+    Vm: object                 # torch tensor V*mask  (dense)
+    n_obs: float               # Y.size or count_nonzero(mask), _solver.py:151,155
+    h2d_bytes: int = 0
+
+
+def _densify(a):
+    return a.toarray() if hasattr(a, "toarray") else a
+
+
+def _as_bool_mask(mask, shape):
+    mask = np.asarray(_densify(mask))
+    if mask.shape != tuple(shape):
+        raise ValueError(f"mask has shape {mask.shape}, expected {tuple(shape)}")
+    if mask.dtype != np.bool_:
+        if not np.all((mask == 0) | (mask == 1)):
+            raise ValueError("mask must be binary (0/1 or bool): weighted masks are not supported by the bit-packed path")
+        mask = mask != 0
+    return mask
+
+
+def prepare_data(Y, mask, *, transpose, dtype, device) -> PreparedData:
+    """Validate, orient, pack and upload V and the observation mask.
+
+    Binary V goes to two 1-bit planes (packed on the host, so the H2D copy is 32-64x smaller
+    than the reference's fp64 arrays); V with values strictly inside (0,1) goes to the dense
+    ``V*mask`` layout in the compute dtype plus a mask bit plane.  ``transpose`` implements
+    dir-beta == beta-dir on V^T (``_solver.py:113-123``).
+    """
+    import torch
+    dev = require_cuda(device)
+    if isinstance(Y, BitMatrix):
+        P = Y
+        M = mask
+        if M is not None and not isinstance(M, BitMatrix):
+            M = BitMatrix.from_dense(_as_bool_mask(M, P.shape))
+        h2d = 0
+        if not P.is_device:
+            h2d += P.words.nbytes if isinstance(P.words, np.ndarray) else P.words.numel() * 4
+            P = P.to_device(dev)
+        if M is not None and not M.is_device:
+            h2d += M.words.nbytes if isinstance(M.words, np.ndarray) else M.words.numel() * 4
+            M = M.to_device(dev)
+        if M is not None:
+            P = P & M
+        if transpose:
+            P = P.transpose()
+            M = M.transpose() if M is not None else None
+        m, n = P.shape
+        n_obs = float(M.count()) if M is not None else float(m) * float(n)
+        return PreparedData(m, n, "bits", P, M, None, n_obs, h2d)
+
+    Y = np.asarray(_densify(Y), dtype=np.float64)
+    if Y.ndim != 2:
+        raise ValueError("Y must be 2-D")
+    mk = None if mask is None else _as_bool_mask(mask, Y.shape)
+    if transpose:
+        Y = Y.T
+        mk = None if mk is None else mk.T
+    m, n = Y.shape
+    n_obs = float(Y.size) if mk is None else float(np.count_nonzero(mk))
+    if np.all((Y == 0) | (Y == 1)):
+        pos = (Y != 0) if mk is None else ((Y != 0) & mk)
+        P = BitMatrix.from_dense(pos)
+        M = None if mk is None else BitMatrix.from_dense(mk)
+        h2d = P.words.nbytes + (0 if M is None else M.words.nbytes)
+        return PreparedData(m, n, "bits", P.to_device(dev), None if M is None else M.to_device(dev), None, n_obs, h2d)
+    # probabilistic V: dense V*mask in the compute dtype + mask bits
+    Yd = torch.from_numpy(np.ascontiguousarray(Y)).to(dev)
+    h2d = Y.nbytes
+    md = None
+    M = None
+    if mk is not None:
+        md = torch.from_numpy(np.ascontiguousarray(mk).view(np.uint8)).to(dev)
+        h2d += mk.nbytes
+        M, _ = pack_bits_device(md, None)
+    Vm = pack_dense_device(Yd, md, dtype)
+    return PreparedData(m, n, "dense", None, M, Vm, n_obs, h2d)
+
+
+def make_problem(data: PreparedData, k, *, dtype, alpha, beta, eps, mask_semantics, projection, max_iter_cap,
+                 device, n_obs=None) -> DeviceProblem:
+    prob = DeviceProblem(data.m, data.n, k, dtype=dtype, vkind=data.vkind, has_mask=data.M is not None,
+                         alpha=alpha, beta=beta, eps=eps, n_obs=data.n_obs if n_obs is None else n_obs,
+                         mask_semantics=mask_semantics, projection=projection, max_iter_cap=max_iter_cap,
+                         device=device)
+    if data.vkind == "bits":
+        prob.set_bits(data.P, data.M)
+    else:
+        prob.set_dense(data.Vm, data.M)
+    return prob
+
+
+def final_simplex_cleanup(W, H, orientation):
+    """Tail of the reference solver (``_solver.py:192-213``): renormalise the simplex factor
+    only when its worst deviation exceeds 1e-9; vectors with sum <= 1e-12 are left alone."""
+    tiny, dev_tol = 1e-12, 1e-9
+    if orientation == "beta-dir":
+        if W.size:
+            rs = W.sum(axis=1, keepdims=True)
+            dev = np.max(np.abs(rs - 1.0))
+            if np.isfinite(dev) and dev > dev_tol:
+                ok = (rs > tiny).ravel()
+                if ok.any():
+                    W[ok, :] = W[ok, :] / rs[ok]
+    else:
+        if H.size:
+            cs = H.sum(axis=0, keepdims=True)
+            dev = np.max(np.abs(cs - 1.0))
+            if np.isfinite(dev) and dev > dev_tol:
+                ok = (cs > tiny).ravel()
+                if ok.any():
+                    H[:, ok] = H[:, ok] / cs[:, ok]
+    return W, H
+
+
+def _row_shard(m, rank, world):
+    """Contiguous row block of this rank (boundaries on multiples of 32 rows)."""
+    per = (m + world - 1) // world
+    per = (per + 31) // 32 * 32
+    r0 = min(m, rank * per)
+    return r0, min(m, r0 + per)
+
+
+def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2, W_init=None, H_init=None,
+                   mask=None, random_state=None, verbose=0, orientation="beta-dir", eps=1e-8, *,
+                   projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
+                   distributed=False, shard=None, stats=None):
+    """NBMF-MM solver, drop-in for ``nbmf_mm._solver.nbmf_mm_solver`` (``_solver.py:61-216``).
+
+    Returns ``(W (m x k), H (k x n), losses, 0.0, n_iter)`` exactly as the reference does
+    (``time_elapsed`` is hard-coded 0.0 there, ``_solver.py:216``).  Keyword-only extras:
+    ``projection_method`` ("normalize" | "duchi"), ``mask_semantics`` ("reference" quirk |
+    "strict"), ``dtype`` ("float64" parity mode | "float32" throughput mode), ``device``,
+    ``distributed`` (row-shard over the default ``torch.distributed`` group, one rank per GPU:
+    every rank passes the FULL ``Y`` and gets the full result), ``shard=(row0, m_total)`` (with
+    ``distributed``: ``Y``/``mask`` are already this rank's row block of an ``m_total``-row
+    problem in internal orientation; the returned W is the local block, H is global).
+    """
+    if orientation not in _CANON:
+        raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
+    if max_iter < 1:
+        # the reference leaves `iteration` unbound for max_iter=0 (_solver.py:215)
+        raise UnboundLocalError("max_iter must be >= 1")
+    if random_state is not None:
+        np.random.seed(random_state)                      # global legacy stream, as _solver.py:102-103
+    transpose = orientation == "dir-beta"
+    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device)
+    m, n, k = data.m, data.n, int(n_components)
+    if shard is not None:
+        if transpose or not distributed:
+            raise ValueError("shard=(row0, m_total) needs distributed=True and the internal (beta-dir) orientation")
+        shard_row0, m = int(shard[0]), int(shard[1])
+    if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
+        W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
+    if W_init is None:
+        W_init = np.random.uniform(0.1, 0.9, (m, k))      # W first, then H: _solver.py:126-129
+    if H_init is None:
+        H_init = np.random.uniform(0.1, 0.9, (k, n))
+    W_init = np.asarray(W_init, dtype=np.float64)
+    H_init = np.asarray(H_init, dtype=np.float64)
+
+    rank, world = 0, 1
+    if distributed:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    n_obs_global = data.n_obs
+    if shard is not None:
+        r0, r1 = shard_row0, shard_row0 + data.m
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([data.n_obs], dtype=torch.float64, device=require_cuda(device))
+            dist.all_reduce(t)
+            n_obs_global = float(t.item())
+        W_local = W_init[r0:r1]
+    elif world > 1:
+        r0, r1 = _row_shard(m, rank, world)
+        if r1 <= r0:
+            raise ValueError(f"rank {rank} of {world} has no rows (m={m}); use fewer ranks")
+        data = PreparedData(r1 - r0, n, data.vkind,
+                            None if data.P is None else data.P.rows(r0, r1),
+                            None if data.M is None else data.M.rows(r0, r1),
+                            None if data.Vm is None else data.Vm[r0:r1], n_obs_global, data.h2d_bytes)
+        W_local = W_init[r0:r1]
+    else:
+        r0, r1 = 0, m
+        W_local = W_init
+
+    prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
+                        projection=projection_method, max_iter_cap=max_iter, device=device, n_obs=n_obs_global)
+    try:
+        if world > 1:
+            prob.init_comm()
+        prob.set_factors(W_local, H_init, normalize_w=True)
+        losses_arr, n_iter, converged = prob.fit(max_iter, tol)
+        W_loc, H = prob.get_factors()
+    finally:
+        prob.close()
+
+    if shard is not None:
+        W = W_loc
+    elif world > 1:
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, (r0, W_loc))
+        W = np.zeros((m, k), dtype=np.float64)
+        for pr0, pw in parts:
+            W[pr0:pr0 + pw.shape[0]] = pw
+    else:
+        W = W_loc
+
+    losses = [np.float64(v) for v in losses_arr]
+    if verbose > 0:                                        # same lines as _solver.py:165-166,172-173
+        for i in range(0, n_iter, 10):
+            print(f"Iter {i:4d}: Loss = {losses[i]:.6f}")
+        if converged:
+            print(f"Converged at iteration {n_iter - 1}")
+    if stats is not None:
+        isz = np.dtype(dtype).itemsize                     # factors cross PCIe in the compute dtype
+        stats.update(h2d_bytes=data.h2d_bytes + isz * (W_local.size + H_init.size), converged=converged,
+                     d2h_bytes=isz * (W_loc.size + H.size) + losses_arr.nbytes, world=world)
+
+    W_final, H_final = W, H                                # (m x k), (k x n) internal
+    if transpose:                                          # _solver.py:182-184
+        W_final, H_final = np.ascontiguousarray(H_final.T), np.ascontiguousarray(W_final.T)
+    W_final, H_final = final_simplex_cleanup(W_final, H_final, orientation)
+    return W_final, H_final, losses, 0.0, n_iter
+
+
+def nbmf_mm_update_beta_dir(Y, W, H, mask, alpha, beta, eps=1e-8, *, projection_method="normalize",
+                            mask_semantics="reference", dtype="float64", device=None):
+    """One MM iteration, drop-in for ``nbmf_mm._solver.nbmf_mm_update_beta_dir``
+    (``_solver.py:5-59``): ``W`` is ``k x m`` with columns on the simplex, ``H`` is ``k x n``;
+    returns ``(W_new (k x m), H_new (k x n))``.  H is updated first and the W step uses the new H."""
+    W = np.asarray(W, dtype=np.float64)
+    H = np.asarray(H, dtype=np.float64)
+    data = prepare_data(Y, mask, transpose=False, dtype=dtype, device=device)
+    k = W.shape[0]
+    prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
+                        projection=projection_method, max_iter_cap=1, device=device)
+    try:
+        prob.set_factors(np.ascontiguousarray(W.T), H, normalize_w=False)
+        prob.h_half_step()
+        prob.w_half_step()
+        W_new, H_new = prob.get_factors()
+    finally:
+        prob.close()
+    return np.ascontiguousarray(W_new.T), H_new

@@ -1,0 +1,114 @@
+"""Host-side logic of the drop-in estimator that needs no GPU: validation order and error
+messages, orientation aliases, bit packing, shard planning, the simplex clean-up tail."""
+import numpy as np
+import pytest
+
+from nbmf_mm_b200 import NBMF, NBMFMM, BitMatrix
+from nbmf_mm_b200.bits import words_per_row
+from nbmf_mm_b200.solver import _row_shard, final_simplex_cleanup
+from nbmf_mm_b200._utils import check_is_fitted, generate_synthetic_binary_data
+
+
+def test_constructor_matches_reference_signature():
+    est = NBMFMM()
+    p = est.get_params()
+    # reference defaults, _base.py:63-66
+    assert (p["n_components"], p["alpha"], p["beta"], p["max_iter"], p["tol"]) == (10, 1.2, 1.2, 2000, 1e-5)
+    assert p["orientation"] == "beta-dir" and p["W_init"] is None and p["init"] is None and p["verbose"] == 0
+    # README-only kwargs the reference lacks
+    assert p["projection_method"] == "normalize" and p["n_init"] == 1
+    assert NBMF is NBMFMM
+    from sklearn.base import clone
+    assert clone(NBMF(n_components=3, n_init=4)).get_params()["n_init"] == 4
+
+
+def test_non_binary_X_rejected_before_any_device_work():
+    with pytest.raises(ValueError, match="must be binary"):
+        NBMFMM(n_components=3).fit(np.random.default_rng(0).standard_normal((20, 10)))
+    with pytest.raises(ValueError):
+        NBMFMM(n_components=3).fit(np.array([[0.0, np.nan], [1.0, 0.0]]))
+    with pytest.raises(ValueError):
+        NBMFMM(n_components=3).fit(np.zeros(5))
+
+
+def test_orientation_aliases_exact_keys():
+    est = NBMF()
+    table = {"beta-dir": "beta-dir", "dir-beta": "dir-beta", "Beta-Dir": "beta-dir", "Dir-Beta": "dir-beta",
+             "Dir Beta": "dir-beta", "binary ICA": "beta-dir", "Binary ICA": "beta-dir", "bICA": "beta-dir",
+             "Aspect Bernoulli": "dir-beta"}
+    for alias, canon in table.items():
+        assert est._normalize_orientation(alias) == canon
+    for bad in ("Dir-Dir", "BETA-DIR", "aspect bernoulli", ""):
+        with pytest.raises(ValueError, match="Unknown orientation"):
+            est._normalize_orientation(bad)
+    X = (np.random.default_rng(0).random((8, 6)) < 0.4).astype(float)
+    with pytest.raises(ValueError, match="Unknown orientation"):
+        NBMF(n_components=2, orientation="Dir-Dir").fit(X)
+
+
+def test_unfitted_estimator_raises_like_reference():
+    with pytest.raises(ValueError, match="not fitted yet"):
+        NBMF().transform(np.zeros((3, 3)))
+    with pytest.raises(ValueError, match="not fitted yet"):
+        NBMF().inverse_transform(np.zeros((3, 10)))
+    with pytest.raises(ValueError, match="not fitted yet"):
+        check_is_fitted(NBMF(), "components_")
+
+
+def test_bitmatrix_roundtrip_and_layout():
+    rng = np.random.default_rng(1)
+    for m, n in [(1, 1), (3, 31), (5, 32), (7, 33), (9, 1024), (4, 1025), (50, 85)]:
+        A = rng.random((m, n)) < 0.4
+        B = BitMatrix.from_dense(A)
+        assert B.words.shape == (m, words_per_row(n)) and B.words.dtype == np.uint32
+        assert np.array_equal(B.to_dense(bool), A)
+        assert B.count() == int(A.sum())
+        # bit j of word j // 32, little-endian inside the word; padding is zero
+        i, j = m - 1, n - 1
+        assert ((int(B.words[i, j // 32]) >> (j % 32)) & 1) == int(A[i, j])
+        assert B.count() == int(np.unpackbits(B.words.view(np.uint8)).sum())
+        T = B.transpose()
+        assert T.shape == (n, m) and np.array_equal(T.to_dense(bool), A.T)
+    with pytest.raises(ValueError):
+        BitMatrix(np.zeros((3, 5), dtype=np.uint32), (3, 40))
+
+
+def test_row_shards_cover_everything_once():
+    for m in (1, 31, 32, 33, 1000, 1226, 10**6):
+        for world in (1, 2, 3, 4, 8):
+            spans = [_row_shard(m, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and max(s[1] for s in spans) == m
+            covered = sum(max(0, b - a) for a, b in spans)
+            assert covered == m
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 or b1 == b0        # contiguous; trailing ranks may be empty
+            assert all(a % 32 == 0 for a, b in spans if b > a)
+
+
+def test_final_simplex_cleanup_rules():
+    W = np.array([[0.2, 0.8], [0.5, 0.5000001], [0.0, 0.0]])
+    H = np.ones((2, 3))
+    W2, _ = final_simplex_cleanup(W.copy(), H.copy(), "beta-dir")
+    assert np.allclose(W2[:2].sum(axis=1), 1.0, atol=1e-15) and np.array_equal(W2[2], [0.0, 0.0])
+    ok = np.array([[0.25, 0.75], [0.5, 0.5 + 5e-10]])
+    W3, _ = final_simplex_cleanup(ok.copy(), H.copy(), "beta-dir")
+    assert np.array_equal(W3, ok)                  # deviation below 1e-9: untouched
+    Hd = np.array([[0.3, 0.6], [0.3, 0.6]])
+    _, H4 = final_simplex_cleanup(W.copy(), Hd.copy(), "dir-beta")
+    assert np.allclose(H4.sum(axis=0), 1.0)
+
+
+def test_synthetic_generator_contract():
+    X, W, H = generate_synthetic_binary_data(40, 25, 4, sparsity=0.3, random_state=7)
+    assert X.shape == (40, 25) and W.shape == (40, 4) and H.shape == (4, 25)
+    assert set(np.unique(X)) <= {0.0, 1.0} and set(np.unique(H)) <= {0.0, 1.0}
+    assert W.min() >= 0.1 and W.max() <= 0.9
+    X2, _, _ = generate_synthetic_binary_data(40, 25, 4, sparsity=0.3, random_state=7)
+    assert np.array_equal(X, X2)
+
+
+def test_import_shim_exposes_reference_names():
+    import nbmf_mm
+    from nbmf_mm import NBMF as A, NBMFMM as B, nbmf_mm_solver  # noqa: F401
+    from nbmf_mm._utils import generate_synthetic_binary_data as g  # noqa: F401
+    assert A is B and set(nbmf_mm.__all__) == {"NBMFMM", "NBMF", "nbmf_mm_solver"}
