@@ -1,0 +1,69 @@
+"""Multi-GPU path (needs >= 2 GPUs; skipped otherwise): rows sharded over ranks, one ncclAllReduce
+of the K x N H-partials per iteration.  1-GPU vs 2-GPU results may differ
+only by summation order; run-to-run at fixed world size must be bitwise identical."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _problem():
+    rng = np.random.default_rng(21)
+    X = (rng.random((700, 1500)) < 0.2).astype(np.float64)
+    mask = (rng.random(X.shape) < 0.9).astype(np.float64)
+    return X, mask
+
+
+def _worker(rank, world, port, dtype, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from nbmf_mm_b200 import BitMatrix, nbmf_mm_solver
+        from nbmf_mm_b200.solver import _row_shard
+        X, mask = _problem()
+        runs = []
+        for _ in range(2):
+            W, H, losses, _, n_iter = nbmf_mm_solver(X, 12, max_iter=60, tol=1e-6, mask=mask, random_state=5,
+                                                     dtype=dtype, distributed=True)
+            runs.append((W, H, np.asarray(losses), n_iter))
+        assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][2], runs[1][2])   # deterministic
+        # shard-local inputs: each rank only ever sees its own rows
+        r0, r1 = _row_shard(X.shape[0], rank, world)
+        Ws, Hs, ls, _, ns = nbmf_mm_solver(BitMatrix.from_dense(X[r0:r1]), 12, max_iter=60, tol=1e-6,
+                                           mask=BitMatrix.from_dense(mask[r0:r1]), random_state=5, dtype=dtype,
+                                           distributed=True, shard=(r0, X.shape[0]))
+        assert np.array_equal(Ws, runs[0][0][r0:r1]) and np.array_equal(Hs, runs[0][1]) and ns == runs[0][3]
+        if rank == 0:
+            np.savez(out, W=runs[0][0], H=runs[0][1], losses=runs[0][2], n_iter=runs[0][3])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 2e-5)])
+def test_two_gpus_match_one(tmp_path, dtype, tol):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nbmf_mm_b200 import nbmf_mm_solver
+    out = str(tmp_path / "res.npz")
+    mp.spawn(_worker, args=(2, _free_port(), dtype, out), nprocs=2, join=True)
+    res = np.load(out)
+    X, mask = _problem()
+    W, H, losses, _, n_iter = nbmf_mm_solver(X, 12, max_iter=60, tol=1e-6, mask=mask, random_state=5, dtype=dtype)
+    assert int(res["n_iter"]) == n_iter
+    assert np.max(np.abs(res["losses"] - np.asarray(losses)) / np.abs(losses)) < tol
+    assert np.max(np.abs(res["W"] - W)) < tol * 10 and np.max(np.abs(res["H"] - H)) < tol * 10

@@ -1,10 +1,19 @@
 """transform / inverse_transform / score / perplexity on the GPU against the golden vectors of the
-reference estimator (_base.py:162-265), including its RNG and mask quirks."""
+reference estimator (_base.py:162-265), including its RNG and mask quirks.
+
+The reference's transform starts from an UN-normalised W ~ U(0.1, 0.9) (_base.py:175), so
+Theta = W.H exceeds 1 for ~30 % of the entries in the first step and 1/(1 - Theta + eps) flips sign.
+For a few rows the 50-step map is then chaotic: a 1e-13 relative perturbation of W0 moves the
+REFERENCE's own output by up to 0.1 (measured on the oracle, see `stable_rows`).  Parity is
+therefore asserted at 1e-9 on the rows where the reference itself is stable, at 1e-9 on all
+rows from a simplex start, and the NLL of `score` is checked exactly on identical factors."""
 import numpy as np
 import pytest
 
+import nbmf_oracle as orc
 from conftest import rel_err
 from nbmf_mm_b200 import NBMF
+from nbmf_mm_b200.solver import make_problem, prepare_data
 
 pytestmark = pytest.mark.gpu
 
@@ -12,44 +21,71 @@ pytestmark = pytest.mark.gpu
 def fitted(datasets, golden_transform, dtype="float64"):
     est = NBMF(n_components=4, max_iter=80, tol=0.0, random_state=1, dtype=dtype).fit(datasets["animals"])
     assert rel_err(est.components_, golden_transform["components"]) < (1e-9 if dtype == "float64" else 1e-3)
+    est.components_ = golden_transform["components"]               # identical H: isolates transform / score
     return est
 
 
+def stable_rows(X, H, mask, W0, ref):
+    """Rows on which the reference map is insensitive to a 1e-13 relative perturbation of W0."""
+    ok = np.ones(X.shape[0], dtype=bool)
+    for seed in range(3):
+        Wp = W0 * (1 + 1e-13 * np.random.default_rng(seed).standard_normal(W0.shape))
+        ok &= np.abs(orc.transform(X, H, mask, Wp) - ref).max(axis=1) < 1e-10
+    return ok
+
+
 @pytest.mark.parametrize("tag", ["nomask", "mask"])
-def test_transform_matches_reference(datasets, golden_transform, tag):
+def test_transform_matches_reference_where_it_is_stable(datasets, golden_transform, tag):
     est = fitted(datasets, golden_transform)
-    est.components_ = golden_transform["components"]               # identical H: isolates transform
-    mk = None if tag == "nomask" else golden_transform["mask"]
+    X, g = datasets["animals"], golden_transform
+    mk = None if tag == "nomask" else g["mask"]
     np.random.seed(99)                                             # transform draws from the GLOBAL rng (_base.py:175)
-    Wt = est.transform(datasets["animals"], mask=mk)
-    assert Wt.shape == golden_transform[f"{tag}/Wt"].shape
-    assert rel_err(Wt, golden_transform[f"{tag}/Wt"]) < 1e-9
+    Wt = est.transform(X, mask=mk)
+    ref = g[f"{tag}/Wt"]
+    assert Wt.shape == ref.shape
+    ok = stable_rows(X, g["components"], mk, g[f"{tag}/W0"], ref)
+    assert ok.mean() > 0.8
+    assert rel_err(Wt[ok], ref[ok]) < 1e-9
     assert np.allclose(Wt.sum(axis=1), 1.0, atol=1e-12) and Wt.min() >= 0 and Wt.max() <= 1
     np.random.seed(99)
-    assert np.array_equal(est.transform(datasets["animals"], mask=mk), Wt)
-    assert not np.array_equal(est.transform(datasets["animals"], mask=mk), Wt)   # unseeded second call differs
+    assert np.array_equal(est.transform(X, mask=mk), Wt)              # same global seed -> same draw -> same bits
+    assert not np.array_equal(est.transform(X, mask=mk), Wt)          # unseeded second call differs, as in the reference
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 2e-5)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_fixed_h_w_solver_from_simplex_start(datasets, golden_transform, dtype, tol, masked):
+    """The same 50 fixed-H W steps + clip + renormalise (_base.py:178-198) from a well-posed start."""
+    X, H = datasets["animals"], golden_transform["components"]
+    mk = golden_transform["mask"] if masked else None
+    W0 = np.random.default_rng(3).dirichlet(np.ones(4), size=X.shape[0])
+    want = orc.transform(X, H, mk, W0)
+    data = prepare_data(X, mk, transpose=False, dtype=dtype, device=None)
+    with make_problem(data, 4, dtype=dtype, alpha=1.0, beta=1.0, eps=1e-8, mask_semantics="reference",
+                      projection="normalize", max_iter_cap=1, device=None) as prob:
+        prob.set_factors(W0, H, normalize_w=False)
+        prob.transform(50)
+        got, _ = prob.get_factors()
+    assert rel_err(got, want) < tol
+    assert np.allclose(got.sum(axis=1), 1.0, atol=1e-12 if dtype == "float64" else 1e-6)
 
 
 @pytest.mark.parametrize("tag", ["nomask", "mask"])
-def test_score_and_perplexity_match_reference(datasets, golden_transform, tag):
+def test_score_and_perplexity(datasets, golden_transform, tag):
     est = fitted(datasets, golden_transform)
-    est.components_ = golden_transform["components"]
-    mk = None if tag == "nomask" else golden_transform["mask"]
+    X, g = datasets["animals"], golden_transform
+    mk = None if tag == "nomask" else g["mask"]
     np.random.seed(99)
-    s = est.score(datasets["animals"], mask=mk)
-    assert isinstance(s, float) and abs(s - float(golden_transform[f"{tag}/score"])) < 1e-9 * abs(s)
+    W = est.transform(X)                                              # score() transforms WITHOUT the mask (_base.py:235)
     np.random.seed(99)
-    p = est.perplexity(datasets["animals"], mask=mk)
+    s = est.score(X, mask=mk)
+    assert isinstance(s, float)
+    want = orc.mean_loglik(X, orc.inverse_transform(W, g["components"]), mk)     # NLL part on identical factors
+    assert abs(s - want) < 1e-11 * abs(want)
+    assert abs(s - float(g[f"{tag}/score"])) < 0.05 * abs(s)          # end to end: limited by the chaotic rows only
+    np.random.seed(99)
+    p = est.perplexity(X, mask=mk)
     assert p >= 1.0 and abs(p - np.exp(-s)) < 1e-12 * p
-
-
-def test_fp32_transform_close(datasets, golden_transform):
-    est = fitted(datasets, golden_transform, dtype="float32")
-    est.components_ = golden_transform["components"]
-    np.random.seed(99)
-    Wt = est.transform(datasets["animals"])
-    assert rel_err(Wt, golden_transform["nomask/Wt"]) < 1e-4
-    assert np.allclose(Wt.sum(axis=1), 1.0, atol=1e-6)
 
 
 def test_transform_new_rows_and_feature_mismatch(datasets, golden_transform):
@@ -57,6 +93,8 @@ def test_transform_new_rows_and_feature_mismatch(datasets, golden_transform):
     Xnew = (np.random.default_rng(3).random((20, 85)) < 0.3).astype(float)
     W = est.transform(Xnew)
     assert W.shape == (20, 4) and np.all(W >= 0) and np.all(W <= 1)
+    Xhat = est.inverse_transform(W)
+    assert Xhat.shape == Xnew.shape and np.all((Xhat >= 0) & (Xhat <= 1))
     with pytest.raises(ValueError, match="features"):
         est.transform(np.zeros((5, 84)))
     # dir-beta models also use the beta-dir W step in transform, exactly like the reference
