@@ -50,6 +50,10 @@ extern "C" {
 #define NBMF_PROJ_NORMALIZE 0 /* multiplicative step, /n, L1 renormalisation (_solver.py:53-57) */
 #define NBMF_PROJ_DUCHI 1     /* multiplicative step / n_obs(row), Euclidean simplex projection; unpinned */
 
+#define NBMF_ENGINE_AUTO 0   /* tensor engine when eligible and m, n >= 512, else SIMT */
+#define NBMF_ENGINE_SIMT 1   /* packed-FFMA2 CUDA-core kernels: every dtype / K <= 64 / layout */
+#define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, 3xTF32 split: float32, bit-packed V, K <= 32, reference mask semantics */
+
 typedef struct nbmf_ctx nbmf_ctx;
 
 /* Problem description; replaces the keyword arguments of nbmf_mm_solver (_solver.py:61-75). */
@@ -66,7 +70,7 @@ typedef struct nbmf_config {
   double eps;            /* 1e-8 in the reference */
   double n_obs;          /* loss denominator: Y.size or count_nonzero(mask) over ALL shards (_solver.py:151,155) */
   int32_t max_iter_cap;  /* capacity of the on-device loss history */
-  int32_t reserved;
+  int32_t engine;        /* NBMF_ENGINE_AUTO | _SIMT | _TENSOR (env NBMF_ENGINE=auto|simt|tensor overrides) */
 } nbmf_config;
 
 int nbmf_version(void);
@@ -132,6 +136,8 @@ int nbmf_transform(nbmf_ctx* ctx, int32_t n_steps);
 int nbmf_comm_unique_id(void* id128_host);                          /* rank 0; 128 bytes */
 int nbmf_comm_init(nbmf_ctx* ctx, const void* id128_host, int32_t rank, int32_t world);
 int nbmf_comm_world(nbmf_ctx* ctx);
+/* engine actually selected for this context: NBMF_ENGINE_SIMT or NBMF_ENGINE_TENSOR */
+int nbmf_engine(nbmf_ctx* ctx);
 
 /* ---- measurement helpers ---- */
 /* sustained FMA-pipe throughput (TFLOP/s) of packed FFMA2 (dtype F32) or DFMA (F64); synchronises */

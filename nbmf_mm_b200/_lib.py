@@ -17,6 +17,8 @@ NBMF_F32, NBMF_F64, NBMF_U8 = 0, 1, 2
 NBMF_V_BITS, NBMF_V_DENSE = 0, 1
 NBMF_MASK_REFERENCE, NBMF_MASK_STRICT = 0, 1
 NBMF_PROJ_NORMALIZE, NBMF_PROJ_DUCHI = 0, 1
+NBMF_ENGINE_AUTO, NBMF_ENGINE_SIMT, NBMF_ENGINE_TENSOR = 0, 1, 2
+ENGINES = {"auto": NBMF_ENGINE_AUTO, "simt": NBMF_ENGINE_SIMT, "tensor": NBMF_ENGINE_TENSOR}
 
 
 class NbmfConfig(C.Structure):
@@ -24,7 +26,7 @@ class NbmfConfig(C.Structure):
         ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int32), ("dtype", C.c_int32),
         ("vkind", C.c_int32), ("mask_semantics", C.c_int32), ("projection", C.c_int32),
         ("has_mask", C.c_int32), ("alpha", C.c_double), ("beta", C.c_double), ("eps", C.c_double),
-        ("n_obs", C.c_double), ("max_iter_cap", C.c_int32), ("reserved", C.c_int32),
+        ("n_obs", C.c_double), ("max_iter_cap", C.c_int32), ("engine", C.c_int32),
     ]
 
 
@@ -60,6 +62,7 @@ SIGNATURES = {
     "nbmf_comm_unique_id": (_INT, [_P]),
     "nbmf_comm_init": (_INT, [_P, _P, _I32, _I32]),
     "nbmf_comm_world": (_INT, [_P]),
+    "nbmf_engine": (_INT, [_P]),
     "nbmf_fma_peak": (_INT, [_INT, _I32, _P, _P, C.POINTER(_DBL)]),
     "nbmf_profile_enable": (_INT, [_P, _INT]),
     "nbmf_profile_read": (_INT, [_P, C.POINTER(_DBL), C.POINTER(_I32), C.POINTER(_DBL), C.POINTER(_I32)]),

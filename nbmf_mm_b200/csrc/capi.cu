@@ -103,8 +103,11 @@ struct Plan {
   int h_ncb, h_nsplit, w_nsplit, n_prior;
   int64_t h_rows_per_split, w_cols_per_split;
   size_t sz;   // sizeof(Real)
+  bool tensor;           // tcgen05 engine (tc_passes.cuh) instead of the SIMT pass kernels
+  int64_t mpad, wpr_t;   // tensor engine: rows padded to 128, words per row of the transposed plane
   // workspace offsets
   size_t oW, oH, oHt, oCDpart, oCDsum, oLLpart, oLLsum, oPrior, oG, oQ, oRowcount, oHist, oState, oLoss, total;
+  size_t oWa, oWb, oHa, oHb, oPt;
 };
 
 struct nbmf_ctx {
@@ -139,10 +142,12 @@ struct nbmf_ctx {
 };
 
 static void prof_clear(std::vector<cudaEvent_t>& v);
+static int format_w(nbmf_ctx* c, bool guarded);
+static int format_h(nbmf_ctx* c, bool guarded);
 
-static int choose_split(int64_t blocks, int64_t max_split) {
+static int choose_split(int64_t blocks, int64_t max_split, int occ = 1) {
   if (max_split < 1) max_split = 1;
-  const double sms = 148.0;
+  const double sms = 148.0 * occ;
   int best = 1;
   double best_score = -1.0;
   for (int s = 1; s <= max_split; ++s) {
@@ -164,6 +169,19 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   const int strict = (c.mask_semantics == NBMF_MASK_STRICT && c.has_mask) ? 1 : 0;
   if (!lookup_pass(c.dtype, c.vkind == NBMF_V_DENSE, strict, c.k, &p->pl))
     return fail(NBMF_ERR_UNSUPPORTED, "no kernel variant for this (dtype, vkind, k)");
+  // engine: 0 = auto, 1 = SIMT (packed FFMA2), 2 = tensor (tcgen05, 3xTF32); NBMF_ENGINE overrides
+  int engine = c.engine;
+  if (const char* e = getenv("NBMF_ENGINE")) {
+    if (!strcmp(e, "simt")) engine = NBMF_ENGINE_SIMT;
+    else if (!strcmp(e, "tensor")) engine = NBMF_ENGINE_TENSOR;
+    else if (!strcmp(e, "auto")) engine = NBMF_ENGINE_AUTO;
+  }
+  const bool eligible = c.dtype == NBMF_F32 && c.vkind == NBMF_V_BITS && !strict && c.k <= 32;
+  if (engine == NBMF_ENGINE_TENSOR && !eligible)
+    return fail(NBMF_ERR_UNSUPPORTED, "tensor engine needs float32, bit-packed V, reference mask semantics and k <= 32");
+  p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR || (engine == NBMF_ENGINE_AUTO && c.m >= 512 && c.n >= 512));
+  if (p->tensor) { p->pl.kp = 32; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
+  const int occ = p->tensor ? 2 : 1;
   p->sz = c.dtype == NBMF_F32 ? 4 : 8;
   p->wpr = nbmf_words_per_row(c.n);
   p->ldh = p->wpr * 32;
@@ -173,12 +191,12 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   int64_t max_split = std::min<int64_t>(64, (c.m + 127) / 128);
   const size_t cd_one = (size_t)2 * kp * p->ldh * p->sz;
   while (max_split > 1 && cd_one * (size_t)max_split > ((size_t)2 << 30)) --max_split;
-  p->h_nsplit = choose_split(p->h_ncb, max_split);
+  p->h_nsplit = choose_split(p->h_ncb, max_split, occ);
   p->h_rows_per_split = ((c.m + p->h_nsplit - 1) / p->h_nsplit + 31) / 32 * 32;
   p->h_nsplit = (int)((c.m + p->h_rows_per_split - 1) / p->h_rows_per_split);
   // W pass: row blocks x column splits
   const int64_t nrb = (c.m + p->pl.w_bmr - 1) / p->pl.w_bmr;
-  p->w_nsplit = choose_split(nrb, std::min<int64_t>(32, (c.n + 127) / 128));
+  p->w_nsplit = choose_split(nrb, std::min<int64_t>(32, (c.n + 127) / 128), occ);
   p->w_cols_per_split = ((c.n + p->w_nsplit - 1) / p->w_nsplit + 127) / 128 * 128;
   p->w_nsplit = (int)((c.n + p->w_cols_per_split - 1) / p->w_cols_per_split);
   p->n_prior = h_epilogue_blocks(c.n, kp);
@@ -199,6 +217,16 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   p->oHist = take((size_t)(std::max(c.max_iter_cap, 1) + 2) * 8);
   p->oState = take(sizeof(FitState));
   p->oLoss = take(64);
+  p->mpad = (c.m + 127) / 128 * 128;
+  p->wpr_t = nbmf_words_per_row(c.m);
+  p->oWa = p->oWb = p->oHa = p->oHb = p->oPt = 0;
+  if (p->tensor) {
+    p->oWa = take((size_t)p->mpad * 32 * 2 * 4);
+    p->oWb = take((size_t)p->mpad * 32 * 2 * 4);
+    p->oHa = take((size_t)p->ldh * 32 * 2 * 4);
+    p->oHb = take((size_t)p->ldh * 32 * 2 * 4);
+    p->oPt = take((size_t)c.n * p->wpr_t * 4);
+  }
   p->total = o;
   return NBMF_OK;
 }
@@ -314,6 +342,10 @@ extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t
   c->P = P;
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
+  if (c->p.tensor) {   // the H pass of the tensor engine owns columns: it reads the transposed plane
+    launch_transpose_bits(P, c->cfg.m, c->cfg.n, c->p.wpr, c->at<uint32_t>(c->p.oPt), c->p.wpr_t, c->st);
+    CHECK_LAUNCH(1);
+  }
   return NBMF_OK;
 }
 extern "C" int nbmf_set_data_dense(nbmf_ctx* c, const void* Vm, const uint32_t* M) {
@@ -340,6 +372,9 @@ extern "C" int nbmf_set_factors(nbmf_ctx* c, const void* w, const void* h, int n
   CHECK_LAUNCH((w ? 1 : 0) + (h ? 1 : 0) + 1);
   c->enqueued = 0;
   c->tail_enqueued = false;
+  int rc;
+  if (w && (rc = format_w(c, false))) return rc;
+  if (h && (rc = format_h(c, false))) return rc;
   return NBMF_OK;
 }
 extern "C" int nbmf_get_factors(nbmf_ctx* c, void* w, void* h) {
@@ -350,6 +385,19 @@ extern "C" int nbmf_get_factors(nbmf_ctx* c, void* w, void* h) {
 }
 
 // ------------------------------------------------------------------------------------ steps
+static int format_w(nbmf_ctx* c, bool guarded) {
+  if (!c->p.tensor) return NBMF_OK;
+  launch_format_w(c->W(), c->cfg.m, c->p.mpad, c->ws + c->p.oWa, c->ws + c->p.oWb, guarded ? c->state() : nullptr, c->st);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+static int format_h(nbmf_ctx* c, bool guarded) {
+  if (!c->p.tensor) return NBMF_OK;
+  launch_format_h(c->H(), c->p.ldh, c->ws + c->p.oHa, c->ws + c->p.oHb, guarded ? c->state() : nullptr, c->st);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+
 static int allreduce(nbmf_ctx* c, bool with_cd) {
   if (c->world <= 1) return NBMF_OK;
   const size_t count = (size_t)2 * c->p.pl.kp * c->p.ldh;
@@ -385,7 +433,10 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd) {
   a.CD = c->ws + p.oCDpart; a.LL = c->at<double>(p.oLLpart);
   a.eps = c->cfg.eps; a.done = &c->state()->done; a.compute_cd = compute_cd;
   prof_mark(c, c->prof_h);
-  p.pl.h_launch(a, p.h_nsplit, c->st);
+  if (p.tensor)
+    launch_h_pass_tensor(a, c->ws + p.oHa, c->ws + p.oWa, c->ws + p.oWb, c->at<uint32_t>(p.oPt), p.wpr_t, p.h_nsplit, c->st);
+  else
+    p.pl.h_launch(a, p.h_nsplit, c->st);
   prof_mark(c, c->prof_h);
   const int64_t count = compute_cd ? (int64_t)2 * p.pl.kp * p.ldh : 0;
   launch_h_reduce(c->cfg.dtype, c->ws + p.oCDpart, p.h_nsplit, count, c->ws + p.oCDsum, c->at<double>(p.oLLpart),
@@ -399,7 +450,7 @@ static int enqueue_h_epilogue(nbmf_ctx* c) {
   launch_h_epilogue(c->cfg.dtype, c->ws + p.oCDsum, c->cfg.n, c->cfg.k, p.pl.kp, p.ldh, c->cfg.alpha, c->cfg.beta,
                     c->cfg.eps, c->H(), c->Ht(), c->at<double>(p.oPrior), c->state(), c->st);
   CHECK_LAUNCH(1);
-  return NBMF_OK;
+  return format_h(c, true);
 }
 
 static int enqueue_w_step(nbmf_ctx* c) {
@@ -415,13 +466,16 @@ static int enqueue_w_step(nbmf_ctx* c) {
   a.cols_per_split = p.w_cols_per_split;
   a.G = c->ws + p.oG; a.Q = c->ws + p.oQ; a.eps = c->cfg.eps; a.done = &c->state()->done;
   prof_mark(c, c->prof_w);
-  p.pl.w_launch(a, p.w_nsplit, c->st);
+  if (p.tensor)
+    launch_w_pass_tensor(a, c->ws + p.oWa, c->ws + p.oHa, c->ws + p.oHb, p.w_nsplit, c->st);
+  else
+    p.pl.w_launch(a, p.w_nsplit, c->st);
   prof_mark(c, c->prof_w);
   const void* rowcount = (c->cfg.projection == NBMF_PROJ_DUCHI && c->M) ? (const void*)(c->ws + p.oRowcount) : nullptr;
   launch_w_epilogue(c->cfg.dtype, c->ws + p.oG, c->ws + p.oQ, p.w_nsplit, c->cfg.m, c->cfg.n, c->cfg.k, p.pl.kp,
                     c->cfg.projection, rowcount, c->W(), c->state(), c->st);
   CHECK_LAUNCH(2);
-  return NBMF_OK;
+  return format_w(c, true);
 }
 
 extern "C" int nbmf_h_half_step(nbmf_ctx* c) {
@@ -579,7 +633,7 @@ extern "C" int nbmf_transform(nbmf_ctx* c, int32_t n_steps) {
     if ((rc = enqueue_w_step(c))) return rc;
   launch_clip_rows(c->cfg.dtype, c->W(), c->cfg.m, c->cfg.k, c->p.pl.kp, 1e-8, 1.0, c->st);
   CHECK_LAUNCH(1);
-  return NBMF_OK;
+  return format_w(c, false);
 }
 
 // ------------------------------------------------------------------------------------ comm
@@ -607,6 +661,7 @@ extern "C" int nbmf_comm_init(nbmf_ctx* c, const void* id128, int32_t rank, int3
   return NBMF_OK;
 }
 extern "C" int nbmf_comm_world(nbmf_ctx* c) { return c ? c->world : 0; }
+extern "C" int nbmf_engine(nbmf_ctx* c) { return !c ? 0 : (c->p.tensor ? NBMF_ENGINE_TENSOR : NBMF_ENGINE_SIMT); }
 
 // ------------------------------------------------------------------------------------ measurement
 static void prof_clear(std::vector<cudaEvent_t>& v) {

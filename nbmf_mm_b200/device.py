@@ -146,7 +146,7 @@ class DeviceProblem:
 
     def __init__(self, m, n, k, *, dtype="float64", vkind="bits", has_mask=False, alpha=1.2, beta=1.2,
                  eps=1e-8, n_obs=None, mask_semantics="reference", projection="normalize",
-                 max_iter_cap=2000, device=None):
+                 max_iter_cap=2000, device=None, engine="auto"):
         torch = _torch()
         self.lib = _lib.load()
         self.dev = require_cuda(device)
@@ -167,6 +167,9 @@ class DeviceProblem:
         cfg.alpha, cfg.beta, cfg.eps = float(alpha), float(beta), float(eps)
         cfg.n_obs = float(self.m * self.n if n_obs is None else n_obs)
         cfg.max_iter_cap = int(max_iter_cap)
+        if engine not in _lib.ENGINES:
+            raise ValueError(f"engine must be one of {sorted(_lib.ENGINES)}, got {engine!r}")
+        cfg.engine = _lib.ENGINES[engine]
         self.cfg = cfg
         nbytes = self.lib.nbmf_workspace_bytes(C.byref(cfg))
         if nbytes < 0:
@@ -178,6 +181,7 @@ class DeviceProblem:
                                             C.byref(self._ctx)), "nbmf_create")
         self._keep = []          # tensors the context borrows
         self.world = 1
+        self.engine = "tensor" if self.lib.nbmf_engine(self._ctx) == _lib.NBMF_ENGINE_TENSOR else "simt"
 
     # -- lifetime
     def close(self):

@@ -49,12 +49,14 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         "reference" reproduces the reference's H-step/loss treatment of unobserved entries as
         observed zeros (``_solver.py:43,153-154``); "strict" is the README/paper behaviour.
     device : torch device or None;  distributed : bool, row-shard over torch.distributed.
+    engine : {"auto", "simt", "tensor"}: CUDA-core (packed FFMA2) kernels or the tcgen05/TMEM 3xTF32
+        kernels (float32, binary X, K <= 32 only); "auto" picks tensor when eligible and m, n >= 512.
     """
 
     def __init__(self, n_components=10, alpha=1.2, beta=1.2, max_iter=2000, tol=1e-5,
                  W_init=None, H_init=None, init=None, random_state=None, verbose=0,
                  orientation="beta-dir", projection_method="normalize", n_init=1,
-                 dtype="float64", mask_semantics="reference", device=None, distributed=False):
+                 dtype="float64", mask_semantics="reference", device=None, distributed=False, engine="auto"):
         self.n_components = n_components
         self.alpha = alpha
         self.beta = beta
@@ -72,6 +74,7 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         self.mask_semantics = mask_semantics
         self.device = device
         self.distributed = distributed
+        self.engine = engine
 
     # ------------------------------------------------------------------ helpers
     def _normalize_orientation(self, orientation):
@@ -112,7 +115,8 @@ class NBMFMM(BaseEstimator, TransformerMixin):
                 alpha=self.alpha, beta=self.beta, W_init=self.W_init, H_init=self.H_init, mask=mask,
                 random_state=seed, verbose=self.verbose, orientation=orientation,
                 projection_method=self.projection_method, mask_semantics=self.mask_semantics,
-                dtype=self.dtype, device=self.device, distributed=self.distributed, stats=stats)
+                dtype=self.dtype, device=self.device, distributed=self.distributed, stats=stats,
+                engine=self.engine)
             if best is None or out[2][-1] < best[0][2][-1]:
                 best = (out, stats, r)
         (W, H, losses, _, n_iter), stats, best_r = best
@@ -139,7 +143,7 @@ class NBMFMM(BaseEstimator, TransformerMixin):
             raise ValueError(f"X has {data.n} features, the model was fitted with {self.components_.shape[1]}")
         prob = make_problem(data, self.n_components, dtype=self.dtype, alpha=1.0, beta=1.0, eps=1e-8,
                             mask_semantics="reference", projection="normalize", max_iter_cap=1,
-                            device=self.device, n_obs=n_obs)
+                            device=self.device, n_obs=n_obs, engine=self.engine)
         return data, prob
 
     def _transform_device(self, X, mask):

@@ -106,11 +106,11 @@ def prepare_data(Y, mask, *, transpose, dtype, device) -> PreparedData:
 
 
 def make_problem(data: PreparedData, k, *, dtype, alpha, beta, eps, mask_semantics, projection, max_iter_cap,
-                 device, n_obs=None) -> DeviceProblem:
+                 device, n_obs=None, engine="auto") -> DeviceProblem:
     prob = DeviceProblem(data.m, data.n, k, dtype=dtype, vkind=data.vkind, has_mask=data.M is not None,
                          alpha=alpha, beta=beta, eps=eps, n_obs=data.n_obs if n_obs is None else n_obs,
                          mask_semantics=mask_semantics, projection=projection, max_iter_cap=max_iter_cap,
-                         device=device)
+                         device=device, engine=engine)
     if data.vkind == "bits":
         prob.set_bits(data.P, data.M)
     else:
@@ -152,7 +152,7 @@ def _row_shard(m, rank, world):
 def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2, W_init=None, H_init=None,
                    mask=None, random_state=None, verbose=0, orientation="beta-dir", eps=1e-8, *,
                    projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
-                   distributed=False, shard=None, stats=None):
+                   distributed=False, shard=None, stats=None, engine="auto"):
     """NBMF-MM solver, drop-in for ``nbmf_mm._solver.nbmf_mm_solver`` (``_solver.py:61-216``).
 
     Returns ``(W (m x k), H (k x n), losses, 0.0, n_iter)`` exactly as the reference does
@@ -162,7 +162,9 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     ``distributed`` (row-shard over the default ``torch.distributed`` group, one rank per GPU:
     every rank passes the FULL ``Y`` and gets the full result), ``shard=(row0, m_total)`` (with
     ``distributed``: ``Y``/``mask`` are already this rank's row block of an ``m_total``-row
-    problem in internal orientation; the returned W is the local block, H is global).
+    problem in internal orientation; the returned W is the local block, H is global),
+    ``engine`` ("auto" | "simt" | "tensor": packed-FFMA2 CUDA-core kernels or the tcgen05/TMEM
+    3xTF32 kernels; the tensor engine needs float32, binary V, K <= 32).
     """
     if orientation not in _CANON:
         raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
@@ -216,7 +218,8 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         W_local = W_init
 
     prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
-                        projection=projection_method, max_iter_cap=max_iter, device=device, n_obs=n_obs_global)
+                        projection=projection_method, max_iter_cap=max_iter, device=device, n_obs=n_obs_global,
+                        engine=engine)
     try:
         if world > 1:
             prob.init_comm()
@@ -247,7 +250,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     if stats is not None:
         isz = np.dtype(dtype).itemsize                     # factors cross PCIe in the compute dtype
         stats.update(h2d_bytes=data.h2d_bytes + isz * (W_local.size + H_init.size), converged=converged,
-                     d2h_bytes=isz * (W_loc.size + H.size) + losses_arr.nbytes, world=world)
+                     d2h_bytes=isz * (W_loc.size + H.size) + losses_arr.nbytes, world=world, engine=prob.engine)
 
     W_final, H_final = W, H                                # (m x k), (k x n) internal
     if transpose:                                          # _solver.py:182-184
@@ -257,7 +260,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
 
 
 def nbmf_mm_update_beta_dir(Y, W, H, mask, alpha, beta, eps=1e-8, *, projection_method="normalize",
-                            mask_semantics="reference", dtype="float64", device=None):
+                            mask_semantics="reference", dtype="float64", device=None, engine="auto"):
     """One MM iteration, drop-in for ``nbmf_mm._solver.nbmf_mm_update_beta_dir``
     (``_solver.py:5-59``): ``W`` is ``k x m`` with columns on the simplex, ``H`` is ``k x n``;
     returns ``(W_new (k x m), H_new (k x n))``.  H is updated first and the W step uses the new H."""
@@ -266,7 +269,7 @@ def nbmf_mm_update_beta_dir(Y, W, H, mask, alpha, beta, eps=1e-8, *, projection_
     data = prepare_data(Y, mask, transpose=False, dtype=dtype, device=device)
     k = W.shape[0]
     prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
-                        projection=projection_method, max_iter_cap=1, device=device)
+                        projection=projection_method, max_iter_cap=1, device=device, engine=engine)
     try:
         prob.set_factors(np.ascontiguousarray(W.T), H, normalize_w=False)
         prob.h_half_step()

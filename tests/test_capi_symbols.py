@@ -55,9 +55,16 @@ def test_workspace_planning_is_deterministic_and_sane():
     cfg = _lib.NbmfConfig()
     cfg.m, cfg.n, cfg.k, cfg.dtype, cfg.vkind = 1_000_000, 100_000, 32, 0, 0
     cfg.has_mask, cfg.alpha, cfg.beta, cfg.eps, cfg.n_obs, cfg.max_iter_cap = 1, 1.2, 1.2, 1e-8, 9e10, 50
+    cfg.engine = _lib.NBMF_ENGINE_SIMT
     a = lib.nbmf_workspace_bytes(ctypes.byref(cfg))
     b = lib.nbmf_workspace_bytes(ctypes.byref(cfg))
     assert a == b and 128e6 < a < 8e9          # W alone is 128 MB; partial buffers stay bounded
+    cfg.engine = _lib.NBMF_ENGINE_TENSOR       # + transposed bit plane (12.5 GB) and the split/swizzled factor blocks
+    t = lib.nbmf_workspace_bytes(ctypes.byref(cfg))
+    assert a + 12.5e9 < t < a + 15e9
+    cfg.dtype = 1                              # the tensor engine is float32 only
+    assert lib.nbmf_workspace_bytes(ctypes.byref(cfg)) < 0 and b"tensor engine" in lib.nbmf_last_error()
+    cfg.dtype, cfg.engine = 0, _lib.NBMF_ENGINE_AUTO
     cfg.k = 0
     assert lib.nbmf_workspace_bytes(ctypes.byref(cfg)) < 0
 
