@@ -104,10 +104,10 @@ struct Plan {
   int64_t h_rows_per_split, w_cols_per_split;
   size_t sz;   // sizeof(Real)
   bool tensor;           // tcgen05 engine (tc_passes.cuh) instead of the SIMT pass kernels
-  int64_t mpad, wpr_t;   // tensor engine: rows padded to 128, words per row of the transposed plane
+  int64_t mpad;          // tensor engine: rows padded to 128
   // workspace offsets
   size_t oW, oH, oHt, oCDpart, oCDsum, oLLpart, oLLsum, oPrior, oG, oQ, oRowcount, oHist, oState, oLoss, total;
-  size_t oWa, oWb, oHa, oHb, oPt;
+  size_t oWf, oHf, oPc, oPM;   // tensor engine: formatted factor blocks and re-tiled bit planes
 };
 
 struct nbmf_ctx {
@@ -176,12 +176,14 @@ static int make_plan(const nbmf_config& c, Plan* p) {
     else if (!strcmp(e, "tensor")) engine = NBMF_ENGINE_TENSOR;
     else if (!strcmp(e, "auto")) engine = NBMF_ENGINE_AUTO;
   }
-  const bool eligible = c.dtype == NBMF_F32 && c.vkind == NBMF_V_BITS && !strict && c.k <= 32;
+  // eps >= 1e-9: the tensor H pass takes one log per product of four x >= eps (no underflow)
+  const bool eligible = c.dtype == NBMF_F32 && c.vkind == NBMF_V_BITS && !strict && c.k <= 32 && c.eps >= 1e-9;
   if (engine == NBMF_ENGINE_TENSOR && !eligible)
-    return fail(NBMF_ERR_UNSUPPORTED, "tensor engine needs float32, bit-packed V, reference mask semantics and k <= 32");
+    return fail(NBMF_ERR_UNSUPPORTED,
+                "tensor engine needs float32, bit-packed V, reference mask semantics, k <= 32 and eps >= 1e-9");
   p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR || (engine == NBMF_ENGINE_AUTO && c.m >= 512 && c.n >= 512));
   if (p->tensor) { p->pl.kp = 32; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
-  const int occ = p->tensor ? 2 : 1;
+  const int occ = 1;
   p->sz = c.dtype == NBMF_F32 ? 4 : 8;
   p->wpr = nbmf_words_per_row(c.n);
   p->ldh = p->wpr * 32;
@@ -218,14 +220,12 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   p->oState = take(sizeof(FitState));
   p->oLoss = take(64);
   p->mpad = (c.m + 127) / 128 * 128;
-  p->wpr_t = nbmf_words_per_row(c.m);
-  p->oWa = p->oWb = p->oHa = p->oHb = p->oPt = 0;
+  p->oWf = p->oHf = p->oPc = p->oPM = 0;
   if (p->tensor) {
-    p->oWa = take((size_t)p->mpad * 32 * 2 * 4);
-    p->oWb = take((size_t)p->mpad * 32 * 2 * 4);
-    p->oHa = take((size_t)p->ldh * 32 * 2 * 4);
-    p->oHb = take((size_t)p->ldh * 32 * 2 * 4);
-    p->oPt = take((size_t)c.n * p->wpr_t * 4);
+    p->oWf = take((size_t)p->mpad * 128 * 4);
+    p->oHf = take((size_t)p->ldh * 128 * 4);
+    p->oPc = take((size_t)p->ldh * p->mpad / 8);
+    p->oPM = take((size_t)p->mpad * p->wpr * 8);
   }
   p->total = o;
   return NBMF_OK;
@@ -342,9 +342,9 @@ extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t
   c->P = P;
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
-  if (c->p.tensor) {   // the H pass of the tensor engine owns columns: it reads the transposed plane
-    launch_transpose_bits(P, c->cfg.m, c->cfg.n, c->p.wpr, c->at<uint32_t>(c->p.oPt), c->p.wpr_t, c->st);
-    CHECK_LAUNCH(1);
+  if (c->p.tensor) {   // the tensor kernels read planes re-tiled per TMEM lane (format_factors.cu)
+    launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, c->at<uint32_t>(c->p.oPc), c->ws + c->p.oPM, c->st);
+    CHECK_LAUNCH(2);
   }
   return NBMF_OK;
 }
@@ -387,13 +387,13 @@ extern "C" int nbmf_get_factors(nbmf_ctx* c, void* w, void* h) {
 // ------------------------------------------------------------------------------------ steps
 static int format_w(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;
-  launch_format_w(c->W(), c->cfg.m, c->p.mpad, c->ws + c->p.oWa, c->ws + c->p.oWb, guarded ? c->state() : nullptr, c->st);
+  launch_format_w(c->W(), c->cfg.m, c->p.mpad, c->ws + c->p.oWf, guarded ? c->state() : nullptr, c->st);
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }
 static int format_h(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;
-  launch_format_h(c->H(), c->p.ldh, c->ws + c->p.oHa, c->ws + c->p.oHb, guarded ? c->state() : nullptr, c->st);
+  launch_format_h(c->H(), c->p.ldh, c->ws + c->p.oHf, guarded ? c->state() : nullptr, c->st);
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }
@@ -434,7 +434,7 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd) {
   a.eps = c->cfg.eps; a.done = &c->state()->done; a.compute_cd = compute_cd;
   prof_mark(c, c->prof_h);
   if (p.tensor)
-    launch_h_pass_tensor(a, c->ws + p.oHa, c->ws + p.oWa, c->ws + p.oWb, c->at<uint32_t>(p.oPt), p.wpr_t, p.h_nsplit, c->st);
+    launch_h_pass_tensor(a, c->ws + p.oWf, c->at<uint32_t>(p.oPc), p.mpad / 32, p.h_nsplit, c->st);
   else
     p.pl.h_launch(a, p.h_nsplit, c->st);
   prof_mark(c, c->prof_h);
@@ -467,7 +467,7 @@ static int enqueue_w_step(nbmf_ctx* c) {
   a.G = c->ws + p.oG; a.Q = c->ws + p.oQ; a.eps = c->cfg.eps; a.done = &c->state()->done;
   prof_mark(c, c->prof_w);
   if (p.tensor)
-    launch_w_pass_tensor(a, c->ws + p.oWa, c->ws + p.oHa, c->ws + p.oHb, p.w_nsplit, c->st);
+    launch_w_pass_tensor(a, c->ws + p.oHf, c->ws + p.oPM, p.w_nsplit, c->st);
   else
     p.pl.w_launch(a, p.w_nsplit, c->st);
   prof_mark(c, c->prof_w);

@@ -81,6 +81,25 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) 
                ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t (&v)[32]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+               "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+               ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                 "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                 "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+
+// One lane of a fully converged warp.  The MMA / bulk-copy issue loops run warp-uniformly and only
+// guard the instruction itself with this predicate: operands then live in uniform registers.  Issuing
+// from a divergent `if (tid == x)` region instead makes the compiler wrap every tcgen05.mma in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall, measured at 54 cycles per MMA (tools/tc_bench.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}\n" : "=r"(p));
+  return p != 0;
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -92,21 +111,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a lost arrival traps (CUDA error) instead of hanging the GPU.
+// Bounded wait: a lost arrival traps (CUDA error) instead of hanging the GPU.  try_wait suspends the thread in
+// hardware for a while before it reports failure, so 2^24 failed probes are far beyond any legitimate wait.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (ok) return;
-    if ((spin & 1023u) == 1023u) {                        // ~4 s at 2 GHz: far beyond any legitimate wait
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 8000000000ll) __trap();
-    }
-  }
+  if (mbar_try(addr, parity)) return;
+  for (uint32_t spin = 0; !mbar_try(addr, parity); ++spin)
+    if (spin > (1u << 24)) __trap();
 }
 // 1-D bulk copy global -> shared (TMA engine, no tensor map), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -1,22 +1,33 @@
 // Tensor-core (tcgen05 / TMEM) versions of the two pass kernels for K <= 32, fp32, bit-packed V.
 //
 // Same math as passes.cuh, restructured like attention on Blackwell (S = QK^T -> P -> O = PV):
-//   MMA1  Theta tile = factor tile . streamed factor block          (tcgen05.mma, SS, accumulate in TMEM)
+//   MMA1  Theta tile = resident factor tile [TMEM] . streamed factor block [smem]   (tcgen05.mma, TS form)
 //   SIMT  tcgen05.ld Theta -> masked ratio in registers -> tcgen05.st back to TMEM
-//   MMA2  accumulator (+)= ratio[TMEM] . streamed factor block       (tcgen05.mma, TS: A operand from TMEM)
-// fp32 accuracy comes from a 3-term TF32 split: x = hi + lo with hi = tf32(x) (the tensor core reads
-// only the top 19 bits), lo = x - hi, and a.b ~ hi.hi + hi.lo + lo.hi (measured ~1.5e-6 relative,
-// tools/tc_probe.cu).  Operand blocks are pre-split and pre-swizzled in global memory by the epilogue
-// kernels (format_factors.cu), so every shared-memory stage is filled by plain 1-D bulk copies
-// (cp.async.bulk + mbarrier complete_tx): no tensor maps, no swizzling in the hot loop.
+//   MMA2  accumulator (+)= ratio [TMEM] . streamed factor block [smem]               (tcgen05.mma, TS form)
+// Both MMAs take their A operand from TMEM: an SS-form MMA with a 128-row A tile re-reads 4 KB of shared
+// memory per K step and is bound by the 128 B/clk shared-memory port (40 clk per N=32 MMA, measured),
+// the TS form runs at the tensor pipe's 16 clk (tools/tc_bench.cu).
 //
-// One persistent-style CTA per SM: 16 SIMT warps + 1 control warp.  SIMT warp w works on TMEM lane
-// quarter (w & 3) -- the hardware restricts a warp to lanes 32*(warp % 4).. -- and on slice (w >> 2)
-// of every block's columns, so four warps per scheduler hide each other's MUFU / TMEM latencies.
-// Theta and the ratio regions are double buffered in TMEM: while the SIMT warps work on block b the
-// tensor pipe runs MMA2(b-1) and MMA1(b+1).  The TMEM accumulators are flushed into fp32 shared-memory
-// accumulators every kFlush blocks because the tensor core's accumulate truncates: an unbroken chain of
-// 3e4 accumulations drifts by ~1e-4 relative (measured), a chain of a few hundred by ~1e-6.
+// fp32 accuracy comes from a 3-term TF32 split: x = hi + lo with hi = x truncated to tf32 (what the
+// tensor core reads), lo = x - hi, and a.b ~ hi.hi + hi.lo + lo.hi (~1e-6 relative, tools/tc_probe.cu).
+// The streamed operand blocks are pre-split and pre-swizzled in global memory by format_factors.cu, so
+// each pipeline stage is ONE 1-D bulk copy (cp.async.bulk + mbarrier complete_tx): no tensor maps.
+//
+// CTA = 21 warps, one CTA per SM (it owns all 512 TMEM columns).  The streamed blocks are dealt to two
+// independent pipelines ("groups"): group g owns blocks b = g, g+2, .., its own Theta and ratio regions
+// and its own accumulators in TMEM, eight SIMT warps and two issuing warps.  While one group sits in the
+// fixed latencies of a block (barrier round trips, TMEM loads and stores, MMA completion) the other one
+// computes, which is what keeps both the issue slots and the tensor pipe busy.
+//   warps 0..15   SIMT.  Warp w works on TMEM lane quarter (w & 3) -- the hardware restricts a warp to
+//                 lanes 32*(w % 4).. --, group g = (w >> 2) & 1 and half h = w >> 3 of the block's columns.
+//   warps 16, 17  MMA1 issuer of group 0 / 1;  warps 18, 19  MMA2 issuer of group 0 / 1.  The whole warp runs
+//                 the loop (uniform control flow, operands in uniform registers); one elected lane executes
+//                 the tcgen05.mma / commit instructions.  One warp cannot issue everything: its barrier waits
+//                 and commits are serial and cost ~200 clk each (measured with tools/tc_trace.cu).
+//   warp 20       bulk-copy producer for the shared-memory stages (shared by both groups).
+// The tensor core's fp32 accumulate truncates, so an unbroken chain of 3e4 accumulations drifts by ~1e-4
+// relative (measured); each group's TMEM accumulators are flushed into fp32 registers by the group's own
+// SIMT warps every kFlush blocks, just before they release the first block of the next chain.
 #pragma once
 #include "args.h"
 #include "common.cuh"
@@ -24,29 +35,24 @@
 
 namespace nbmf {
 
-struct TcFactors {
-  const float* Ha;   // [ldh/64][hi|lo][64 rows j x 32 k]            Ht blocks, K-major, SW128
-  const float* Hb;   // [ldh/64][hi|lo][2 K-blocks][32 rows k x 32 j] H blocks
-  const float* Wa;   // [mpad/64][hi|lo][64 rows i x 32 k]           W blocks
-  const float* Wb;   // [mpad/64][hi|lo][2 K-blocks][32 rows k x 32 i] W^T blocks
-};
-
-struct WTcArgs {
-  TcFactors f;
-  const uint32_t* P;
-  const uint32_t* M;
-  int64_t m, n, wpr;
-  int64_t cols_per_split;    // multiple of 64
-  float* G;                  // [nsplit][m][32]
-  float* Q;                  // [nsplit][m]
-  float eps;
-  const int* done;
-};
+// Optional cycle trace of CTA (0,0) (tools/tc_trace.cu defines TC_TRACE): event e of warp slot w at block b.
+#ifdef TC_TRACE
+__device__ long long* g_tc_trace = nullptr;       // [4 warp slots][TC_TRACE_BLOCKS][8 events]
+#define TC_TRACE_BLOCKS 256
+#define TC_EV(slot, b, e)                                                                                     \
+  do {                                                                                                        \
+    if (g_tc_trace && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (b) < TC_TRACE_BLOCKS) \
+      g_tc_trace[((slot) * TC_TRACE_BLOCKS + (b)) * 8 + (e)] = clock64();                                     \
+  } while (0)
+#else
+#define TC_EV(slot, b, e) do { } while (0)
+#endif
 
 struct HTcArgs {
-  TcFactors f;
-  const uint32_t* Pt;        // transposed plane: [n][wpr_t], bit i of row j = P[i][j]
-  int64_t m, n, ldh, wpr_t;
+  const float* H;            // [32][ldh] k-major factor (pad rows/columns 0.5): source of the resident A tile
+  const float* Wf;           // [mpad/32][4][1024]  W rows hi | lo | W^T hi | lo   (format_factors.cu)
+  const uint32_t* Pc;        // [ldh/128][nrb][128] bit r of word (jt, rb, jj) = P[32 rb + r][128 jt + jj]
+  int64_t m, n, ldh, nrb;
   int64_t rows_per_split;    // multiple of 32
   float* CD;                 // [nsplit][2][32][ldh]
   double* LL;                // [nsplit * gridDim.x]
@@ -55,37 +61,52 @@ struct HTcArgs {
   int compute_cd;
 };
 
+struct WTcArgs {
+  const float* W;            // [m][32] row-major factor: source of the resident A tile
+  const float* Hf;           // [ldh/64][4][2048]  Ht rows hi | lo | H (2 K-blocks) hi | lo
+  const uint2* PM;           // [mpad/128][wpr][128] {P word, observed word} of row 128 it + ii, columns 32 cw..
+  int64_t m, n, wpr;
+  int64_t cols_per_split;    // multiple of 64
+  float* G;                  // [nsplit][m][32]
+  float* Q;                  // [nsplit][m]
+  float eps;
+  const int* done;
+};
+
 constexpr int TC_SIMT_WARPS = 16;
-constexpr int TC_THREADS = (TC_SIMT_WARPS + 1) * 32;   // + control warp
-constexpr int TC_CTRL_TID = TC_SIMT_WARPS * 32;
-constexpr int TC_BLK_FLOATS = 64 * 32;                  // one hi (or lo) 64-row operand block
-constexpr int TC_STAGES = 4;
-constexpr int kFlush = 16;                              // blocks per TMEM accumulation chain
+constexpr int TC_MMA1_WARP = 16;                        // + group
+constexpr int TC_MMA2_WARP = 18;                        // + group
+constexpr int TC_TMA_WARP = 20;
+constexpr int TC_THREADS = 21 * 32;
+constexpr int kFlush = 8;                               // own blocks per TMEM accumulation chain
 
 // =====================================================================================
-// H pass (thread = column j = TMEM lane).  CTA = 128 columns j, streams 32-row blocks of W.
-//   MMA1: Theta^T[128 j x 32 i] = Ht[128x32] . W[32x32]^T
-//   SIMT: bit i of the transposed plane Pt; rp / rn ratios (hi, lo) -> TMEM; fused NLL in registers
-//   MMA2: C^T[128 j x 32 k] += Rp[128 x 32 i] . W^T[32 k x 32 i]^T   (and D^T with Rn)
-// TMEM: Theta[2] 0..63 | R[2] = {Rp_hi, Rp_lo, Rn_hi, Rn_lo} x 32 at 64..191, 192..319 | C 320..351 | D 352..383
+// H pass (TMEM lane = column j).  CTA = 128 columns j, streams 32-row blocks of W.
+//   MMA1: Theta^T[128 j x 32 i] = Ht[128 x 32 k] . W[32 i x 32 k]^T
+//   SIMT: bit i of the column-tiled plane Pc; r = 1/x; planes Rp = [p] r and R = r (hi, lo each);
+//         fused NLL: one MUFU.LG2 per product of four x
+//   MMA2: C^T[128 j x 32 k] += Rp[128 x 32 i] . W^T[32 k x 32 i]^T,  S^T += R . W^T;  D = S - C at the end
+// TMEM: A hi 0..31, lo 32..63 | Theta[g] 64..127 | R[g] 128..383 (per 8 rows: Rp_hi Rp_lo R_hi R_lo)
+//       | {C, S}[g] 384..511
 // =====================================================================================
-constexpr int HTC_STAGE_BYTES = 16384;                  // W rows hi|lo (8 KB) + W^T K-block hi|lo (8 KB)
-constexpr int HTC_OFF_STAGE = 32768;
-constexpr int HTC_OFF_ACC = HTC_OFF_STAGE + TC_STAGES * HTC_STAGE_BYTES;
-constexpr int HTC_SMEM = HTC_OFF_ACC + 64 * 128 * 4 + 1024;
+constexpr int HTC_STAGES = 6;
+constexpr int HTC_STAGE_BYTES = 16384;
+constexpr int HTC_OFF_ACC = HTC_STAGES * HTC_STAGE_BYTES;        // fp32 accumulators [32][512 SIMT threads]
+constexpr int HTC_SMEM = HTC_OFF_ACC + 32 * 512 * 4 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs a) {
   using namespace tc;
   if (*a.done) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sH = smem;                                         // Ht tile [hi 16 KB][lo 16 KB], 128 rows j
-  float* sAcc = reinterpret_cast<float*>(smem + HTC_OFF_ACC);       // [64 accumulator columns][128 lanes]
-  __shared__ uint64_t bar_h, bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_theta[2], bar_s[2], bar_cd;
+  float* sAcc = reinterpret_cast<float*>(smem + HTC_OFF_ACC);      // thread t: 16 C then 16 S sums at [e * 512 + t]
+  __shared__ uint64_t bar_full[HTC_STAGES], bar_empty[HTC_STAGES];
+  __shared__ uint64_t bar_a, bar_theta[2], bar_tfree[2], bar_s[2], bar_rfree[2], bar_cd[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ double red_scratch[TC_THREADS / 32];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // provably warp-uniform
   const int64_t jb = (int64_t)blockIdx.x * 128;
   const int split = blockIdx.y;
   const int64_t r0 = (int64_t)split * a.rows_per_split;
@@ -93,180 +114,247 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   const int nb = r1 > r0 ? (int)((r1 - r0 + 31) / 32) : 0;
   const bool cd = a.compute_cd != 0;
 
-  for (int e = tid; e < 64 * 128; e += TC_THREADS) sAcc[e] = 0.0f;
-  if (warp == TC_SIMT_WARPS) tmem_alloc(&tmem_base_s, 512);
-  if (tid == TC_CTRL_TID) {
-    mbar_init(&bar_h, 1);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    mbar_init(&bar_theta[0], 1); mbar_init(&bar_theta[1], 1);
-    mbar_init(&bar_s[0], TC_SIMT_WARPS); mbar_init(&bar_s[1], TC_SIMT_WARPS);
-    mbar_init(&bar_cd, 1);
+  if (warp == TC_TMA_WARP) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int s = 0; s < HTC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_a, TC_SIMT_WARPS);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bar_theta[g], 1); mbar_init(&bar_tfree[g], TC_SIMT_WARPS / 2);
+      mbar_init(&bar_s[g], TC_SIMT_WARPS / 2); mbar_init(&bar_rfree[g], 1); mbar_init(&bar_cd[g], 1);
+    }
     mbar_fence_init();
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
-  const uint32_t tTheta = tb, tR = tb + 64, tC = tb + 320, tD = tb + 352;
-  const int nflush = nb > 0 ? (nb - 1) / kFlush : 0;                // mid-pass flushes before the final one
+  const uint32_t tA = tb, tTheta = tb + 64, tR = tb + 128, tAcc = tb + 384;
+  constexpr uint32_t id = idesc_tf32(128, 32);
 
   double ll_total = 0.0;
-  if (tid == TC_CTRL_TID) {
-    // ------------------------------------------------------------- control thread
-    const int64_t hblk = jb / 64;
-    mbar_expect_tx(&bar_h, 32768);
-    bulk_g2s(sH, a.f.Ha + (size_t)(hblk * 2 + 0) * TC_BLK_FLOATS, 8192, &bar_h);
-    bulk_g2s(sH + 8192, a.f.Ha + (size_t)((hblk + 1) * 2 + 0) * TC_BLK_FLOATS, 8192, &bar_h);
-    bulk_g2s(sH + 16384, a.f.Ha + (size_t)(hblk * 2 + 1) * TC_BLK_FLOATS, 8192, &bar_h);
-    bulk_g2s(sH + 24576, a.f.Ha + (size_t)((hblk + 1) * 2 + 1) * TC_BLK_FLOATS, 8192, &bar_h);
-    auto produce = [&](int b) {
-      const int s = b & (TC_STAGES - 1);
-      if (b >= TC_STAGES) mbar_wait(&bar_empty[s], ((b / TC_STAGES) - 1) & 1);
-      unsigned char* st = smem + HTC_OFF_STAGE + s * HTC_STAGE_BYTES;
-      const int64_t row = r0 + 32 * (int64_t)b;
-      const int64_t wblk = row / 64;
-      const int sub = (int)((row % 64) / 32);                       // which 32-row half of the 64-row block
-      const float* wa = a.f.Wa + (size_t)wblk * 2 * TC_BLK_FLOATS;
-      const float* wb = a.f.Wb + (size_t)wblk * 2 * TC_BLK_FLOATS;
-      mbar_expect_tx(&bar_full[s], 16384);
-      bulk_g2s(st, wa + sub * 1024, 4096, &bar_full[s]);                          // W rows hi
-      bulk_g2s(st + 4096, wa + TC_BLK_FLOATS + sub * 1024, 4096, &bar_full[s]);   // W rows lo
-      bulk_g2s(st + 8192, wb + sub * 1024, 4096, &bar_full[s]);                   // W^T K-block hi
-      bulk_g2s(st + 12288, wb + TC_BLK_FLOATS + sub * 1024, 4096, &bar_full[s]);  // W^T K-block lo
-    };
-    const uint64_t dHh = desc_kmajor_sw128(smem_u32(sH)), dHl = desc_kmajor_sw128(smem_u32(sH + 16384));
-    constexpr uint32_t id = idesc_tf32(128, 32);
-    auto mma1 = [&](int b) {
-      const int s = b & (TC_STAGES - 1);
-      mbar_wait(&bar_full[s], (b / TC_STAGES) & 1);
-      fence_after_sync();
-      unsigned char* st = smem + HTC_OFF_STAGE + s * HTC_STAGE_BYTES;
-      const uint64_t dWh = desc_kmajor_sw128(smem_u32(st)), dWl = desc_kmajor_sw128(smem_u32(st + 4096));
-      const uint32_t tT = tTheta + 32 * (b & 1);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_ss(tT, dHh + 2 * ks, dWh + 2 * ks, id, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_ss(tT, dHh + 2 * ks, dWl + 2 * ks, id, 1);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_ss(tT, dHl + 2 * ks, dWh + 2 * ks, id, 1);
-      commit(&bar_theta[b & 1]);
-    };
-    for (int b = 0; b < nb && b < 3; ++b) produce(b);
-    mbar_wait(&bar_h, 0);
-    if (nb > 0) mma1(0);
-    if (nb > 1) mma1(1);
+  if (warp == TC_TMA_WARP) {
+    // ------------------------------------------------------------- producer: one 16 KB bulk copy per block
+    const bool leader = elect_one();
+    const float* src = a.Wf + (size_t)(r0 >> 5) * 4096;
     for (int b = 0; b < nb; ++b) {
-      const int s = b & (TC_STAGES - 1);
-      unsigned char* st = smem + HTC_OFF_STAGE + s * HTC_STAGE_BYTES;
-      mbar_wait(&bar_s[b & 1], (b >> 1) & 1);
-      fence_after_sync();
-      if (cd) {
-        const uint64_t dTh = desc_kmajor_sw128(smem_u32(st + 8192)), dTl = desc_kmajor_sw128(smem_u32(st + 12288));
-        const uint32_t tRp = tR + 128 * (b & 1), tRpl = tRp + 32, tRn = tRp + 64, tRnl = tRp + 96;
-        const bool chain_start = (b % kFlush) == 0;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t acc = (ks > 0 || !chain_start) ? 1u : 0u;
-          mma_ts(tC, tRp + 8 * ks, dTh + 2 * ks, id, acc);
-          mma_ts(tD, tRn + 8 * ks, dTh + 2 * ks, id, acc);
-        }
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          mma_ts(tC, tRp + 8 * ks, dTl + 2 * ks, id, 1);
-          mma_ts(tD, tRn + 8 * ks, dTl + 2 * ks, id, 1);
-          mma_ts(tC, tRpl + 8 * ks, dTh + 2 * ks, id, 1);
-          mma_ts(tD, tRnl + 8 * ks, dTh + 2 * ks, id, 1);
-        }
-        commit(&bar_empty[s]);
-        if (b + 1 == nb || ((b + 1) % kFlush) == 0) commit(&bar_cd);   // a chain ends here
-      } else {
-        mbar_arrive(&bar_empty[s]);                                    // loss-only pass: MMA1 was the last reader
+      const int s = b % HTC_STAGES;
+      if (b >= HTC_STAGES) mbar_wait(&bar_empty[s], ((b / HTC_STAGES) - 1) & 1);
+      if (leader) {
+        mbar_expect_tx(&bar_full[s], HTC_STAGE_BYTES);
+        bulk_g2s(smem + s * HTC_STAGE_BYTES, src + (size_t)b * 4096, HTC_STAGE_BYTES, &bar_full[s]);
       }
-      if (b + 2 < nb) mma1(b + 2);
-      if (b + 3 < nb) produce(b + 3);
+      __syncwarp();
     }
-  } else if (warp < TC_SIMT_WARPS) {
-    // ------------------------------------------------------------- SIMT warps: lane = column j, 8 rows i per block
-    const int q = warp & 3, sub = warp >> 2;
+  } else if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
+    // ------------------------------------------------------------- MMA1 issuer of group g
+    const int g = warp - TC_MMA1_WARP;
+    const bool leader = elect_one();
+    const uint32_t tT = tTheta + 32 * g;
+    mbar_wait(&bar_a, 0);
+    fence_after_sync();
+    for (int b = g; b < nb; b += 2) {
+      const int s = b % HTC_STAGES;
+      mbar_wait(&bar_full[s], (b / HTC_STAGES) & 1);
+      if (b >= 2) mbar_wait(&bar_tfree[g], ((b >> 1) - 1) & 1);        // Theta(b-2) sits in the SIMT registers
+      fence_after_sync();
+      TC_EV(0, b, 0);
+      if (leader) {
+        const uint32_t st = smem_u32(smem + s * HTC_STAGE_BYTES);
+        const uint64_t dWh = desc_kmajor_sw128(st), dWl = desc_kmajor_sw128(st + 4096);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dWh + 2 * ks, id, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dWl + 2 * ks, id, 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 32 + 8 * ks, dWh + 2 * ks, id, 1);
+        commit(&bar_theta[g]);
+        if (!cd) commit(&bar_empty[s]);                                // loss-only pass: MMA1 is the last reader
+      }
+      __syncwarp();
+      TC_EV(0, b, 1);
+    }
+  } else if (warp == TC_MMA2_WARP || warp == TC_MMA2_WARP + 1) {
+    // ------------------------------------------------------------- MMA2 issuer of group g
+    const int g = warp - TC_MMA2_WARP;
+    const bool leader = elect_one();
+    const uint32_t tRb = tR + 128 * g, tC = tAcc + 64 * g, tS = tC + 32;
+    if (cd) {
+      for (int b = g; b < nb; b += 2) {
+        const int ob = b >> 1;                                         // index among the group's own blocks
+        const bool chain_start = (ob % kFlush) == 0;
+        mbar_wait(&bar_s[g], ob & 1);
+        fence_after_sync();
+        TC_EV(0, b, 2);
+        if (leader) {
+          const int s = b % HTC_STAGES;
+          const uint32_t st = smem_u32(smem + s * HTC_STAGE_BYTES);
+          const uint64_t dTh = desc_kmajor_sw128(st + 8192), dTl = desc_kmajor_sw128(st + 12288);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (ks > 0 || !chain_start) ? 1u : 0u;
+            const uint32_t tr = tRb + 32 * ks;                         // Rp_hi +0, Rp_lo +8, R_hi +16, R_lo +24
+            mma_ts(tC, tr, dTh + 2 * ks, id, acc);
+            mma_ts(tS, tr + 16, dTh + 2 * ks, id, acc);
+            mma_ts(tC, tr, dTl + 2 * ks, id, 1);
+            mma_ts(tS, tr + 16, dTl + 2 * ks, id, 1);
+            mma_ts(tC, tr + 8, dTh + 2 * ks, id, 1);
+            mma_ts(tS, tr + 24, dTh + 2 * ks, id, 1);
+          }
+          commit(&bar_rfree[g]);
+          commit(&bar_empty[s]);
+          if (b + 2 >= nb || ((ob + 1) % kFlush) == 0) commit(&bar_cd[g]);   // a chain ends here
+        }
+        __syncwarp();
+        TC_EV(0, b, 3);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- SIMT warps: lane = column j, 16 rows i per block
+    const int q = warp & 3, w4 = warp >> 2, g = w4 & 1, h = w4 >> 1;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int tl = q * 32 + lane;                                      // TMEM lane == column inside the CTA tile
     const int64_t col = jb + tl;
-    const int64_t colc = min(col, a.n - 1);
-    const uint32_t* __restrict__ Pcol = a.Pt + (size_t)colc * a.wpr_t + (r0 >> 5);
     const float eps = a.eps;
-    float ll = 0.f;
-    auto flush = [&](int idx) {                                        // TMEM chain -> fp32 shared accumulators
-      mbar_wait(&bar_cd, idx & 1);
-      fence_after_sync();
-      uint32_t v[16];
-      tmem_ld16(tC + lane_off + 16 * sub, v);
-      wait_ld();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) sAcc[(16 * sub + e) * 128 + tl] += __uint_as_float(v[e]);
-    };
-    for (int b = 0; b < nb; ++b) {
-      const uint32_t pbits = Pcol[b] >> (8 * sub);
-      if (cd && b > 0 && (b % kFlush) == 0) flush(b / kFlush - 1);
-      mbar_wait(&bar_theta[b & 1], (b >> 1) & 1);
-      fence_after_sync();
-      uint32_t v[8], ph[8], pl[8], nh[8], nl[8];
-      tmem_ld8(tTheta + 32 * (b & 1) + lane_off + 8 * sub, v);
-      wait_ld();
+    {  // resident A operand: this thread's column of H, k = 8 w4 .. 8 w4 + 7, split into hi / lo
+      uint32_t hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float theta = __uint_as_float(v[e]);
-        const bool p = (pbits >> e) & 1u;
-        const float x = (p ? theta : (1.0f - theta)) + eps;
-        const float r = rcp_(x);
-        ll += logu_(x);
-        const float hi = tc::tf32_trunc(r);
-        const float lo = r - hi;
-        ph[e] = __float_as_uint(p ? hi : 0.0f);
-        pl[e] = __float_as_uint(p ? lo : 0.0f);
-        nh[e] = __float_as_uint(p ? 0.0f : hi);
-        nl[e] = __float_as_uint(p ? 0.0f : lo);
+        const float x = a.H[(size_t)(8 * w4 + e) * a.ldh + col];
+        const float xh = tf32_trunc(x);
+        hi[e] = __float_as_uint(xh);
+        lo[e] = __float_as_uint(x - xh);
       }
+      tmem_st8(tA + lane_off + 8 * w4, hi);
+      tmem_st8(tA + 32 + lane_off + 8 * w4, lo);
+      wait_st();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a);
+    }
+    // fp32 sums of this thread's accumulator slice (k = 16 h .. 16 h + 15 of the group's C and S) live in
+    // shared memory: they are touched once per chain, registers are what the hot loop is short of
+    float* __restrict__ myacc = sAcc + tid;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) myacc[e * 512] = 0.f;
+    int flushed = 0;                                                   // chains of this group already flushed
+    auto flush = [&]() {                                               // TMEM chain -> fp32 accumulators
+      mbar_wait(&bar_cd[g], flushed & 1);
+      fence_after_sync();
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {                           // C, then S
+        uint32_t c[16];
+        tmem_ld16(tAcc + 64 * g + 32 * part + lane_off + 16 * h, c);
+        wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) myacc[(16 * part + e) * 512] += __uint_as_float(c[e]);
+      }
+      ++flushed;
+    };
+    const uint32_t* __restrict__ pc = a.Pc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
+    uint32_t word = g < nb ? pc[(size_t)g * 128] : 0u;
+    float ll = 0.f, ll_sum = 0.f, ll_c = 0.f;                          // fp64 is slow here: compensated fp32 sum
+    for (int b = g; b < nb; b += 2) {
+      const int ob = b >> 1;
+      const uint32_t bits = word >> (16 * h);
+      if (b + 2 < nb) word = pc[(size_t)(b + 2) * 128];                // prefetch the next block's bits
+      TC_EV(1 + g, b, 0);
+      mbar_wait(&bar_theta[g], ob & 1);
+      TC_EV(1 + g, b, 1);
+      fence_after_sync();
+      uint32_t v[16];
+      {
+        uint32_t v0[8], v1[8];
+        tmem_ld8(tTheta + 32 * g + lane_off + 16 * h, v0);
+        tmem_ld8(tTheta + 32 * g + lane_off + 16 * h + 8, v1);
+        wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { v[e] = v0[e]; v[8 + e] = v1[e]; }
+      }
+      TC_EV(1 + g, b, 2);
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tfree[g]);                       // Theta[g] may be overwritten by MMA1(b+2)
+      float llb = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint32_t out[32];
+        float prod = 1.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float theta = __uint_as_float(v[8 * u + e]);
+          const bool p = (bits >> (8 * u + e)) & 1u;
+          const float x = (p ? theta : (1.0f - theta)) + eps;
+          const float r = rcp_(x);
+          prod = (e & 3) ? prod * x : x;
+          if ((e & 3) == 3) llb += logu_(prod);                        // eps >= 1e-9: four factors cannot underflow
+          const float hi = tf32_trunc(r), lo = r - hi;
+          out[e] = __float_as_uint(p ? hi : 0.0f);
+          out[8 + e] = __float_as_uint(p ? lo : 0.0f);
+          out[16 + e] = __float_as_uint(hi);
+          out[24 + e] = __float_as_uint(lo);
+        }
+        if (cd) {
+          if (u == 0 && b >= 2) {                                      // MMA2(b-2) must be done reading R[g]
+            TC_EV(1 + g, b, 3);
+            mbar_wait(&bar_rfree[g], (ob - 1) & 1);
+            fence_after_sync();
+            TC_EV(1 + g, b, 4);
+          }
+          tmem_st32(tR + 128 * g + lane_off + 32 * (2 * h + u), out);
+        }
+      }
+      TC_EV(1 + g, b, 5);
       if (cd) {
-        const uint32_t tRp = tR + 128 * (b & 1) + lane_off + 8 * sub;
-        tmem_st8(tRp, ph);
-        tmem_st8(tRp + 32, pl);
-        tmem_st8(tRp + 64, nh);
-        tmem_st8(tRp + 96, nl);
+        if (ob > 0 && (ob % kFlush) == 0) flush();                     // previous chain: its MMAs ended a block ago
         wait_st();
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_s[b & 1]);
-      if ((b & 15) == 15) { ll_total += (double)ll; ll = 0.f; }
+      if (lane == 0) mbar_arrive(&bar_s[g]);
+      TC_EV(1 + g, b, 6);
+      ll += llb;
+      if ((ob & 15) == 15) {                                           // Kahan step every 16 own blocks
+        const float y = ll - ll_c, t = ll_sum + y;
+        ll_c = (t - ll_sum) - y;
+        ll_sum = t;
+        ll = 0.f;
+      }
     }
-    ll_total += (double)ll;
-    if (cd) {
-      if (nb > 0) flush(nflush);
-      float* __restrict__ base = a.CD + (size_t)(split * 2) * 32 * a.ldh;   // C rows 0..31 then D rows 0..31
-#pragma unroll
-      for (int e = 0; e < 16; ++e)                                     // column j of row k: coalesced across the warp
-        base[(size_t)(16 * sub + e) * a.ldh + col] = sAcc[(16 * sub + e) * 128 + tl];
-    }
+    ll_total = ((double)ll_sum - (double)ll_c) + (double)ll;
     if (col >= a.n) ll_total = 0.0;
+    if (cd) {
+      if (g < nb) flush();                                             // the group's last chain
+      asm volatile("bar.sync 1, 512;" ::: "memory");                   // the 16 SIMT warps only
+      if (g == 0) {                                                    // group 0 + group 1 (thread tid + 128), fixed order
+        float* __restrict__ base = a.CD + (size_t)(split * 2) * 32 * a.ldh;   // C rows 0..31 then D rows 0..31
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {                                 // column j of row k: coalesced across the warp
+          const float c = myacc[e * 512] + myacc[e * 512 + 128];
+          const float sm = myacc[(16 + e) * 512] + myacc[(16 + e) * 512 + 128];
+          base[(size_t)(16 * h + e) * a.ldh + col] = c;
+          base[(size_t)(32 + 16 * h + e) * a.ldh + col] = sm - c;
+        }
+      }
+    }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == TC_SIMT_WARPS) tmem_dealloc(tb, 512);
+  if (warp == TC_TMA_WARP) tmem_dealloc(tb, 512);
   const double tot = block_sum<TC_THREADS>(ll_total, red_scratch);
   if (tid == 0) a.LL[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<float>();
 }
 
 // =====================================================================================
-// W pass (thread = row i = TMEM lane).  CTA = 128 rows i, streams 64-column blocks of H.
-//   MMA1: Theta'[128 i x 64 j] = W[128x32] . Ht[64x32]^T
-//   SIMT: s = +-1/x on observed entries (p - q, exact), q-sum in registers, s -> TMEM (hi, lo)
+// W pass (TMEM lane = row i).  CTA = 128 rows i, streams 64-column blocks of H.
+//   MMA1: Theta'[128 i x 64 j] = W[128 x 32 k] . Ht[64 j x 32 k]^T
+//   SIMT: signed ratio s = 1/(+-x) on observed entries (= p - q), q-sum from sum|s| - sum s, s -> TMEM (hi, lo)
 //   MMA2: G[128 i x 32 k] += S[128 x 64 j] . H[32 k x 64 j]^T
-// TMEM: Theta[2] 0..127 | S[2] = {S_hi, S_lo} x 64 at 128..255, 256..383 | G 384..415
+// TMEM: A hi 0..31, lo 32..63 | Theta[g] 64..191 | S[g] 192..447 (per 8 columns: S_hi S_lo) | G[g] 448..511
 // =====================================================================================
-constexpr int WTC_STAGE_BYTES = 32768;                  // Ha hi|lo (16 KB) + Hb hi|lo (16 KB)
-constexpr int WTC_OFF_STAGE = 32768;
-constexpr int WTC_OFF_ACC = WTC_OFF_STAGE + TC_STAGES * WTC_STAGE_BYTES;
-constexpr int WTC_OFF_Q = WTC_OFF_ACC + 32 * 128 * 4;
+constexpr int WTC_STAGES = 5;
+constexpr int WTC_STAGE_BYTES = 32768;
+constexpr int WTC_OFF_ACC = WTC_STAGES * WTC_STAGE_BYTES;         // fp32 accumulators [16][512 SIMT threads]
+constexpr int WTC_OFF_Q = WTC_OFF_ACC + 16 * 512 * 4;
 constexpr int WTC_SMEM = WTC_OFF_Q + 4 * 128 * 4 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs a) {
@@ -274,169 +362,210 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   if (*a.done) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sW = smem;                                         // W tile [hi 16 KB][lo 16 KB], 128 rows i
-  float* sAcc = reinterpret_cast<float*>(smem + WTC_OFF_ACC);       // [32 k][128 lanes]
-  float* sQ = reinterpret_cast<float*>(smem + WTC_OFF_Q);           // [4 column slices][128 lanes]
-  __shared__ uint64_t bar_w, bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_theta[2], bar_s[2], bar_g;
+  float* sAcc = reinterpret_cast<float*>(smem + WTC_OFF_ACC);       // thread t: 16 G sums at [e * 512 + t]
+  float* sQ = reinterpret_cast<float*>(smem + WTC_OFF_Q);           // [4 (group, half)][128 lanes]
+  __shared__ uint64_t bar_full[WTC_STAGES], bar_empty[WTC_STAGES];
+  __shared__ uint64_t bar_a, bar_theta[2], bar_tfree[2], bar_s[2], bar_sfree[2], bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int64_t ib = (int64_t)blockIdx.x * 128;
   const int64_t c0 = (int64_t)blockIdx.y * a.cols_per_split;
   const int64_t c1 = min(a.n, c0 + a.cols_per_split);
   const int nb = c1 > c0 ? (int)((c1 - c0 + 63) / 64) : 0;
 
-  for (int e = tid; e < 32 * 128; e += TC_THREADS) sAcc[e] = 0.0f;
-  if (warp == TC_SIMT_WARPS) tmem_alloc(&tmem_base_s, 512);
-  if (tid == TC_CTRL_TID) {
-    mbar_init(&bar_w, 1);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    mbar_init(&bar_theta[0], 1); mbar_init(&bar_theta[1], 1);
-    mbar_init(&bar_s[0], TC_SIMT_WARPS); mbar_init(&bar_s[1], TC_SIMT_WARPS);
-    mbar_init(&bar_g, 1);
+  if (warp == TC_TMA_WARP) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int s = 0; s < WTC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_a, TC_SIMT_WARPS);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bar_theta[g], 1); mbar_init(&bar_tfree[g], TC_SIMT_WARPS / 2);
+      mbar_init(&bar_s[g], TC_SIMT_WARPS / 2); mbar_init(&bar_sfree[g], 1); mbar_init(&bar_g[g], 1);
+    }
     mbar_fence_init();
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
-  const uint32_t tTheta = tb, tS = tb + 128, tG = tb + 384;
-  const int nflush = nb > 0 ? (nb - 1) / kFlush : 0;
+  const uint32_t tA = tb, tTheta = tb + 64, tS = tb + 192, tG = tb + 448;
+  constexpr uint32_t id1 = idesc_tf32(128, 64), id2 = idesc_tf32(128, 32);
 
-  if (tid == TC_CTRL_TID) {
-    // ------------------------------------------------------------- control thread
-    const int64_t wblk = ib / 64;
-    mbar_expect_tx(&bar_w, 32768);
-    bulk_g2s(sW, a.f.Wa + (size_t)(wblk * 2 + 0) * TC_BLK_FLOATS, 8192, &bar_w);
-    bulk_g2s(sW + 8192, a.f.Wa + (size_t)((wblk + 1) * 2 + 0) * TC_BLK_FLOATS, 8192, &bar_w);
-    bulk_g2s(sW + 16384, a.f.Wa + (size_t)(wblk * 2 + 1) * TC_BLK_FLOATS, 8192, &bar_w);
-    bulk_g2s(sW + 24576, a.f.Wa + (size_t)((wblk + 1) * 2 + 1) * TC_BLK_FLOATS, 8192, &bar_w);
-    auto produce = [&](int b) {
-      const int s = b & (TC_STAGES - 1);
-      if (b >= TC_STAGES) mbar_wait(&bar_empty[s], ((b / TC_STAGES) - 1) & 1);
-      unsigned char* st = smem + WTC_OFF_STAGE + s * WTC_STAGE_BYTES;
-      const int64_t hblk = c0 / 64 + b;
-      mbar_expect_tx(&bar_full[s], 32768);
-      bulk_g2s(st, a.f.Ha + (size_t)hblk * 2 * TC_BLK_FLOATS, 16384, &bar_full[s]);
-      bulk_g2s(st + 16384, a.f.Hb + (size_t)hblk * 2 * TC_BLK_FLOATS, 16384, &bar_full[s]);
-    };
-    const uint64_t dWh = desc_kmajor_sw128(smem_u32(sW)), dWl = desc_kmajor_sw128(smem_u32(sW + 16384));
-    constexpr uint32_t id1 = idesc_tf32(128, 64), id2 = idesc_tf32(128, 32);
-    auto mma1 = [&](int b) {
-      const int s = b & (TC_STAGES - 1);
-      mbar_wait(&bar_full[s], (b / TC_STAGES) & 1);
-      fence_after_sync();
-      unsigned char* st = smem + WTC_OFF_STAGE + s * WTC_STAGE_BYTES;
-      const uint64_t dHh = desc_kmajor_sw128(smem_u32(st)), dHl = desc_kmajor_sw128(smem_u32(st + 8192));
-      const uint32_t tT = tTheta + 64 * (b & 1);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_ss(tT, dWh + 2 * ks, dHh + 2 * ks, id1, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_ss(tT, dWh + 2 * ks, dHl + 2 * ks, id1, 1);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_ss(tT, dWl + 2 * ks, dHh + 2 * ks, id1, 1);
-      commit(&bar_theta[b & 1]);
-    };
-    for (int b = 0; b < nb && b < 3; ++b) produce(b);
-    mbar_wait(&bar_w, 0);
-    if (nb > 0) mma1(0);
-    if (nb > 1) mma1(1);
+  if (warp == TC_TMA_WARP) {
+    // ------------------------------------------------------------- producer: one 32 KB bulk copy per block
+    const bool leader = elect_one();
+    const float* src = a.Hf + (size_t)(c0 >> 6) * 8192;
     for (int b = 0; b < nb; ++b) {
-      const int s = b & (TC_STAGES - 1);
-      unsigned char* st = smem + WTC_OFF_STAGE + s * WTC_STAGE_BYTES;
-      mbar_wait(&bar_s[b & 1], (b >> 1) & 1);
+      const int s = b % WTC_STAGES;
+      if (b >= WTC_STAGES) mbar_wait(&bar_empty[s], ((b / WTC_STAGES) - 1) & 1);
+      if (leader) {
+        mbar_expect_tx(&bar_full[s], WTC_STAGE_BYTES);
+        bulk_g2s(smem + s * WTC_STAGE_BYTES, src + (size_t)b * 8192, WTC_STAGE_BYTES, &bar_full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
+    // ------------------------------------------------------------- MMA1 issuer of group g
+    const int g = warp - TC_MMA1_WARP;
+    const bool leader = elect_one();
+    const uint32_t tT = tTheta + 64 * g;
+    mbar_wait(&bar_a, 0);
+    fence_after_sync();
+    for (int b = g; b < nb; b += 2) {
+      const int s = b % WTC_STAGES;
+      mbar_wait(&bar_full[s], (b / WTC_STAGES) & 1);
+      if (b >= 2) mbar_wait(&bar_tfree[g], ((b >> 1) - 1) & 1);
       fence_after_sync();
-      const uint32_t tSh = tS + 128 * (b & 1), tSl = tSh + 64;
-      const bool chain_start = (b % kFlush) == 0;
+      if (leader) {
+        const uint32_t st = smem_u32(smem + s * WTC_STAGE_BYTES);
+        const uint64_t dHh = desc_kmajor_sw128(st), dHl = desc_kmajor_sw128(st + 8192);
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {                                   // S.H, S.H_lo, S_lo.H
-        const uint32_t ta = (t == 2) ? tSl : tSh;
-        unsigned char* hb = st + 16384 + (t == 1 ? 8192 : 0);
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dHh + 2 * ks, id1, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dHl + 2 * ks, id1, 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 32 + 8 * ks, dHh + 2 * ks, id1, 1);
+        commit(&bar_theta[g]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == TC_MMA2_WARP || warp == TC_MMA2_WARP + 1) {
+    // ------------------------------------------------------------- MMA2 issuer of group g
+    const int g = warp - TC_MMA2_WARP;
+    const bool leader = elect_one();
+    const uint32_t tSb = tS + 128 * g, tGa = tG + 32 * g;
+    for (int b = g; b < nb; b += 2) {
+      const int ob = b >> 1;
+      const bool chain_start = (ob % kFlush) == 0;
+      mbar_wait(&bar_s[g], ob & 1);
+      fence_after_sync();
+      if (leader) {
+        const int s = b % WTC_STAGES;
+        const uint32_t st = smem_u32(smem + s * WTC_STAGE_BYTES);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t dB = desc_kmajor_sw128(smem_u32(hb + (ks >> 2) * 4096)) + 2 * (ks & 3);
-          mma_ts(tG, ta + 8 * ks, dB, id2, ((t | ks) > 0 || !chain_start) ? 1u : 0u);
+          const uint64_t dBh = desc_kmajor_sw128(st + 16384 + (ks >> 2) * 4096) + 2 * (ks & 3);
+          const uint64_t dBl = desc_kmajor_sw128(st + 24576 + (ks >> 2) * 4096) + 2 * (ks & 3);
+          const uint32_t ts = tSb + 16 * ks;                             // S_hi +0, S_lo +8
+          mma_ts(tGa, ts, dBh, id2, (ks > 0 || !chain_start) ? 1u : 0u);
+          mma_ts(tGa, ts, dBl, id2, 1);
+          mma_ts(tGa, ts + 8, dBh, id2, 1);
         }
+        commit(&bar_sfree[g]);
+        commit(&bar_empty[s]);
+        if (b + 2 >= nb || ((ob + 1) % kFlush) == 0) commit(&bar_g[g]);
       }
-      commit(&bar_empty[s]);
-      if (b + 1 == nb || ((b + 1) % kFlush) == 0) commit(&bar_g);
-      if (b + 2 < nb) mma1(b + 2);
-      if (b + 3 < nb) produce(b + 3);
+      __syncwarp();
     }
-  } else if (warp < TC_SIMT_WARPS) {
-    // ------------------------------------------------------------- SIMT warps: lane = row i, 16 columns j per block
-    const int q = warp & 3, sub = warp >> 2;
+  } else {
+    // ------------------------------------------------------------- SIMT warps: lane = row i, 32 columns j per block
+    const int q = warp & 3, w4 = warp >> 2, g = w4 & 1, h = w4 >> 1;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int tl = q * 32 + lane;
     const int64_t row = ib + tl;
-    const int64_t rowc = min(row, a.m - 1);
-    const uint32_t* __restrict__ Prow = a.P + (size_t)rowc * a.wpr + (c0 >> 5) + (sub >> 1);
-    const uint32_t* __restrict__ Mrow = a.M ? a.M + (size_t)rowc * a.wpr + (c0 >> 5) + (sub >> 1) : nullptr;
-    const int shift = (sub & 1) * 16;
     const float eps = a.eps;
-    float qacc = 0.f;
-    auto flush = [&](int idx) {
-      mbar_wait(&bar_g, idx & 1);
-      fence_after_sync();
-      uint32_t v[8];
-      tmem_ld8(tG + lane_off + 8 * sub, v);
-      wait_ld();
+    {  // resident A operand: this thread's row of W, k = 8 w4 .. 8 w4 + 7 (zero beyond m)
+      float x[8];
+      if (row < a.m) {
+        const float4 x0 = *reinterpret_cast<const float4*>(a.W + (size_t)row * 32 + 8 * w4);
+        const float4 x1 = *reinterpret_cast<const float4*>(a.W + (size_t)row * 32 + 8 * w4 + 4);
+        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sAcc[(8 * sub + e) * 128 + tl] += __uint_as_float(v[e]);
-    };
-    for (int b = 0; b < nb; ++b) {
-      const int64_t colw = c0 + 64 * (int64_t)b + 32 * (sub >> 1);    // first column of this thread's bit word
-      const int64_t rem = c1 - colw;
-      const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
-      const uint32_t pbits = Prow[2 * b] >> shift;
-      const uint32_t mbits = ((Mrow ? Mrow[2 * b] : 0xffffffffu) & valid) >> shift;
-      if (b > 0 && (b % kFlush) == 0) flush(b / kFlush - 1);
-      mbar_wait(&bar_theta[b & 1], (b >> 1) & 1);
-      fence_after_sync();
-      uint32_t v[16], sh[16], sl[16];
-      tmem_ld16(tTheta + 64 * (b & 1) + lane_off + 16 * sub, v);
-      wait_ld();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float theta = __uint_as_float(v[e]);
-        const bool p = (pbits >> e) & 1u, o = (mbits >> e) & 1u;
-        const float x = (p ? theta : (1.0f - theta)) + eps;
-        float r = rcp_(x);
-        r = o ? r : 0.0f;
-        const float s = p ? r : -r;
-        qacc += p ? 0.0f : r;
-        const float hi = tc::tf32_trunc(s);
-        sh[e] = __float_as_uint(hi);
-        sl[e] = __float_as_uint(s - hi);
+        for (int e = 0; e < 8; ++e) x[e] = 0.f;
       }
-      const uint32_t tSh = tS + 128 * (b & 1) + lane_off + 16 * sub;
-      tmem_st16(tSh, sh);
-      tmem_st16(tSh + 64, sl);
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = tf32_trunc(x[e]);
+        hi[e] = __float_as_uint(xh);
+        lo[e] = __float_as_uint(x[e] - xh);
+      }
+      tmem_st8(tA + lane_off + 8 * w4, hi);
+      tmem_st8(tA + 32 + lane_off + 8 * w4, lo);
       wait_st();
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_s[b & 1]);
+      if (lane == 0) mbar_arrive(&bar_a);
     }
-    if (nb > 0) flush(nflush);
-    sQ[sub * 128 + tl] = qacc;
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == TC_SIMT_WARPS) tmem_dealloc(tb, 512);
-  if (warp < TC_SIMT_WARPS) {
-    const int q = warp & 3, sub = warp >> 2, tl = q * 32 + lane;
-    const int64_t row = ib + tl;
-    if (row < a.m) {
-      float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * 32 + 8 * sub;
-      float g[8];
+    float* __restrict__ myacc = sAcc + tid;                            // k = 16 h .. 16 h + 15 of the group's G
 #pragma unroll
-      for (int e = 0; e < 8; ++e) g[e] = sAcc[(8 * sub + e) * 128 + tl];
-      *reinterpret_cast<float4*>(Gg) = make_float4(g[0], g[1], g[2], g[3]);
-      *reinterpret_cast<float4*>(Gg + 4) = make_float4(g[4], g[5], g[6], g[7]);
-      if (sub == 0)                                                   // fixed order: bit-reproducible
+    for (int e = 0; e < 16; ++e) myacc[e * 512] = 0.f;
+    int flushed = 0;
+    auto flush = [&]() {
+      mbar_wait(&bar_g[g], flushed & 1);
+      fence_after_sync();
+      uint32_t c[16];
+      tmem_ld16(tG + 32 * g + lane_off + 16 * h, c);
+      wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) myacc[e * 512] += __uint_as_float(c[e]);
+      ++flushed;
+    };
+    const uint2* __restrict__ pm = a.PM + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5) + h) * 128 + tl;
+    uint2 word = g < nb ? pm[(size_t)(2 * g) * 128] : make_uint2(0u, 0u);
+    float qsum = 0.f;
+    for (int b = g; b < nb; b += 2) {
+      const int ob = b >> 1;
+      const uint2 bits = word;
+      if (b + 2 < nb) word = pm[(size_t)(2 * (b + 2)) * 128];
+      mbar_wait(&bar_theta[g], ob & 1);
+      fence_after_sync();
+      float sum_s = 0.f, sum_a = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint32_t v[16], out[32];
+        tmem_ld16(tTheta + 64 * g + lane_off + 32 * h + 16 * u, v);
+        wait_ld();
+        if (u == 1) {                                                  // Theta[g] may be overwritten by MMA1(b+2)
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tfree[g]);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float theta = __uint_as_float(v[e]);
+          const bool p = (bits.x >> (16 * u + e)) & 1u, o = (bits.y >> (16 * u + e)) & 1u;
+          const float xs = p ? theta + eps : (theta - 1.0f) - eps;     // -(1 - theta + eps) for the zeros
+          float s = rcp_(xs);
+          s = o ? s : 0.0f;
+          sum_s += s;
+          sum_a += fabsf(s);
+          const float hi = tf32_trunc(s);
+          out[16 * (e >> 3) + (e & 7)] = __float_as_uint(hi);
+          out[16 * (e >> 3) + 8 + (e & 7)] = __float_as_uint(s - hi);
+        }
+        if (u == 0 && b >= 2) {                                        // MMA2(b-2) must be done reading S[g]
+          mbar_wait(&bar_sfree[g], (ob - 1) & 1);
+          fence_after_sync();
+        }
+        tmem_st32(tS + 128 * g + lane_off + 16 * (4 * h + 2 * u), out);
+      }
+      if (ob > 0 && (ob % kFlush) == 0) flush();                       // previous chain: its MMAs ended a block ago
+      wait_st();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_s[g]);
+      qsum += 0.5f * (sum_a - sum_s);                                  // sum over the observed zeros of 1/x
+    }
+    if (g < nb) flush();
+    sQ[w4 * 128 + tl] = qsum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");                     // the 16 SIMT warps only
+    if (g == 0 && row < a.m) {                                         // group 0 + group 1 (thread tid + 128), fixed order
+      float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * 32 + 16 * h;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        *reinterpret_cast<float4*>(Gg + e) =
+            make_float4(myacc[e * 512] + myacc[e * 512 + 128], myacc[(e + 1) * 512] + myacc[(e + 1) * 512 + 128],
+                        myacc[(e + 2) * 512] + myacc[(e + 2) * 512 + 128], myacc[(e + 3) * 512] + myacc[(e + 3) * 512 + 128]);
+      if (h == 0)
         a.Q[(size_t)blockIdx.y * a.m + row] = ((sQ[tl] + sQ[128 + tl]) + sQ[256 + tl]) + sQ[384 + tl];
     }
   }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == TC_TMA_WARP) tmem_dealloc(tb, 512);
 }
 
 inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
