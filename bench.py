@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--obs", type=float, default=0.9)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
@@ -212,7 +213,7 @@ def run_ours(a):
 
     steps, warmup = a.steps, a.warmup
     prob = DeviceProblem(m_local, N, K, dtype=a.dtype, vkind="bits", has_mask=True, alpha=1.2, beta=1.2, eps=1e-8,
-                         n_obs=n_obs, max_iter_cap=steps + warmup + 2, device=dev)
+                         n_obs=n_obs, max_iter_cap=steps + warmup + 2, device=dev, engine=a.engine)
     prob.set_bits(P, Mk)
     if world > 1:
         prob.init_comm()
@@ -260,20 +261,47 @@ def run_ours(a):
     h_ach = h_flop / (h_avg_ms * 1e-3) * 1e-12 if h_cnt else None
     w_ach = w_flop / (w_avg_ms * 1e-3) * 1e-12 if w_cnt else None
     nominal = 2 * 128 * 148 * (sampler.max_mhz or 1965) * 1e6 * 1e-12
-    roofline = {
-        "bound": "fp32" if a.dtype == "float32" else "fp64", "kernel": "h_pass_kernel (H half-step + fused NLL)",
-        "achieved": h_ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (h_ach / peak_tf) if h_ach else None,
-        "peak_source": "measured in this run: nbmf_fma_peak (packed FFMA2 chains, 148x8 CTAs); MEASURED_PEAKS.json has no FP32 entry",
-        "nominal_peak": nominal, "frac_of_nominal": (h_ach / nominal) if h_ach else None,
-        "traffic": None,
+    engine = prob.engine
+    mp = measured_peaks()
+    common = {
+        "unit": "TFLOP/s", "traffic": None, "engine": engine,
         "algorithmic_flop_per_entry": {"h_pass": 6 * K, "w_pass": 4 * K, "iteration": 10 * K},
         "avg_launch_ms": h_avg_ms, "launches_timed": h_cnt, "share_of_step": h_ms / ms_total if ms_total else None,
-        "w_pass": {"achieved": w_ach, "frac": (w_ach / peak_tf) if w_ach else None, "avg_launch_ms": w_avg_ms,
-                   "share_of_step": w_ms / ms_total if ms_total else None},
-        "iteration_frac": (10.0 * K * entries_local * steps / (ms_total * 1e-3) * 1e-12 / peak_tf),
+        "fp32_simt_peak": {"value": peak_tf, "source": "measured in this run: nbmf_fma_peak (packed FFMA2 chains, 148x8 CTAs); "
+                           "MEASURED_PEAKS.json has no FP32 entry", "nominal": nominal,
+                           "h_pass_frac": (h_ach / peak_tf) if h_ach else None, "w_pass_frac": (w_ach / peak_tf) if w_ach else None,
+                           "iteration_frac": (10.0 * K * entries_local * steps / (ms_total * 1e-3) * 1e-12 / peak_tf)},
         "hbm_context": {"algorithmic_bytes_per_entry_iteration": 0.375, "hbm_gbs_used": 0.375 * value / world * 1e-9,
-                        "hbm_peak_gbs": measured_peaks().get("hbm_gbs")},
+                        "hbm_peak_gbs": mp.get("hbm_gbs")},
     }
+    if engine == "tensor":
+        # kind::tf32 runs at half the bf16 rate; the kernels are timed inside a long step -> sustained figure
+        bf16 = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")
+        tpeak = bf16 / 2 if bf16 else 1590.0 / 2
+        src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (the file has no TF32 entry; kind::tf32 is half the bf16 rate)"
+               if bf16 else "fallback 1.59 PFLOP/s bf16 / 2 (B200_PROFILING.md); MEASURED_PEAKS.json absent")
+        roofline = dict(common, **{
+            "bound": "tensor", "kernel": "h_pass_tc_kernel (H half-step + fused NLL, tcgen05 3xTF32)",
+            "achieved": h_ach, "peak": tpeak, "frac": (h_ach / tpeak) if h_ach else None, "peak_source": src,
+            "executed_tensor_tflops": 3.0 * h_ach if h_ach else None,
+            "frac_executed": (3.0 * h_ach / tpeak) if h_ach else None,
+            "note": "achieved = algorithmic flop (6K per entry) / launch time; the 3-term TF32 split executes 3x that on the "
+                    "tensor pipe (frac_executed), so frac cannot exceed 1/3",
+            "w_pass": {"kernel": "w_pass_tc_kernel", "achieved": w_ach, "frac": (w_ach / tpeak) if w_ach else None,
+                       "frac_executed": (3.0 * w_ach / tpeak) if w_ach else None, "avg_launch_ms": w_avg_ms,
+                       "share_of_step": w_ms / ms_total if ms_total else None},
+            "iteration_frac": (10.0 * K * entries_local * steps / (ms_total * 1e-3) * 1e-12 / tpeak),
+        })
+    else:
+        roofline = dict(common, **{
+            "bound": "fp32" if a.dtype == "float32" else "fp64", "kernel": "h_pass_kernel (H half-step + fused NLL)",
+            "achieved": h_ach, "peak": peak_tf, "frac": (h_ach / peak_tf) if h_ach else None,
+            "peak_source": common["fp32_simt_peak"]["source"],
+            "nominal_peak": nominal, "frac_of_nominal": (h_ach / nominal) if h_ach else None,
+            "w_pass": {"achieved": w_ach, "frac": (w_ach / peak_tf) if w_ach else None, "avg_launch_ms": w_avg_ms,
+                       "share_of_step": w_ms / ms_total if ms_total else None},
+            "iteration_frac": (10.0 * K * entries_local * steps / (ms_total * 1e-3) * 1e-12 / peak_tf),
+        })
 
     # ---- end-to-end through the public API with HOST buffers (pinned), H2D/D2H inside the timed region
     e2e = None
@@ -288,7 +316,7 @@ def run_ours(a):
         t0 = time.perf_counter()
         out = nbmf_mm_solver(BitMatrix(Ph, (m_local, N)), K, max_iter=steps, tol=0.0, alpha=1.2, beta=1.2,
                              mask=BitMatrix(Mh, (m_local, N)), random_state=0, dtype=a.dtype, device=dev,
-                             distributed=True, shard=(r0, M_rows), stats=stats)
+                             distributed=True, shard=(r0, M_rows), stats=stats, engine=a.engine)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         assert out[4] == steps

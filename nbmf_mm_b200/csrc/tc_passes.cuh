@@ -195,10 +195,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
             const uint32_t tr = tRb + 32 * ks;                         // Rp_hi +0, Rp_lo +8, R_hi +16, R_lo +24
             mma_ts(tC, tr, dTh + 2 * ks, id, acc);
             mma_ts(tS, tr + 16, dTh + 2 * ks, id, acc);
+#if !defined(TC_EXP) || TC_EXP < 2     // TC_EXP: timing experiments only (results are wrong)
             mma_ts(tC, tr, dTl + 2 * ks, id, 1);
             mma_ts(tS, tr + 16, dTl + 2 * ks, id, 1);
+#endif
+#if !defined(TC_EXP) || TC_EXP < 1
             mma_ts(tC, tr + 8, dTh + 2 * ks, id, 1);
             mma_ts(tS, tr + 24, dTh + 2 * ks, id, 1);
+#endif
           }
           commit(&bar_rfree[g]);
           commit(&bar_empty[s]);
@@ -253,15 +257,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
     const uint32_t* __restrict__ pc = a.Pc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
     uint32_t word = g < nb ? pc[(size_t)g * 128] : 0u;
     float ll = 0.f, ll_sum = 0.f, ll_c = 0.f;                          // fp64 is slow here: compensated fp32 sum
+    // A probe of an mbarrier costs ~200 clk even when its phase completed long ago, so every wait of the
+    // loop is probed early and only checked where it is needed: the latency hides behind the arithmetic.
+    bool ok_theta = false;
     for (int b = g; b < nb; b += 2) {
       const int ob = b >> 1;
       const uint32_t bits = word >> (16 * h);
       if (b + 2 < nb) word = pc[(size_t)(b + 2) * 128];                // prefetch the next block's bits
       TC_EV(1 + g, b, 0);
-      mbar_wait(&bar_theta[g], ob & 1);
+      if (!ok_theta) mbar_wait(&bar_theta[g], ob & 1);
       TC_EV(1 + g, b, 1);
       fence_after_sync();
       uint32_t v[16];
+      const bool ok_rfree = !(cd && b >= 2);
       {
         uint32_t v0[8], v1[8];
         tmem_ld8(tTheta + 32 * g + lane_off + 16 * h, v0);
@@ -294,15 +302,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
           out[24 + e] = __float_as_uint(lo);
         }
         if (cd) {
-          if (u == 0 && b >= 2) {                                      // MMA2(b-2) must be done reading R[g]
+          if (u == 0) {                                                // MMA2(b-2) must be done reading R[g]
             TC_EV(1 + g, b, 3);
-            mbar_wait(&bar_rfree[g], (ob - 1) & 1);
+            if (!ok_rfree) mbar_wait(&bar_rfree[g], (ob - 1) & 1);
             fence_after_sync();
             TC_EV(1 + g, b, 4);
           }
           tmem_st32(tR + 128 * g + lane_off + 32 * (2 * h + u), out);
         }
       }
+      ok_theta = b + 2 < nb && mbar_try(smem_u32(&bar_theta[g]), (ob + 1) & 1);
       TC_EV(1 + g, b, 5);
       if (cd) {
         if (ob > 0 && (ob % kFlush) == 0) flush();                     // previous chain: its MMAs ended a block ago
@@ -449,8 +458,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
           const uint64_t dBl = desc_kmajor_sw128(st + 24576 + (ks >> 2) * 4096) + 2 * (ks & 3);
           const uint32_t ts = tSb + 16 * ks;                             // S_hi +0, S_lo +8
           mma_ts(tGa, ts, dBh, id2, (ks > 0 || !chain_start) ? 1u : 0u);
+#if !defined(TC_EXP) || TC_EXP < 2
           mma_ts(tGa, ts, dBl, id2, 1);
+#endif
+#if !defined(TC_EXP) || TC_EXP < 1
           mma_ts(tGa, ts + 8, dBh, id2, 1);
+#endif
         }
         commit(&bar_sfree[g]);
         commit(&bar_empty[s]);
@@ -506,17 +519,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     const uint2* __restrict__ pm = a.PM + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5) + h) * 128 + tl;
     uint2 word = g < nb ? pm[(size_t)(2 * g) * 128] : make_uint2(0u, 0u);
     float qsum = 0.f;
+    bool ok_theta = false;                                             // early barrier probes, see the H pass
     for (int b = g; b < nb; b += 2) {
       const int ob = b >> 1;
       const uint2 bits = word;
       if (b + 2 < nb) word = pm[(size_t)(2 * (b + 2)) * 128];
-      mbar_wait(&bar_theta[g], ob & 1);
+      if (!ok_theta) mbar_wait(&bar_theta[g], ob & 1);
       fence_after_sync();
       float sum_s = 0.f, sum_a = 0.f;
+      bool ok_sfree = true;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         uint32_t v[16], out[32];
         tmem_ld16(tTheta + 64 * g + lane_off + 32 * h + 16 * u, v);
+        if (u == 0 && b >= 2) ok_sfree = mbar_try(smem_u32(&bar_sfree[g]), (ob - 1) & 1);
         wait_ld();
         if (u == 1) {                                                  // Theta[g] may be overwritten by MMA1(b+2)
           fence_before_sync();
@@ -536,12 +552,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
           out[16 * (e >> 3) + (e & 7)] = __float_as_uint(hi);
           out[16 * (e >> 3) + 8 + (e & 7)] = __float_as_uint(s - hi);
         }
-        if (u == 0 && b >= 2) {                                        // MMA2(b-2) must be done reading S[g]
-          mbar_wait(&bar_sfree[g], (ob - 1) & 1);
+        if (u == 0) {                                                  // MMA2(b-2) must be done reading S[g]
+          if (!ok_sfree) mbar_wait(&bar_sfree[g], (ob - 1) & 1);
           fence_after_sync();
         }
         tmem_st32(tS + 128 * g + lane_off + 16 * (4 * h + 2 * u), out);
       }
+      ok_theta = b + 2 < nb && mbar_try(smem_u32(&bar_theta[g]), (ob + 1) & 1);
       if (ob > 0 && (ob % kFlush) == 0) flush();                       // previous chain: its MMAs ended a block ago
       wait_st();
       fence_before_sync();
