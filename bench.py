@@ -346,6 +346,8 @@ def run_ours(a):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        from nbmf_mm_b200.device import destroy_cached_comms
+        destroy_cached_comms()
         dist.destroy_process_group()
 
 

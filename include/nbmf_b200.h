@@ -136,6 +136,11 @@ int nbmf_transform(nbmf_ctx* ctx, int32_t n_steps);
 int nbmf_comm_unique_id(void* id128_host);                          /* rank 0; 128 bytes */
 int nbmf_comm_init(nbmf_ctx* ctx, const void* id128_host, int32_t rank, int32_t world);
 int nbmf_comm_world(nbmf_ctx* ctx);
+/* a communicator that outlives contexts (ncclCommInitRank costs ~1 s): create once per set of ranks, attach
+ * to every context that shards over them, destroy after the last context is gone */
+int nbmf_comm_create(const void* id128_host, int32_t rank, int32_t world, void** comm_out);
+int nbmf_comm_attach(nbmf_ctx* ctx, void* comm, int32_t rank, int32_t world);
+int nbmf_comm_destroy(void* comm);
 /* engine actually selected for this context: NBMF_ENGINE_SIMT or NBMF_ENGINE_TENSOR */
 int nbmf_engine(nbmf_ctx* ctx);
 

@@ -62,6 +62,9 @@ SIGNATURES = {
     "nbmf_comm_unique_id": (_INT, [_P]),
     "nbmf_comm_init": (_INT, [_P, _P, _I32, _I32]),
     "nbmf_comm_world": (_INT, [_P]),
+    "nbmf_comm_create": (_INT, [_P, _I32, _I32, C.POINTER(_P)]),
+    "nbmf_comm_attach": (_INT, [_P, _P, _I32, _I32]),
+    "nbmf_comm_destroy": (_INT, [_P]),
     "nbmf_engine": (_INT, [_P]),
     "nbmf_fma_peak": (_INT, [_INT, _I32, _P, _P, C.POINTER(_DBL)]),
     "nbmf_profile_enable": (_INT, [_P, _INT]),

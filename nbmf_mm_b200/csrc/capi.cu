@@ -129,6 +129,7 @@ struct nbmf_ctx {
   bool poll_pending = false;
   // comm
   void* comm = nullptr;
+  bool owns_comm = false;
   int world = 1, rank = 0;
   // optional per-launch timing of the two pass kernels (bench.py roofline)
   bool profile = false;
@@ -326,7 +327,7 @@ extern "C" int nbmf_create(const nbmf_config* cfg, void* ws, int64_t ws_bytes, v
 
 extern "C" int nbmf_destroy(nbmf_ctx* c) {
   if (!c) return NBMF_OK;
-  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->comm && c->owns_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   prof_clear(c->prof_h);
   prof_clear(c->prof_w);
   if (c->poll_ev) cudaEventDestroy(c->poll_ev);
@@ -656,8 +657,36 @@ extern "C" int nbmf_comm_init(nbmf_ctx* c, const void* id128, int32_t rank, int3
   memcpy(&id, id128, 128);
   rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
   if (rc) return nccl_fail(rc, "ncclCommInitRank");
+  c->owns_comm = true;
   c->world = world;
   c->rank = rank;
+  return NBMF_OK;
+}
+// A communicator that outlives contexts: ncclCommInitRank costs ~1 s, a caller that fits many problems on
+// the same ranks creates it once and attaches it to every context.
+extern "C" int nbmf_comm_create(const void* id128, int32_t rank, int32_t world, void** comm_out) {
+  if (!id128 || !comm_out || world < 2 || rank < 0 || rank >= world) return fail(NBMF_ERR_ARG, "nbmf_comm_create: bad arguments");
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclId id;
+  memcpy(&id, id128, 128);
+  void* comm = nullptr;
+  rc = g_nccl.CommInitRank(&comm, world, id, rank);
+  if (rc) return nccl_fail(rc, "ncclCommInitRank");
+  *comm_out = comm;
+  return NBMF_OK;
+}
+extern "C" int nbmf_comm_attach(nbmf_ctx* c, void* comm, int32_t rank, int32_t world) {
+  if (!c || !comm || world < 2 || rank < 0 || rank >= world) return fail(NBMF_ERR_ARG, "nbmf_comm_attach: bad arguments");
+  if (c->comm && c->owns_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  c->comm = comm;
+  c->owns_comm = false;
+  c->world = world;
+  c->rank = rank;
+  return NBMF_OK;
+}
+extern "C" int nbmf_comm_destroy(void* comm) {
+  if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
   return NBMF_OK;
 }
 extern "C" int nbmf_comm_world(nbmf_ctx* c) { return c ? c->world : 0; }

@@ -48,6 +48,42 @@ __device__ long long* g_tc_trace = nullptr;       // [4 warp slots][TC_TRACE_BLO
 #define TC_EV(slot, b, e) do { } while (0)
 #endif
 
+// Per-entry ratio arithmetic of the tensor kernels, written as PTX so that ONE predicate per entry (the data
+// bit) drives both the choice of x and the masking of the outputs: ptxas otherwise rebuilds a 32-bit mask
+// per entry with two shifts, and the ALU pipe (shifts, logic, selects) is the busiest SIMT pipe here.
+//   H pass: x = (p ? theta : 1 - theta) + eps, r = 1/x, tf32 hi / lo of r, and their copies masked by p.
+__device__ __forceinline__ void h_entry(float theta, uint32_t bits, uint32_t bit, float eps, float& x, float& hi,
+                                        float& lo, float& phi, float& plo) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f32 y, r;\n\t"
+      "and.b32 t, %6, %7;\n\tsetp.ne.b32 p, t, 0;\n\t"
+      "mov.f32 y, %5;\n\t@!p sub.f32 y, 0f3F800000, y;\n\t"
+      "add.f32 y, y, %8;\n\t"
+      "rcp.approx.ftz.f32 r, y;\n\t"
+      "and.b32 %1, r, 0xffffe000;\n\t"
+      "sub.f32 %2, r, %1;\n\t"
+      "selp.f32 %3, %1, 0f00000000, p;\n\t"
+      "selp.f32 %4, %2, 0f00000000, p;\n\t"
+      "mov.f32 %0, y;\n\t}\n"
+      : "=f"(x), "=f"(hi), "=f"(lo), "=f"(phi), "=f"(plo)
+      : "f"(theta), "r"(bits), "r"(bit), "f"(eps));
+}
+//   W pass: signed ratio s = 1/(theta + eps) on ones, -1/((1 - theta) + eps) on observed zeros, 0 on unobserved
+//   entries; q accumulates the zeros' 1/x (= -s) with one predicated subtract.
+__device__ __forceinline__ void w_entry(float theta, uint32_t pbits, uint32_t obits, uint32_t bit, float eps, float& s,
+                                        float& q) {
+  asm("{\n\t.reg .pred p, o;\n\t.reg .b32 t;\n\t.reg .f32 y;\n\t"
+      "and.b32 t, %3, %5;\n\tsetp.ne.b32 p, t, 0;\n\t"
+      "and.b32 t, %4, %5;\n\tsetp.ne.b32 o, t, 0;\n\t"
+      "add.f32 y, %2, %6;\n\t"
+      "@!p add.f32 y, %2, 0fBF800000;\n\t"
+      "@!p sub.f32 y, y, %6;\n\t"
+      "rcp.approx.ftz.f32 y, y;\n\t"
+      "selp.f32 %0, y, 0f00000000, o;\n\t"
+      "@!p sub.f32 %1, %1, %0;\n\t}\n"
+      : "=f"(s), "+f"(q)
+      : "f"(theta), "r"(pbits), "r"(obits), "r"(bit), "f"(eps));
+}
+
 struct HTcArgs {
   const float* H;            // [32][ldh] k-major factor (pad rows/columns 0.5): source of the resident A tile
   const float* Wf;           // [mpad/32][4][1024]  W rows hi | lo | W^T hi | lo   (format_factors.cu)
@@ -78,7 +114,7 @@ constexpr int TC_MMA1_WARP = 16;                        // + group
 constexpr int TC_MMA2_WARP = 18;                        // + group
 constexpr int TC_TMA_WARP = 20;
 constexpr int TC_THREADS = 21 * 32;
-constexpr int kFlush = 8;                               // own blocks per TMEM accumulation chain
+constexpr int kFlush = 8;                                // own blocks per TMEM accumulation chain
 
 // =====================================================================================
 // H pass (TMEM lane = column j).  CTA = 128 columns j, streams 32-row blocks of W.
@@ -289,15 +325,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
         float prod = 1.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float theta = __uint_as_float(v[8 * u + e]);
-          const bool p = (bits >> (8 * u + e)) & 1u;
-          const float x = (p ? theta : (1.0f - theta)) + eps;
-          const float r = rcp_(x);
+          float x, hi, lo, phi, plo;
+          h_entry(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps, x, hi, lo, phi, plo);
           prod = (e & 3) ? prod * x : x;
           if ((e & 3) == 3) llb += logu_(prod);                        // eps >= 1e-9: four factors cannot underflow
-          const float hi = tf32_trunc(r), lo = r - hi;
-          out[e] = __float_as_uint(p ? hi : 0.0f);
-          out[8 + e] = __float_as_uint(p ? lo : 0.0f);
+          out[e] = __float_as_uint(phi);
+          out[8 + e] = __float_as_uint(plo);
           out[16 + e] = __float_as_uint(hi);
           out[24 + e] = __float_as_uint(lo);
         }
@@ -356,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
 // =====================================================================================
 // W pass (TMEM lane = row i).  CTA = 128 rows i, streams 64-column blocks of H.
 //   MMA1: Theta'[128 i x 64 j] = W[128 x 32 k] . Ht[64 j x 32 k]^T
-//   SIMT: signed ratio s = 1/(+-x) on observed entries (= p - q), q-sum from sum|s| - sum s, s -> TMEM (hi, lo)
+//   SIMT: signed ratio s = 1/(+-x) on observed entries (= p - q), q-sum of the zeros' 1/x, s -> TMEM (hi, lo)
 //   MMA2: G[128 i x 32 k] += S[128 x 64 j] . H[32 k x 64 j]^T
 // TMEM: A hi 0..31, lo 32..63 | Theta[g] 64..191 | S[g] 192..447 (per 8 columns: S_hi S_lo) | G[g] 448..511
 // =====================================================================================
@@ -526,11 +559,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
       if (b + 2 < nb) word = pm[(size_t)(2 * (b + 2)) * 128];
       if (!ok_theta) mbar_wait(&bar_theta[g], ob & 1);
       fence_after_sync();
-      float sum_s = 0.f, sum_a = 0.f;
+      float qb = 0.f;                                                  // this block's sum over the observed zeros of 1/x
       bool ok_sfree = true;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        uint32_t v[16], out[32];
+        uint32_t v[16];
         tmem_ld16(tTheta + 64 * g + lane_off + 32 * h + 16 * u, v);
         if (u == 0 && b >= 2) ok_sfree = mbar_try(smem_u32(&bar_sfree[g]), (ob - 1) & 1);
         wait_ld();
@@ -540,23 +573,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
           if (lane == 0) mbar_arrive(&bar_tfree[g]);
         }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float theta = __uint_as_float(v[e]);
-          const bool p = (bits.x >> (16 * u + e)) & 1u, o = (bits.y >> (16 * u + e)) & 1u;
-          const float xs = p ? theta + eps : (theta - 1.0f) - eps;     // -(1 - theta + eps) for the zeros
-          float s = rcp_(xs);
-          s = o ? s : 0.0f;
-          sum_s += s;
-          sum_a += fabsf(s);
-          const float hi = tf32_trunc(s);
-          out[16 * (e >> 3) + (e & 7)] = __float_as_uint(hi);
-          out[16 * (e >> 3) + 8 + (e & 7)] = __float_as_uint(s - hi);
+        for (int w = 0; w < 2; ++w) {                                  // 8 entries = one K step of MMA2: S_hi | S_lo
+          uint32_t out[16];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float sv;
+            w_entry(__uint_as_float(v[8 * w + e]), bits.x, bits.y, 1u << (16 * u + 8 * w + e), eps, sv, qb);
+            const float hi = tf32_trunc(sv);
+            out[e] = __float_as_uint(hi);
+            out[8 + e] = __float_as_uint(sv - hi);
+          }
+          if (u == 0 && w == 0) {                                      // MMA2(b-2) must be done reading S[g]
+            if (!ok_sfree) mbar_wait(&bar_sfree[g], (ob - 1) & 1);
+            fence_after_sync();
+          }
+          tmem_st16(tS + 128 * g + lane_off + 16 * (4 * h + 2 * u + w), out);
         }
-        if (u == 0) {                                                  // MMA2(b-2) must be done reading S[g]
-          if (!ok_sfree) mbar_wait(&bar_sfree[g], (ob - 1) & 1);
-          fence_after_sync();
-        }
-        tmem_st32(tS + 128 * g + lane_off + 16 * (4 * h + 2 * u), out);
       }
       ok_theta = b + 2 < nb && mbar_try(smem_u32(&bar_theta[g]), (ob + 1) & 1);
       if (ob > 0 && (ob % kFlush) == 0) flush();                       // previous chain: its MMAs ended a block ago
@@ -564,7 +596,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_s[g]);
-      qsum += 0.5f * (sum_a - sum_s);                                  // sum over the observed zeros of 1/x
+      qsum += qb;
     }
     if (g < nb) flush();
     sQ[w4 * 128 + tl] = qsum;

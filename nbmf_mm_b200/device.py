@@ -311,19 +311,37 @@ class DeviceProblem:
 
     # -- multi-GPU
     def init_comm(self, group=None):
-        """Join the row-shard communicator: rank 0 creates an NCCL unique id, torch.distributed
-        (any backend) carries it to the other ranks, every rank calls ncclCommInitRank."""
+        """Join the row-shard communicator of ``group``: rank 0 creates an NCCL unique id, torch.distributed
+        (any backend) carries it to the other ranks, every rank calls ncclCommInitRank.  The communicator is
+        created once per (group, device) and re-attached to later problems (ncclCommInitRank costs ~1 s)."""
         import torch.distributed as dist
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         if world == 1:
             return
-        _lib.nccl_library_hint()
-        buf = (C.c_ubyte * 128)()
-        if rank == 0:
-            _lib.check(self.lib.nbmf_comm_unique_id(buf), "nbmf_comm_unique_id")
-        payload = [bytes(buf)]
-        dist.broadcast_object_list(payload, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        raw = (C.c_ubyte * 128).from_buffer_copy(payload[0])
-        self._call("nbmf_comm_init", raw, rank, world)
+        key = (id(group) if group is not None else None, world, rank, self.dev.index)
+        comm = _COMM_CACHE.get(key)
+        if comm is None:
+            _lib.nccl_library_hint()
+            buf = (C.c_ubyte * 128)()
+            if rank == 0:
+                _lib.check(self.lib.nbmf_comm_unique_id(buf), "nbmf_comm_unique_id")
+            payload = [bytes(buf)]
+            dist.broadcast_object_list(payload, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            raw = (C.c_ubyte * 128).from_buffer_copy(payload[0])
+            handle = C.c_void_p()
+            _lib.check(self.lib.nbmf_comm_create(raw, rank, world, C.byref(handle)), "nbmf_comm_create")
+            comm = _COMM_CACHE[key] = handle
+        self._call("nbmf_comm_attach", comm, rank, world)
         self.world = world
+
+
+_COMM_CACHE = {}
+
+
+def destroy_cached_comms():
+    """Destroy the cached NCCL communicators (call before torch.distributed.destroy_process_group)."""
+    lib = _lib.load()
+    for comm in _COMM_CACHE.values():
+        lib.nbmf_comm_destroy(comm)
+    _COMM_CACHE.clear()

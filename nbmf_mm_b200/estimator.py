@@ -30,6 +30,29 @@ _ORIENTATION_ALIASES = {
 }
 
 
+def partition_restarts(n_init, rank, world):
+    """Restarts of this rank: r = rank, rank + world, ... (independent fits, no collective)."""
+    return list(range(int(rank), int(n_init), int(world)))
+
+
+def reduce_best_restart(local_best, group=None):
+    """``local_best`` = (final_loss, restart_index, payload) of this rank's best restart, or None if it ran
+    none.  Every rank gets (payload, restart_index) of the globally best restart: lowest final loss, ties to
+    the lowest restart index (= what a sequential loop over the restarts keeps).  Uses only object
+    collectives of torch.distributed, so it runs on any backend (gloo in the CPU tests)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    scores = [None] * world
+    dist.all_gather_object(scores, None if local_best is None else (float(local_best[0]), int(local_best[1])), group=group)
+    ranked = sorted((s[0], s[1], r) for r, s in enumerate(scores) if s is not None)
+    if not ranked:
+        raise ValueError("no rank ran a restart")
+    _, best_idx, owner = ranked[0]
+    box = [local_best[2] if rank == owner else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    return box[0], best_idx
+
+
 class NBMFMM(BaseEstimator, TransformerMixin):
     """Non-negative Binary Matrix Factorization via Majorization-Minimization on B200.
 
@@ -48,7 +71,13 @@ class NBMFMM(BaseEstimator, TransformerMixin):
     mask_semantics : {"reference", "strict"}, default "reference"
         "reference" reproduces the reference's H-step/loss treatment of unobserved entries as
         observed zeros (``_solver.py:43,153-154``); "strict" is the README/paper behaviour.
-    device : torch device or None;  distributed : bool, row-shard over torch.distributed.
+    device : torch device or None.
+    distributed : {False, True, "rows", "restarts"}
+        True / "rows": one problem row-sharded over the ranks of torch.distributed (one rank per GPU), H
+        partials summed with an NCCL allreduce per iteration.  "restarts": the ``n_init`` restarts are dealt
+        round-robin to the ranks (restart r on rank r % world, whole problem on that rank's GPU, no
+        data-path collective); the final losses are compared across ranks and the winner's factors are
+        broadcast, so every rank ends with the same fitted estimator.
     engine : {"auto", "simt", "tensor"}: CUDA-core (packed FFMA2) kernels or the tcgen05/TMEM 3xTF32
         kernels (float32, binary X, K <= 32 only); "auto" picks tensor when eligible and m, n >= 512.
     """
@@ -106,8 +135,18 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         if n_init < 1:
             raise ValueError("n_init must be >= 1")
 
+        if self.distributed not in (False, True, "rows", "restarts"):
+            raise ValueError(f"distributed must be False, True, 'rows' or 'restarts', got {self.distributed!r}")
+        rank, world = 0, 1
+        by_restart = self.distributed == "restarts"
+        if by_restart:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        row_sharded = self.distributed in (True, "rows")
+
         best = None
-        for r in range(n_init):
+        for r in (partition_restarts(n_init, rank, world) if by_restart else range(n_init)):
             seed = self.random_state if (self.random_state is None or n_init == 1) else self.random_state + r
             stats = {}
             out = nbmf_mm_solver(
@@ -115,10 +154,14 @@ class NBMFMM(BaseEstimator, TransformerMixin):
                 alpha=self.alpha, beta=self.beta, W_init=self.W_init, H_init=self.H_init, mask=mask,
                 random_state=seed, verbose=self.verbose, orientation=orientation,
                 projection_method=self.projection_method, mask_semantics=self.mask_semantics,
-                dtype=self.dtype, device=self.device, distributed=self.distributed, stats=stats,
+                dtype=self.dtype, device=self.device, distributed=row_sharded, stats=stats,
                 engine=self.engine)
             if best is None or out[2][-1] < best[0][2][-1]:
                 best = (out, stats, r)
+        if by_restart and world > 1:
+            local = None if best is None else (best[0][2][-1], best[2], (best[0], best[1]))
+            (out, stats), best_r = reduce_best_restart(local)
+            best = (out, stats, best_r)
         (W, H, losses, _, n_iter), stats, best_r = best
 
         self.W_ = W

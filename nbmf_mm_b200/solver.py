@@ -29,6 +29,15 @@ class PreparedData:
     Vm: object                 # torch tensor V*mask  (dense)
     n_obs: float               # Y.size or count_nonzero(mask), _solver.py:151,155
     h2d_bytes: int = 0
+    pending: object = None     # deferred device work (P &= M, orientation, n_obs): see finish()
+
+    def finish(self):
+        """Run the device-side part of the preparation that was deferred so that the host could do other
+        work (drawing the inits) while the asynchronous H2D copies of the bit planes were in flight."""
+        if self.pending is not None:
+            todo, self.pending = self.pending, None
+            todo(self)
+        return self
 
 
 def _densify(a):
@@ -46,7 +55,7 @@ def _as_bool_mask(mask, shape):
     return mask
 
 
-def prepare_data(Y, mask, *, transpose, dtype, device) -> PreparedData:
+def prepare_data(Y, mask, *, transpose, dtype, device, defer=False) -> PreparedData:
     """Validate, orient, pack and upload V and the observation mask.
 
     Binary V goes to two 1-bit planes (packed on the host, so the H2D copy is 32-64x smaller
@@ -68,14 +77,20 @@ def prepare_data(Y, mask, *, transpose, dtype, device) -> PreparedData:
         if M is not None and not M.is_device:
             h2d += M.words.nbytes if isinstance(M.words, np.ndarray) else M.words.numel() * 4
             M = M.to_device(dev)
-        if M is not None:
-            P = P & M
-        if transpose:
-            P = P.transpose()
-            M = M.transpose() if M is not None else None
-        m, n = P.shape
-        n_obs = float(M.count()) if M is not None else float(m) * float(n)
-        return PreparedData(m, n, "bits", P, M, None, n_obs, h2d)
+        m, n = (P.shape[1], P.shape[0]) if transpose else P.shape
+
+        def device_part(d):                                   # everything that waits for the copies
+            Pd, Md = d.P, d.M
+            if Md is not None:
+                Pd = Pd & Md
+            if transpose:
+                Pd = Pd.transpose()
+                Md = Md.transpose() if Md is not None else None
+            d.P, d.M = Pd, Md
+            d.n_obs = float(Md.count()) if Md is not None else float(d.m) * float(d.n)
+
+        data = PreparedData(m, n, "bits", P, M, None, float("nan"), h2d, pending=device_part)
+        return data if defer else data.finish()
 
     Y = np.asarray(_densify(Y), dtype=np.float64)
     if Y.ndim != 2:
@@ -174,7 +189,9 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     if random_state is not None:
         np.random.seed(random_state)                      # global legacy stream, as _solver.py:102-103
     transpose = orientation == "dir-beta"
-    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device)
+    # bit-packed host inputs: the H2D copies are asynchronous (pinned memory); the inits are drawn on the
+    # host while they are in flight and the device-side preparation runs afterwards (data.finish())
+    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True)
     m, n, k = data.m, data.n, int(n_components)
     if shard is not None:
         if transpose or not distributed:
@@ -188,6 +205,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         H_init = np.random.uniform(0.1, 0.9, (k, n))
     W_init = np.asarray(W_init, dtype=np.float64)
     H_init = np.asarray(H_init, dtype=np.float64)
+    data.finish()
 
     rank, world = 0, 1
     if distributed:

@@ -89,3 +89,36 @@ def test_row_sharded_step_equals_unsharded(tmp_path, m, n, k):
     assert np.max(np.abs(res["W1"] - W1)) < 1e-13
     _, _, LL = _partials(Y, W, H, mask)
     assert abs(res["LL"] - LL) < 1e-10 * abs(LL)
+
+
+def _restart_worker(rank, world, port, n_init, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nbmf_mm_b200.estimator import partition_restarts, reduce_best_restart
+        losses = np.random.default_rng(7).permutation(n_init).astype(np.float64) // 2     # ties on purpose
+        mine = partition_restarts(n_init, rank, world)
+        best = None
+        for r in mine:                                          # stand-in for the per-restart fit
+            if best is None or losses[r] < best[0]:
+                best = (losses[r], r, {"restart": r, "W": np.full((2, 2), float(r))})
+        payload, idx = reduce_best_restart(best)
+        assert payload["restart"] == idx and np.all(payload["W"] == idx)
+        if rank == 0:
+            np.savez(out, idx=idx, mine=np.asarray(mine))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_init", [1, 5, 8])
+def test_restart_partition_keeps_what_a_sequential_loop_keeps(tmp_path, n_init):
+    """n_init restarts dealt round-robin to the ranks, no data-path collective; the winner is the restart a
+    sequential loop with `<` keeps (lowest loss, first index among ties) and every rank receives it."""
+    from nbmf_mm_b200.estimator import partition_restarts
+    assert sorted(partition_restarts(n_init, 0, 2) + partition_restarts(n_init, 1, 2)) == list(range(n_init))
+    out = str(tmp_path / "best.npz")
+    mp.spawn(_restart_worker, args=(2, _free_port(), n_init, out), nprocs=2, join=True)
+    losses = np.random.default_rng(7).permutation(n_init).astype(np.float64) // 2
+    want = int(np.argmin(losses))                                # first index among ties
+    assert int(np.load(out)["idx"]) == want

@@ -49,6 +49,8 @@ def _worker(rank, world, port, dtype, out):
         if rank == 0:
             np.savez(out, W=runs[0][0], H=runs[0][1], losses=runs[0][2], n_iter=runs[0][3])
     finally:
+        from nbmf_mm_b200.device import destroy_cached_comms
+        destroy_cached_comms()
         dist.destroy_process_group()
 
 
@@ -67,3 +69,37 @@ def test_two_gpus_match_one(tmp_path, dtype, tol):
     assert int(res["n_iter"]) == n_iter
     assert np.max(np.abs(res["losses"] - np.asarray(losses)) / np.abs(losses)) < tol
     assert np.max(np.abs(res["W"] - W)) < tol * 10 and np.max(np.abs(res["H"] - H)) < tol * 10
+
+
+def _restart_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from nbmf_mm_b200 import NBMF
+        X, mask = _problem()
+        est = NBMF(n_components=6, max_iter=40, tol=0.0, random_state=3, n_init=5, dtype="float64",
+                   distributed="restarts").fit(X, mask=mask)
+        if rank == 1:                                            # the non-owner ranks hold the winner too
+            np.savez(out, W=est.W_, H=est.components_, losses=np.asarray(est.loss_curve_), best=est.best_init_)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_restarts_partitioned_over_two_gpus_match_sequential(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nbmf_mm_b200 import NBMF
+    out = str(tmp_path / "restarts.npz")
+    mp.spawn(_restart_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    X, mask = _problem()
+    seq = NBMF(n_components=6, max_iter=40, tol=0.0, random_state=3, n_init=5, dtype="float64").fit(X, mask=mask)
+    assert int(got["best"]) == seq.best_init_
+    assert np.array_equal(got["W"], seq.W_) and np.array_equal(got["H"], seq.components_)
+    assert np.array_equal(got["losses"], np.asarray(seq.loss_curve_))
