@@ -85,6 +85,14 @@ int nbmf_pack_bits(const void* x_dev, int x_dtype, int64_t ldx, const void* mask
 /* dense X [+ mask] -> V*mask in out_dtype with leading dimension nbmf_padded_cols(n), zero padded */
 int nbmf_pack_dense(const void* x_dev, int x_dtype, int64_t ldx, const void* mask_dev, int mask_dtype, int64_t ldm,
                     int64_t m, int64_t n, int out_dtype, void* vm_dev, void* stream);
+/* CSR matrix (int64 indptr[m+1], int32 indices, optional f32/f64 data; all device pointers) -> bit plane, no dense
+ * M x N intermediate (the reference densifies sparse X and mask: _base.py:83-87, _solver.py:106-107).  Explicit
+ * zeros stay zero bits.  *flags_host: bit 0 = a stored value is not 0 or 1, bit 1 = a stored value is outside [0, 1].
+ * Synchronises the stream. */
+int nbmf_pack_csr(const int64_t* indptr_dev, const int32_t* indices_dev, const void* data_dev, int data_dtype, int64_t m,
+                  int64_t n, uint32_t* p_bits_dev, int32_t* flags_dev, int32_t* flags_host, void* stream);
+/* inverse_transform (_base.py:201-210): out (m x n, row-major, dtype) = clip(W (m x k) @ H (k x n), 0, 1) */
+int nbmf_reconstruct(int dtype, const void* w_dev, const void* h_dev, int64_t m, int64_t n, int32_t k, void* out_dev, void* stream);
 /* bit-plane transpose (m x n bits -> n x m bits): dir-beta runs as beta-dir on V^T (_solver.py:113-123) */
 int nbmf_transpose_bits(const uint32_t* src_dev, int64_t m, int64_t n, uint32_t* dst_dev, void* stream);
 /* number of set bits of a plane (count_nonzero(mask), _solver.py:155); synchronises the stream */

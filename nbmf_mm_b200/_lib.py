@@ -41,6 +41,8 @@ SIGNATURES = {
     "nbmf_pack_bits": (_INT, [_P, _INT, _I64, _P, _INT, _I64, _I64, _I64, _P, _P, _P]),
     "nbmf_pack_dense": (_INT, [_P, _INT, _I64, _P, _INT, _I64, _I64, _I64, _INT, _P, _P]),
     "nbmf_transpose_bits": (_INT, [_P, _I64, _I64, _P, _P]),
+    "nbmf_pack_csr": (_INT, [_P, _P, _P, _INT, _I64, _I64, _P, _P, C.POINTER(_I32), _P]),
+    "nbmf_reconstruct": (_INT, [_INT, _P, _P, _I64, _I64, _I32, _P, _P]),
     "nbmf_popcount_bits": (_INT, [_P, _I64, _I64, _P, C.POINTER(C.c_uint64), _P]),
     "nbmf_synth_bits": (_INT, [C.c_uint64, _I64, _I64, _I64, _P, _I32, C.c_float, _P, _P, _P]),
     "nbmf_workspace_bytes": (_I64, [C.POINTER(NbmfConfig)]),

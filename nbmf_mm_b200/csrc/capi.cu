@@ -266,6 +266,24 @@ extern "C" int nbmf_pack_dense(const void* x, int xdt, int64_t ldx, const void* 
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }
+extern "C" int nbmf_pack_csr(const int64_t* indptr, const int32_t* indices, const void* data, int data_dtype, int64_t m,
+                             int64_t n, uint32_t* P, int32_t* flags_dev, int32_t* flags_host, void* stream) {
+  if (!indptr || !P || !flags_dev || !flags_host || m < 1 || n < 1)     // indices may be NULL when nnz == 0
+    return fail(NBMF_ERR_ARG, "nbmf_pack_csr: bad arguments");
+  if (data && data_dtype != NBMF_F32 && data_dtype != NBMF_F64) return fail(NBMF_ERR_ARG, "nbmf_pack_csr: data must be f32 or f64");
+  launch_pack_csr(indptr, indices, data, data_dtype, m, n, nbmf_words_per_row(n), P, flags_dev, (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  CUDA_TRY(cudaMemcpyAsync(flags_host, flags_dev, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return NBMF_OK;
+}
+extern "C" int nbmf_reconstruct(int dtype, const void* w, const void* h, int64_t m, int64_t n, int32_t k, void* out, void* stream) {
+  if (!w || !h || !out || m < 1 || n < 1 || k < 1 || k > 64) return fail(NBMF_ERR_ARG, "nbmf_reconstruct: bad arguments (k in 1..64)");
+  if (dtype != NBMF_F32 && dtype != NBMF_F64) return fail(NBMF_ERR_ARG, "dtype must be NBMF_F32 or NBMF_F64");
+  launch_reconstruct(dtype, w, h, m, n, k, out, (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
 extern "C" int nbmf_transpose_bits(const uint32_t* src, int64_t m, int64_t n, uint32_t* dst, void* stream) {
   if (!src || !dst || m < 1 || n < 1) return fail(NBMF_ERR_ARG, "nbmf_transpose_bits: bad arguments");
   launch_transpose_bits(src, m, n, nbmf_words_per_row(n), dst, nbmf_words_per_row(m), (cudaStream_t)stream);

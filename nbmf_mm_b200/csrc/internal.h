@@ -57,6 +57,9 @@ void launch_pack_bits(int in_dtype, const void* X, int64_t ldx, const void* mask
                       int64_t m, int64_t n, int64_t wpr, uint32_t* P, uint32_t* M, cudaStream_t st);
 void launch_pack_dense(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
                        int64_t m, int64_t n, int out_dtype, int64_t ldv, void* Vm, cudaStream_t st);
+void launch_pack_csr(const int64_t* indptr, const int32_t* indices, const void* data, int data_dtype, int64_t m,
+                     int64_t n, int64_t wpr, uint32_t* P, int* flags, cudaStream_t st);
+void launch_reconstruct(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, void* out, cudaStream_t st);
 void launch_transpose_bits(const uint32_t* src, int64_t m, int64_t n, int64_t wpr_src, uint32_t* dst,
                            int64_t wpr_dst, cudaStream_t st);
 void launch_rowcount(int dtype, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, void* out, cudaStream_t st);

@@ -390,6 +390,67 @@ void launch_transpose_bits(const uint32_t* src, int64_t m, int64_t n, int64_t wp
   transpose_bits_kernel<<<(unsigned)nb, 256, 0, st>>>(src, m, n, wpr_src, dst, wpr_dst);
 }
 
+// CSR -> bit plane without a dense M x N intermediate (reference densifies: _base.py:83-87, _solver.py:106-107).
+// One warp per row; explicit zeros in `data` stay zero bits.  Returns (through `flags`) whether any stored value
+// lies outside {0, 1} (bit 0) or outside [0, 1] (bit 1), which the host turns into the reference's errors.
+template <typename Val>
+__global__ void pack_csr_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                const Val* __restrict__ data, int64_t m, int64_t n, int64_t wpr, uint32_t* __restrict__ P,
+                                int* __restrict__ flags) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= m) return;
+  const int lane = threadIdx.x & 31;
+  int bad = 0;
+  for (int64_t e = indptr[row] + lane; e < indptr[row + 1]; e += 32) {
+    const int64_t col = indices[e];
+    const double v = data ? (double)data[e] : 1.0;
+    if (v != 0.0 && v != 1.0) bad |= 1;
+    if (!(v >= 0.0 && v <= 1.0)) bad |= 2;
+    if (v != 0.0 && col >= 0 && col < n) atomicOr(&P[row * wpr + (col >> 5)], 1u << (col & 31));   // integer atomics
+  }
+  if (bad) atomicOr(flags, bad);
+}
+void launch_pack_csr(const int64_t* indptr, const int32_t* indices, const void* data, int data_dtype, int64_t m,
+                     int64_t n, int64_t wpr, uint32_t* P, int* flags, cudaStream_t st) {
+  cudaMemsetAsync(P, 0, (size_t)m * wpr * 4, st);
+  cudaMemsetAsync(flags, 0, sizeof(int), st);
+  const unsigned grid = (unsigned)((m + 7) / 8);
+  if (!data || data_dtype == 1) pack_csr_kernel<double><<<grid, 256, 0, st>>>(indptr, indices, (const double*)data, m, n, wpr, P, flags);
+  else pack_csr_kernel<float><<<grid, 256, 0, st>>>(indptr, indices, (const float*)data, m, n, wpr, P, flags);
+}
+
+// inverse_transform (_base.py:201-210): out = clip(W @ H, 0, 1), dense m x n by contract.  Block = 128 columns
+// x 8 rows; H is read coalesced, the 8 W rows sit in shared memory.
+template <typename Real>
+__global__ void reconstruct_kernel(const Real* __restrict__ W, const Real* __restrict__ H, int64_t m, int64_t n, int k,
+                                   Real* __restrict__ out) {
+  __shared__ Real sw[8][64];
+  const int64_t r0 = (int64_t)blockIdx.y * 8;
+  for (int t = threadIdx.x; t < 8 * k; t += blockDim.x) {
+    const int r = t / k, kk = t % k;
+    sw[r][kk] = r0 + r < m ? W[(r0 + r) * k + kk] : Real(0);
+  }
+  __syncthreads();
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Real acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = Real(0);
+  for (int kk = 0; kk < k; ++kk) {
+    const Real h = H[(int64_t)kk * n + j];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = fma(sw[r][kk], h, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (r0 + r < m) out[(r0 + r) * n + j] = fmin(fmax(acc[r], Real(0)), Real(1));
+}
+void launch_reconstruct(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, void* out, cudaStream_t st) {
+  dim3 grid((unsigned)((n + 127) / 128), (unsigned)((m + 7) / 8));
+  if (dtype == 0) reconstruct_kernel<float><<<grid, 128, 0, st>>>((const float*)W, (const float*)H, m, n, k, (float*)out);
+  else reconstruct_kernel<double><<<grid, 128, 0, st>>>((const double*)W, (const double*)H, m, n, k, (double*)out);
+}
+
 template <typename Real>
 __global__ void rowcount_kernel(const uint32_t* __restrict__ M, int64_t m, int64_t wpr, Real* __restrict__ out) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

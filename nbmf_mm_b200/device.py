@@ -97,6 +97,47 @@ def pack_dense_device(X_dev, mask_dev, dtype):
     return Vm
 
 
+def pack_csr_device(A, device):
+    """scipy.sparse matrix -> (BitMatrix on ``device``, flags) without a dense host or device copy: only
+    indptr / indices / data cross PCIe.  flags bit 0: a stored value is not 0/1, bit 1: outside [0, 1]."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = require_cuda(device)
+    A = A.tocsr()
+    m, n = A.shape
+    indptr = torch.from_numpy(np.ascontiguousarray(A.indptr, dtype=np.int64)).to(dev)
+    indices = torch.from_numpy(np.ascontiguousarray(A.indices, dtype=np.int32)).to(dev)
+    data = None
+    if A.data.dtype != np.bool_:
+        dt = np.float32 if A.data.dtype == np.float32 else np.float64
+        data = torch.from_numpy(np.ascontiguousarray(A.data, dtype=dt)).to(dev)
+    P = torch.empty((m, words_per_row(n)), dtype=torch.int32, device=dev)
+    flags_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    flags = C.c_int32(0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nbmf_pack_csr(_ptr(indptr), _ptr(indices), _ptr(data), (0 if data.dtype == torch.float32 else 1) if data is not None else 0,
+                                     m, n, _ptr(P), _ptr(flags_dev), C.byref(flags), _stream(dev)), "nbmf_pack_csr")
+    h2d = indptr.numel() * 8 + indices.numel() * 4 + (0 if data is None else data.numel() * data.element_size())
+    return BitMatrix(P, (m, n)), int(flags.value), h2d
+
+
+def reconstruct_device(W, H, dtype, device):
+    """clip(W @ H, 0, 1) on the device (``_base.py:201-210``); returns a host float64 array."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = require_cuda(device)
+    tdt = getattr(torch, np.dtype(dtype).name)
+    Wd = torch.from_numpy(np.ascontiguousarray(W, dtype=np.dtype(dtype))).to(dev)
+    Hd = torch.from_numpy(np.ascontiguousarray(H, dtype=np.dtype(dtype))).to(dev)
+    m, k = Wd.shape
+    n = Hd.shape[1]
+    out = torch.empty((m, n), dtype=tdt, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nbmf_reconstruct(dtype_code(dtype), _ptr(Wd), _ptr(Hd), m, n, k, _ptr(out), _stream(dev)),
+                   "nbmf_reconstruct")
+    return out.cpu().numpy().astype(np.float64)
+
+
 def transpose_device(B: BitMatrix) -> BitMatrix:
     torch = _torch()
     lib = _lib.load()

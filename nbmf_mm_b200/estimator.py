@@ -14,6 +14,7 @@ from sklearn.utils import check_array
 
 from ._utils import check_is_fitted
 from .bits import BitMatrix
+from .device import reconstruct_device
 from .solver import make_problem, nbmf_mm_solver, prepare_data
 
 # exact-key alias table of the reference (_base.py:127-137); keys are NOT case-folded
@@ -116,17 +117,14 @@ class NBMFMM(BaseEstimator, TransformerMixin):
     def _validate_X(X):
         if isinstance(X, BitMatrix):
             return X
-        X = check_array(X, accept_sparse="csr", dtype=np.float64)     # _base.py:83
-        if hasattr(X, "toarray"):
-            X = X.toarray()
-        return X
+        return check_array(X, accept_sparse="csr", dtype=np.float64)  # _base.py:83; CSR stays CSR (packed on the device)
 
     # ------------------------------------------------------------------ fit
     def fit(self, X, y=None, mask=None):
         """Fit the model to binary (or [0,1]-valued) data ``X`` (``_base.py:80-122``)."""
         X = self._validate_X(X)
-        if not isinstance(X, BitMatrix) and not np.all((X >= 0) & (X <= 1)):
-            raise ValueError("X must be binary")                       # _base.py:90-91
+        if isinstance(X, np.ndarray) and not np.all((X >= 0) & (X <= 1)):
+            raise ValueError("X must be binary")                       # _base.py:90-91 (sparse X: checked on the device)
         orientation = self._normalize_orientation(self.orientation)
         self.orientation = orientation                                 # reference mutates it too (_base.py:95)
         if self.projection_method not in ("normalize", "duchi"):
@@ -212,7 +210,9 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         """``clip(W @ components_, 0, 1)`` (``_base.py:201-210``); dense M x N by contract."""
         check_is_fitted(self, ["components_"])
         W = check_array(W, dtype=np.float64)
-        return np.clip(W @ self.components_, 0.0, 1.0)
+        if W.shape[1] != self.components_.shape[0]:
+            raise ValueError(f"W has {W.shape[1]} components, the model has {self.components_.shape[0]}")
+        return reconstruct_device(W, self.components_, self.dtype, self.device)
 
     def score(self, X, mask=None):
         """Average log-likelihood per observed entry (``_base.py:212-247``).
@@ -234,6 +234,29 @@ class NBMFMM(BaseEstimator, TransformerMixin):
 
     def perplexity(self, X, mask=None):
         return float(np.exp(-self.score(X, mask)))
+
+    def evaluate(self, X, mask=None, W=None):
+        """Held-out evaluation of the FITTED factors on the entries selected by ``mask`` (validation / test
+        split), entirely on the device: properly masked mean negative log-likelihood per selected entry and its
+        exponential, i.e. ``compute_perplexity(Y, W_ @ components_, mask)`` of the reference's experiment
+        driver (``examples/reproduce_magron2022.py:40-47``) without materialising Theta.  ``W`` defaults to
+        ``W_`` (``X`` must then have the training rows); pass ``transform(X_new, mask=observed)`` for new rows.
+        Returns ``{"nll": float, "perplexity": float, "n_entries": int}``."""
+        check_is_fitted(self, ["components_"])
+        X = self._validate_X(X)
+        W = self.W_ if W is None else np.asarray(W, dtype=np.float64)
+        data = prepare_data(X, mask, transpose=False, dtype=self.dtype, device=self.device)
+        if (data.m, data.n) != (W.shape[0], self.components_.shape[1]):
+            raise ValueError(f"X is {data.m} x {data.n}, the factors are {W.shape[0]} x {self.components_.shape[1]}")
+        prob = make_problem(data, self.n_components, dtype=self.dtype, alpha=1.0, beta=1.0, eps=1e-8,
+                            mask_semantics="strict", projection="normalize", max_iter_cap=1, device=self.device,
+                            engine="simt")
+        try:
+            prob.set_factors(W, self.components_, normalize_w=False)
+            nll = float(prob.objective())
+        finally:
+            prob.close()
+        return {"nll": nll, "perplexity": float(np.exp(nll)), "n_entries": int(data.n_obs)}
 
 
 NBMF = NBMFMM

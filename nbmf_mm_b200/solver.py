@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 from .bits import BitMatrix
-from .device import DeviceProblem, pack_bits_device, pack_dense_device, require_cuda
+from .device import DeviceProblem, pack_bits_device, pack_csr_device, pack_dense_device, require_cuda
 
 _CANON = ("beta-dir", "dir-beta")
 
@@ -65,12 +65,31 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False) -> PreparedD
     """
     import torch
     dev = require_cuda(device)
+    extra_h2d = 0
+    if hasattr(Y, "tocsr"):
+        # sparse X: indptr / indices / data go to the device and are packed there; nothing M x N is ever built
+        # (the reference densifies: _base.py:83-87, _solver.py:106-107)
+        Pd, flags, extra_h2d = pack_csr_device(Y, dev)
+        if flags & 2:
+            raise ValueError("X must be binary")                      # _base.py:90-91
+        if flags & 1:
+            Y = Y.toarray()                                           # values strictly inside (0,1): dense layout
+            extra_h2d = 0
+        else:
+            if mask is not None and hasattr(mask, "tocsr"):
+                if mask.shape != Y.shape:
+                    raise ValueError(f"mask has shape {mask.shape}, expected {tuple(Y.shape)}")
+                mask, mflags, mh = pack_csr_device(mask, dev)
+                if mflags & 1:
+                    raise ValueError("mask must be binary (0/1 or bool): weighted masks are not supported by the bit-packed path")
+                extra_h2d += mh
+            Y = Pd
     if isinstance(Y, BitMatrix):
         P = Y
         M = mask
         if M is not None and not isinstance(M, BitMatrix):
             M = BitMatrix.from_dense(_as_bool_mask(M, P.shape))
-        h2d = 0
+        h2d = extra_h2d
         if not P.is_device:
             h2d += P.words.nbytes if isinstance(P.words, np.ndarray) else P.words.numel() * 4
             P = P.to_device(dev)

@@ -1,0 +1,93 @@
+"""Callers and data formats either side of the hot path: CSR ingestion without a dense
+M x N copy, inverse_transform on the device, and held-out evaluation of the fitted factors.  Bit planes are
+compared bit for bit; floating-point results in fp64 parity mode against plain NumPy formulas."""
+import numpy as np
+import pytest
+
+from nbmf_mm_b200 import NBMF, BitMatrix
+from nbmf_mm_b200.device import pack_csr_device
+
+pytestmark = pytest.mark.gpu
+sp = pytest.importorskip("scipy.sparse")
+
+
+def _xy(m, n, seed, density=0.15):
+    rng = np.random.default_rng(seed)
+    X = (rng.random((m, n)) < density).astype(np.float64)
+    mask = (rng.random((m, n)) < 0.8).astype(np.float64)
+    return X, mask
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (37, 1025), (300, 70), (64, 4096)])
+def test_csr_packing_is_bit_exact(m, n):
+    X, _ = _xy(m, n, seed=m + n)
+    A = sp.csr_matrix(X)
+    A.data[::7] = 0.0                                           # explicit zeros must stay zero bits
+    want = BitMatrix.from_dense(A.toarray())
+    got, flags, h2d = pack_csr_device(A, None)
+    assert flags == 0 and (h2d < X.nbytes or m * n < 64)
+    assert np.array_equal(got.words.cpu().numpy().view(np.uint32), want.words)
+    empty, flags, _ = pack_csr_device(sp.csr_matrix((m, n)), None)
+    assert flags == 0 and not empty.words.cpu().numpy().any()
+
+
+def test_csr_value_checks_match_the_reference_errors():
+    X, mask = _xy(40, 50, seed=1)
+    bad = sp.csr_matrix(X * 2.0)
+    with pytest.raises(ValueError, match="X must be binary"):
+        NBMF(n_components=3, max_iter=2).fit(bad)
+    weighted = sp.csr_matrix(mask * 0.5)
+    with pytest.raises(ValueError, match="mask must be binary"):
+        NBMF(n_components=3, max_iter=2).fit(sp.csr_matrix(X), mask=weighted)
+
+
+@pytest.mark.parametrize("orientation", ["beta-dir", "dir-beta"])
+def test_sparse_fit_equals_dense_fit(orientation):
+    X, mask = _xy(90, 140, seed=3)
+    kw = dict(n_components=5, max_iter=30, tol=0.0, random_state=0, orientation=orientation)
+    dense = NBMF(**kw).fit(X, mask=mask)
+    sparse = NBMF(**kw).fit(sp.csr_matrix(X), mask=sp.csr_matrix(mask))
+    assert np.array_equal(dense.W_, sparse.W_) and np.array_equal(dense.components_, sparse.components_)
+    assert np.array_equal(dense.loss_curve_, sparse.loss_curve_)
+    assert sparse.transfer_stats_["h2d_bytes"] < dense.transfer_stats_["h2d_bytes"] + 8 * (X.size + mask.size)
+    mixed = NBMF(**kw).fit(sp.csr_matrix(X), mask=mask)          # sparse X, dense mask
+    assert np.array_equal(dense.W_, mixed.W_)
+    # probabilistic sparse X (values strictly inside (0,1)) takes the dense layout, like dense input does
+    Xp = X * 0.7
+    a = NBMF(**kw).fit(Xp)
+    b = NBMF(**kw).fit(sp.csr_matrix(Xp))
+    assert np.array_equal(a.W_, b.W_) and np.array_equal(a.loss_curve_, b.loss_curve_)
+
+
+def test_inverse_transform_on_device():
+    X, _ = _xy(130, 257, seed=4)
+    est = NBMF(n_components=7, max_iter=20, tol=0.0, random_state=1).fit(X)
+    rng = np.random.default_rng(0)
+    W = rng.uniform(0, 0.4, (33, 7))
+    want = np.clip(W @ est.components_, 0.0, 1.0)               # _base.py:208
+    got = est.inverse_transform(W)
+    assert got.shape == want.shape and np.max(np.abs(got - want)) < 1e-14
+    assert np.max(np.abs(est.inverse_transform(est.W_) - np.clip(est.W_ @ est.components_, 0, 1))) < 1e-14
+    with pytest.raises(ValueError):
+        est.inverse_transform(W[:, :5])
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-6)])
+def test_held_out_evaluation_matches_the_experiment_driver_formula(dtype, tol):
+    X, train = _xy(120, 200, seed=5)
+    rng = np.random.default_rng(9)
+    val = ((1 - train) * (rng.random(X.shape) < 0.5)).astype(np.float64)
+    est = NBMF(n_components=6, max_iter=60, tol=0.0, random_state=2, dtype=dtype).fit(X, mask=train)
+    Yhat = est.W_ @ est.components_
+
+    def perplexity(mask):                                       # examples/reproduce_magron2022.py:40-47
+        ll = X * np.log(Yhat + 1e-8) + (1 - X) * np.log(1 - Yhat + 1e-8)
+        return np.exp(-np.sum(mask * ll) / np.count_nonzero(mask))
+
+    for mk in (val, train, None):
+        out = est.evaluate(X, mask=mk)
+        want = perplexity(np.ones_like(X) if mk is None else mk)
+        assert abs(out["perplexity"] - want) < tol * want
+        assert out["n_entries"] == (X.size if mk is None else np.count_nonzero(mk))
+    out = est.evaluate(sp.csr_matrix(X), mask=sp.csr_matrix(val))   # sparse in, same number
+    assert abs(out["perplexity"] - perplexity(val)) < tol * perplexity(val)
