@@ -3,10 +3,13 @@
 // Factors: every streamed factor block is split into tf32 hi + lo parts and written in the K-major,
 // 128-byte-swizzled layout the tcgen05 shared-memory descriptors expect, all operand forms of one
 // block contiguous, so a pipeline stage of the hot kernels is ONE 1-D bulk copy.
-//   Wf [mpad/32][4][32 x 32]   per 32-row block of W:   rows i x k  hi | lo  (B of the H pass MMA1)
-//                                                       rows k x i  hi | lo  (B of the H pass MMA2)
-//   Hf [ldh/64][4][2048]       per 64-column block of H: rows j x k hi | lo  (B of the W pass MMA1)
-//                                                       2 K-blocks of rows k x 32 j, hi | lo (B of MMA2)
+//   Wf [mpad/32][4][4 KB]   per 32-row block of W:   rows i x k  tf32 hi | bf16 correction  (B of the H pass MMA1)
+//                                                    rows k x i  tf32 hi | tf32 lo          (B of the H pass MMA2)
+//   Hf [ldh/64][4][8 KB]    per 64-column block of H: rows j x k tf32 hi | bf16 correction  (B of the W pass MMA1)
+//                                                    2 K-blocks of rows k x 32 j, tf32 hi | lo (B of MMA2)
+// MMA1 (Theta = factor . factor) gets its two correction terms hi.lo + lo.hi from ONE bf16 MMA chain of K = 64:
+// the A tile holds [hi | lo] as bf16, the streamed correction plane holds [lo | hi] as bf16 per row (128 bytes,
+// one swizzle row).  bf16 keeps the fp32 exponent, and 8 bits are enough for terms that are 2^-11 of the sum.
 // Bit planes: the SIMT threads of the tensor kernels own one TMEM lane each (a column j in the H pass, a
 // row i in the W pass) and walk along the other axis, so the planes are re-tiled once per fit so that a
 // warp's 32 lanes read 32 consecutive words:
@@ -30,7 +33,9 @@ __global__ void format_w_kernel(const float* __restrict__ W, int64_t m, int64_t 
   float* blk = Wf + (size_t)(i >> 5) * 4096;
   const uint32_t oa = tc::sw128_offset(r, k) / 4, ob = tc::sw128_offset(k, r) / 4;
   blk[oa] = hi;
-  blk[1024 + oa] = lo;
+  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + 1024);
+  corr[tc::sw128_offset_b16(r, k) / 2] = (unsigned short)tc::bf16_bits(lo);
+  corr[tc::sw128_offset_b16(r, 32 + k) / 2] = (unsigned short)tc::bf16_bits(hi);
   blk[2048 + ob] = hi;
   blk[3072 + ob] = lo;
 }
@@ -48,7 +53,9 @@ __global__ void format_h_kernel(const float* __restrict__ H, int64_t ldh, float*
   const uint32_t oa = tc::sw128_offset(r, k) / 4;
   const uint32_t ob = (uint32_t)(r >> 5) * 1024 + tc::sw128_offset(k, r & 31) / 4;
   blk[oa] = hi;
-  blk[2048 + oa] = lo;
+  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + 2048);
+  corr[tc::sw128_offset_b16(r, k) / 2] = (unsigned short)tc::bf16_bits(lo);
+  corr[tc::sw128_offset_b16(r, 32 + k) / 2] = (unsigned short)tc::bf16_bits(hi);
   blk[4096 + ob] = hi;
   blk[6144 + ob] = lo;
 }

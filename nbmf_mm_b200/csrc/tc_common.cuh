@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace nbmf {
 namespace tc {
@@ -29,6 +30,10 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with bf16 operands, fp32 accumulate, both operands K-major (K = 16 per instruction)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] . B[smem]^T
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -41,6 +46,13 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+// same with bf16 operands: A = 16 bf16 per lane in 8 consecutive 32-bit columns (low half = lower K index)
+__device__ __forceinline__ void mma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
       ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void commit(uint64_t* bar) {   // arrives on `bar` when all prior MMAs of this thread are done
@@ -71,6 +83,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]
                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_st4(uint32_t addr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -132,6 +148,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 }
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// bf16 (round to nearest even) of x as the low 16 bits; x is finite and non-negative here
+__host__ __device__ __forceinline__ uint32_t bf16_bits(float x) {
+#ifdef __CUDA_ARCH__
+  const uint32_t u = __float_as_uint(x);
+#else
+  uint32_t u; memcpy(&u, &x, 4);
+#endif
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+// byte offset of 16-bit element (row r, e) of a K-major SWIZZLE_128B tile with 64 elements (128 bytes) per row
+__host__ __device__ __forceinline__ uint32_t sw128_offset_b16(int r, int e) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((e >> 3) ^ (r & 7)) & 7) << 4) + (e & 7) * 2);
+}
 
 }  // namespace tc
 }  // namespace nbmf

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const uint32_t tA = tb, tTheta = tb + 64, tR = tb + 128, tAcc = tb + 384;
-  constexpr uint32_t id = idesc_tf32(128, 32);
+  constexpr uint32_t id = idesc_tf32(128, 32), idb = idesc_bf16(128, 32);
 
   double ll_total = 0.0;
   if (warp == TC_TMA_WARP) {
@@ -196,13 +196,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       TC_EV(0, b, 0);
       if (leader) {
         const uint32_t st = smem_u32(smem + s * HTC_STAGE_BYTES);
-        const uint64_t dWh = desc_kmajor_sw128(st), dWl = desc_kmajor_sw128(st + 4096);
+        const uint64_t dWh = desc_kmajor_sw128(st), dWc = desc_kmajor_sw128(st + 4096);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dWh + 2 * ks, id, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dWh + 2 * ks, id, ks > 0);            // hi . hi, tf32
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dWl + 2 * ks, id, 1);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 32 + 8 * ks, dWh + 2 * ks, id, 1);
+        for (int ks = 0; ks < 4; ++ks) mma_ts_bf16(tT, tA + 32 + 8 * ks, dWc + 2 * ks, idb, 1);     // hi.lo + lo.hi, bf16
         commit(&bar_theta[g]);
         if (!cd) commit(&bar_empty[s]);                                // loss-only pass: MMA1 is the last reader
       }
@@ -255,17 +253,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
     const int tl = q * 32 + lane;                                      // TMEM lane == column inside the CTA tile
     const int64_t col = jb + tl;
     const float eps = a.eps;
-    {  // resident A operand: this thread's column of H, k = 8 w4 .. 8 w4 + 7, split into hi / lo
-      uint32_t hi[8], lo[8];
+    {  // resident A operand: this thread's column of H, k = 8 w4 .. 8 w4 + 7: tf32 hi plane (32 columns) and
+       // the bf16 correction plane [hi (k = 0..31) | lo (k = 0..31)], two elements per column (32 columns)
+      uint32_t hi[8], bh[4], bl[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float x = a.H[(size_t)(8 * w4 + e) * a.ldh + col];
-        const float xh = tf32_trunc(x);
-        hi[e] = __float_as_uint(xh);
-        lo[e] = __float_as_uint(x - xh);
+      for (int e = 0; e < 8; e += 2) {
+        const float x0 = a.H[(size_t)(8 * w4 + e) * a.ldh + col], x1 = a.H[(size_t)(8 * w4 + e + 1) * a.ldh + col];
+        const float h0 = tf32_trunc(x0), h1 = tf32_trunc(x1);
+        hi[e] = __float_as_uint(h0);
+        hi[e + 1] = __float_as_uint(h1);
+        bh[e >> 1] = bf16_bits(h0) | (bf16_bits(h1) << 16);
+        bl[e >> 1] = bf16_bits(x0 - h0) | (bf16_bits(x1 - h1) << 16);
       }
       tmem_st8(tA + lane_off + 8 * w4, hi);
-      tmem_st8(tA + 32 + lane_off + 8 * w4, lo);
+      tmem_st4(tA + 32 + lane_off + 4 * w4, bh);
+      tmem_st4(tA + 48 + lane_off + 4 * w4, bl);
       wait_st();
       fence_before_sync();
       __syncwarp();
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const uint32_t tA = tb, tTheta = tb + 64, tS = tb + 192, tG = tb + 448;
-  constexpr uint32_t id1 = idesc_tf32(128, 64), id2 = idesc_tf32(128, 32);
+  constexpr uint32_t id1 = idesc_tf32(128, 64), id1b = idesc_bf16(128, 64), id2 = idesc_tf32(128, 32);
 
   if (warp == TC_TMA_WARP) {
     // ------------------------------------------------------------- producer: one 32 KB bulk copy per block
@@ -461,13 +463,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
       fence_after_sync();
       if (leader) {
         const uint32_t st = smem_u32(smem + s * WTC_STAGE_BYTES);
-        const uint64_t dHh = desc_kmajor_sw128(st), dHl = desc_kmajor_sw128(st + 8192);
+        const uint64_t dHh = desc_kmajor_sw128(st), dHc = desc_kmajor_sw128(st + 8192);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dHh + 2 * ks, id1, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dHh + 2 * ks, id1, ks > 0);           // hi . hi, tf32
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dHl + 2 * ks, id1, 1);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 32 + 8 * ks, dHh + 2 * ks, id1, 1);
+        for (int ks = 0; ks < 4; ++ks) mma_ts_bf16(tT, tA + 32 + 8 * ks, dHc + 2 * ks, id1b, 1);    // hi.lo + lo.hi, bf16
         commit(&bar_theta[g]);
       }
       __syncwarp();
@@ -521,15 +521,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = 0.f;
       }
-      uint32_t hi[8], lo[8];
+      uint32_t hi[8], bh[4], bl[4];                                   // see the H pass: tf32 hi plane + bf16 [hi | lo]
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xh = tf32_trunc(x[e]);
-        hi[e] = __float_as_uint(xh);
-        lo[e] = __float_as_uint(x[e] - xh);
+      for (int e = 0; e < 8; e += 2) {
+        const float h0 = tf32_trunc(x[e]), h1 = tf32_trunc(x[e + 1]);
+        hi[e] = __float_as_uint(h0);
+        hi[e + 1] = __float_as_uint(h1);
+        bh[e >> 1] = bf16_bits(h0) | (bf16_bits(h1) << 16);
+        bl[e >> 1] = bf16_bits(x[e] - h0) | (bf16_bits(x[e + 1] - h1) << 16);
       }
       tmem_st8(tA + lane_off + 8 * w4, hi);
-      tmem_st8(tA + 32 + lane_off + 8 * w4, lo);
+      tmem_st4(tA + 32 + lane_off + 4 * w4, bh);
+      tmem_st4(tA + 48 + lane_off + 4 * w4, bl);
       wait_st();
       fence_before_sync();
       __syncwarp();

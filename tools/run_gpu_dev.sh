@@ -1,1 +1,8 @@
-timeout 1500 python -m pytest tests/test_gpu_ingest_eval.py tests/test_gpu_estimator.py tests/test_gpu_transform_score.py -q > gpurun_out/pytest_new.log 2>&1; echo "pytest rc=$?"; tail -30 gpurun_out/pytest_new.log
+timeout 1500 python -m pytest tests/test_gpu_tensor_engine.py -x -q > gpurun_out/pytest_tc.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_tc.log
+timeout 900 python tools/compare_engines.py 200000 20000 32 6 > gpurun_out/compare_engines.log 2>&1; echo "compare rc=$?"; head -3 gpurun_out/compare_engines.log
+timeout 1500 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_full_tc5.log 2> gpurun_out/bench_full_tc5.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_full_tc5.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_full_tc5.log').read().strip().splitlines()[-1]); r=d['roofline']
+print('h_ms=%.2f w_ms=%.2f step=%.2f ms value=%.3e frac=%.3f frac_exec=%.3f loss=%s clocks=%s'%(r['avg_launch_ms'], r['w_pass']['avg_launch_ms'], d['ms_per_step'], d['value'], r['frac'], r.get('frac_executed',0), d['config']['loss_first_last'], d['clocks']))
+PY
