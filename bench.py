@@ -28,10 +28,10 @@ for p in (ROOT, ROOT / "oracle"):
         sys.path.insert(0, str(p))
 
 METRIC = "observed-entry MM updates/s (M*N*iters/s)"
-# tensor-pipe occupancy of the tensor engine relative to the algorithmic flop, in TF32-rate units per 32-row block of
-# 128 columns (one unit = one M=128, N=32 MMA instruction = 16 clk): H pass 8 (MMA1: 4 tf32 + 4 bf16) + 24 (MMA2) = 32
-# for 12 algorithmic units; W pass 16 + 24 = 40 for 16 (per 64-column block of 128 rows).
-H_EXEC, W_EXEC = 32.0 / 12.0, 40.0 / 16.0
+# tensor-pipe occupancy of the tensor engine relative to the algorithmic flop, in TF32-rate units (one unit = one M=128,
+# N=32 MMA instruction = 16 clk; a bf16 MMA covers twice the K extent in the same time): every product chain is one TF32
+# chain (hi.hi) plus one bf16 chain (hi.lo + lo.hi), i.e. 2 units per algorithmic unit in both passes.
+H_EXEC, W_EXEC = 2.0, 2.0
 UNIT = "updates/s"
 SEED = 4
 
@@ -290,8 +290,8 @@ def run_ours(a):
             "executed_tensor_tflops": H_EXEC * h_ach if h_ach else None,
             "frac_executed": (H_EXEC * h_ach / tpeak) if h_ach else None,
             "note": "achieved = algorithmic flop (6K per entry) / launch time; the split-precision scheme occupies the tensor "
-                    "pipe for 8/3 (H pass) and 5/2 (W pass) of that in TF32-rate units: hi.hi in TF32 plus one bf16 MMA chain "
-                    "for the two MMA1 correction terms, three TF32 terms for MMA2 (frac_executed)",
+                    "pipe for 2x that in TF32-rate units: hi.hi as a TF32 MMA chain plus one bf16 MMA chain for the "
+                    "two correction terms hi.lo + lo.hi (frac_executed), so frac cannot exceed 1/2",
             "w_pass": {"kernel": "w_pass_tc_kernel", "achieved": w_ach, "frac": (w_ach / tpeak) if w_ach else None,
                        "frac_executed": (W_EXEC * w_ach / tpeak) if w_ach else None, "avg_launch_ms": w_avg_ms,
                        "share_of_step": w_ms / ms_total if ms_total else None},

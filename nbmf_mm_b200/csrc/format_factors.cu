@@ -4,12 +4,14 @@
 // 128-byte-swizzled layout the tcgen05 shared-memory descriptors expect, all operand forms of one
 // block contiguous, so a pipeline stage of the hot kernels is ONE 1-D bulk copy.
 //   Wf [mpad/32][4][4 KB]   per 32-row block of W:   rows i x k  tf32 hi | bf16 correction  (B of the H pass MMA1)
-//                                                    rows k x i  tf32 hi | tf32 lo          (B of the H pass MMA2)
+//                                                    rows k x i  tf32 hi | bf16 correction  (B of the H pass MMA2)
 //   Hf [ldh/64][4][8 KB]    per 64-column block of H: rows j x k tf32 hi | bf16 correction  (B of the W pass MMA1)
-//                                                    2 K-blocks of rows k x 32 j, tf32 hi | lo (B of MMA2)
-// MMA1 (Theta = factor . factor) gets its two correction terms hi.lo + lo.hi from ONE bf16 MMA chain of K = 64:
-// the A tile holds [hi | lo] as bf16, the streamed correction plane holds [lo | hi] as bf16 per row (128 bytes,
-// one swizzle row).  bf16 keeps the fp32 exponent, and 8 bits are enough for terms that are 2^-11 of the sum.
+//                                                    2 K-blocks of rows k x 32 j, tf32 hi | bf16 correction (MMA2)
+// Every product a.b = hi.hi + (hi.lo + lo.hi): the first term is a TF32 MMA chain, the two correction terms come
+// from ONE bf16 MMA chain with twice the K extent.  MMA1: the A tile holds [hi | lo] as bf16, the streamed
+// correction plane [lo | hi] per row.  MMA2: the SIMT stage packs (hi, lo) of a ratio into one 32-bit column
+// (cvt.rn.bf16x2), the streamed plane holds the matching (lo, hi) pairs.  bf16 keeps the fp32 exponent, and 8
+// bits are enough for terms that are 2^-11 of the sum.
 // Bit planes: the SIMT threads of the tensor kernels own one TMEM lane each (a column j in the H pass, a
 // row i in the W pass) and walk along the other axis, so the planes are re-tiled once per fit so that a
 // warp's 32 lanes read 32 consecutive words:
@@ -37,7 +39,9 @@ __global__ void format_w_kernel(const float* __restrict__ W, int64_t m, int64_t 
   corr[tc::sw128_offset_b16(r, k) / 2] = (unsigned short)tc::bf16_bits(lo);
   corr[tc::sw128_offset_b16(r, 32 + k) / 2] = (unsigned short)tc::bf16_bits(hi);
   blk[2048 + ob] = hi;
-  blk[3072 + ob] = lo;
+  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 3072);     // row k: (lo, hi) pairs per i
+  corr2[tc::sw128_offset_b16(k, 2 * r) / 2] = (unsigned short)tc::bf16_bits(lo);
+  corr2[tc::sw128_offset_b16(k, 2 * r + 1) / 2] = (unsigned short)tc::bf16_bits(hi);
 }
 
 __global__ void format_h_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Hf,
@@ -57,7 +61,10 @@ __global__ void format_h_kernel(const float* __restrict__ H, int64_t ldh, float*
   corr[tc::sw128_offset_b16(r, k) / 2] = (unsigned short)tc::bf16_bits(lo);
   corr[tc::sw128_offset_b16(r, 32 + k) / 2] = (unsigned short)tc::bf16_bits(hi);
   blk[4096 + ob] = hi;
-  blk[6144 + ob] = lo;
+  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 6144);     // 2 K-blocks; row k: (lo, hi) pairs per j
+  const int rr = r & 31;
+  corr2[((r >> 5) * 4096 + tc::sw128_offset_b16(k, 2 * rr)) / 2] = (unsigned short)tc::bf16_bits(lo);
+  corr2[((r >> 5) * 4096 + tc::sw128_offset_b16(k, 2 * rr + 1)) / 2] = (unsigned short)tc::bf16_bits(hi);
 }
 
 void launch_format_w(const void* W, int64_t m, int64_t mpad, void* Wf, const FitState* state, cudaStream_t st) {

@@ -157,6 +157,12 @@ __host__ __device__ __forceinline__ uint32_t bf16_bits(float x) {
 #endif
   return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
 }
+// {low half: bf16(lo_elem), high half: bf16(hi_elem)}, round to nearest
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
 // byte offset of 16-bit element (row r, e) of a K-major SWIZZLE_128B tile with 64 elements (128 bytes) per row
 __host__ __device__ __forceinline__ uint32_t sw128_offset_b16(int r, int e) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((e >> 3) ^ (r & 7)) & 7) << 4) + (e & 7) * 2);

@@ -51,20 +51,23 @@ __device__ long long* g_tc_trace = nullptr;       // [4 warp slots][TC_TRACE_BLO
 // Per-entry ratio arithmetic of the tensor kernels, written as PTX so that ONE predicate per entry (the data
 // bit) drives both the choice of x and the masking of the outputs: ptxas otherwise rebuilds a 32-bit mask
 // per entry with two shifts, and the ALU pipe (shifts, logic, selects) is the busiest SIMT pipe here.
-//   H pass: x = (p ? theta : 1 - theta) + eps, r = 1/x, tf32 hi / lo of r, and their copies masked by p.
-__device__ __forceinline__ void h_entry(float theta, uint32_t bits, uint32_t bit, float eps, float& x, float& hi,
-                                        float& lo, float& phi, float& plo) {
-  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f32 y, r;\n\t"
+//   H pass: x = (p ? theta : 1 - theta) + eps, r = 1/x, hi = tf32(r), c = bf16x2(hi, r - hi) in one 32-bit
+//   word (low half = hi: the K order of the bf16 correction MMA), and the copies of hi and c masked by p.
+__device__ __forceinline__ void h_entry(float theta, uint32_t bits, uint32_t bit, float eps, float& x, uint32_t& hi,
+                                        uint32_t& c, uint32_t& phi, uint32_t& pc) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f32 y, r, h, l;\n\t"
       "and.b32 t, %6, %7;\n\tsetp.ne.b32 p, t, 0;\n\t"
       "mov.f32 y, %5;\n\t@!p sub.f32 y, 0f3F800000, y;\n\t"
       "add.f32 y, y, %8;\n\t"
       "rcp.approx.ftz.f32 r, y;\n\t"
-      "and.b32 %1, r, 0xffffe000;\n\t"
-      "sub.f32 %2, r, %1;\n\t"
-      "selp.f32 %3, %1, 0f00000000, p;\n\t"
-      "selp.f32 %4, %2, 0f00000000, p;\n\t"
+      "and.b32 h, r, 0xffffe000;\n\t"
+      "sub.f32 l, r, h;\n\t"
+      "cvt.rn.bf16x2.f32 %2, l, h;\n\t"
+      "mov.b32 %1, h;\n\t"
+      "selp.b32 %3, %1, 0, p;\n\t"
+      "selp.b32 %4, %2, 0, p;\n\t"
       "mov.f32 %0, y;\n\t}\n"
-      : "=f"(x), "=f"(hi), "=f"(lo), "=f"(phi), "=f"(plo)
+      : "=f"(x), "=r"(hi), "=r"(c), "=r"(phi), "=r"(pc)
       : "f"(theta), "r"(bits), "r"(bit), "f"(eps));
 }
 //   W pass: signed ratio s = 1/(theta + eps) on ones, -1/((1 - theta) + eps) on observed zeros, 0 on unobserved
@@ -122,7 +125,7 @@ constexpr int kFlush = 8;                                // own blocks per TMEM 
 //   SIMT: bit i of the column-tiled plane Pc; r = 1/x; planes Rp = [p] r and R = r (hi, lo each);
 //         fused NLL: one MUFU.LG2 per product of four x
 //   MMA2: C^T[128 j x 32 k] += Rp[128 x 32 i] . W^T[32 k x 32 i]^T,  S^T += R . W^T;  D = S - C at the end
-// TMEM: A hi 0..31, lo 32..63 | Theta[g] 64..127 | R[g] 128..383 (per 8 rows: Rp_hi Rp_lo R_hi R_lo)
+// TMEM: A hi 0..31, bf16 [hi|lo] 32..63 | Theta[g] 64..127 | R[g] 128..383 (per 8 rows: Rp_hi R_hi Rp_c R_c)
 //       | {C, S}[g] 384..511
 // =====================================================================================
 constexpr int HTC_STAGES = 6;
@@ -222,20 +225,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
         if (leader) {
           const int s = b % HTC_STAGES;
           const uint32_t st = smem_u32(smem + s * HTC_STAGE_BYTES);
-          const uint64_t dTh = desc_kmajor_sw128(st + 8192), dTl = desc_kmajor_sw128(st + 12288);
+          const uint64_t dTh = desc_kmajor_sw128(st + 8192), dTc = desc_kmajor_sw128(st + 12288);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t acc = (ks > 0 || !chain_start) ? 1u : 0u;
-            const uint32_t tr = tRb + 32 * ks;                         // Rp_hi +0, Rp_lo +8, R_hi +16, R_lo +24
-            mma_ts(tC, tr, dTh + 2 * ks, id, acc);
-            mma_ts(tS, tr + 16, dTh + 2 * ks, id, acc);
-#if !defined(TC_EXP) || TC_EXP < 2     // TC_EXP: timing experiments only (results are wrong)
-            mma_ts(tC, tr, dTl + 2 * ks, id, 1);
-            mma_ts(tS, tr + 16, dTl + 2 * ks, id, 1);
-#endif
-#if !defined(TC_EXP) || TC_EXP < 1
-            mma_ts(tC, tr + 8, dTh + 2 * ks, id, 1);
-            mma_ts(tS, tr + 24, dTh + 2 * ks, id, 1);
+            const uint32_t tr = tRb + 32 * ks;                         // Rp_hi +0, R_hi +8, Rp_c +16, R_c +24
+            mma_ts(tC, tr, dTh + 2 * ks, id, acc);                     // hi . hi, tf32
+            mma_ts(tS, tr + 8, dTh + 2 * ks, id, acc);
+#if !defined(TC_EXP) || TC_EXP < 1     // TC_EXP: timing experiments only (results are wrong)
+            mma_ts_bf16(tC, tr + 16, dTc + 2 * ks, idb, 1);            // hi.lo + lo.hi, bf16, K = 16 = 8 rows x (hi, lo)
+            mma_ts_bf16(tS, tr + 24, dTc + 2 * ks, idb, 1);
 #endif
           }
           commit(&bar_rfree[g]);
@@ -326,15 +325,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
         uint32_t out[32];
         float prod = 1.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float x, hi, lo, phi, plo;
-          h_entry(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps, x, hi, lo, phi, plo);
+        for (int e = 0; e < 8; ++e) {                                  // out: Rp_hi | R_hi | Rp_c | R_c, 8 columns each
+          float x;
+          h_entry(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
           prod = (e & 3) ? prod * x : x;
           if ((e & 3) == 3) llb += logu_(prod);                        // eps >= 1e-9: four factors cannot underflow
-          out[e] = __float_as_uint(phi);
-          out[8 + e] = __float_as_uint(plo);
-          out[16 + e] = __float_as_uint(hi);
-          out[24 + e] = __float_as_uint(lo);
         }
         if (cd) {
           if (u == 0) {                                                // MMA2(b-2) must be done reading R[g]
@@ -393,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
 //   MMA1: Theta'[128 i x 64 j] = W[128 x 32 k] . Ht[64 j x 32 k]^T
 //   SIMT: signed ratio s = 1/(+-x) on observed entries (= p - q), q-sum of the zeros' 1/x, s -> TMEM (hi, lo)
 //   MMA2: G[128 i x 32 k] += S[128 x 64 j] . H[32 k x 64 j]^T
-// TMEM: A hi 0..31, lo 32..63 | Theta[g] 64..191 | S[g] 192..447 (per 8 columns: S_hi S_lo) | G[g] 448..511
+// TMEM: A hi 0..31, bf16 [hi|lo] 32..63 | Theta[g] 64..191 | S[g] 192..447 (per 8 columns: S_hi S_c) | G[g] 448..511
 // =====================================================================================
 constexpr int WTC_STAGES = 5;
 constexpr int WTC_STAGE_BYTES = 32768;
@@ -434,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const uint32_t tA = tb, tTheta = tb + 64, tS = tb + 192, tG = tb + 448;
-  constexpr uint32_t id1 = idesc_tf32(128, 64), id1b = idesc_bf16(128, 64), id2 = idesc_tf32(128, 32);
+  constexpr uint32_t id1 = idesc_tf32(128, 64), id1b = idesc_bf16(128, 64), id2 = idesc_tf32(128, 32), id2b = idesc_bf16(128, 32);
 
   if (warp == TC_TMA_WARP) {
     // ------------------------------------------------------------- producer: one 32 KB bulk copy per block
@@ -488,14 +483,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t dBh = desc_kmajor_sw128(st + 16384 + (ks >> 2) * 4096) + 2 * (ks & 3);
-          const uint64_t dBl = desc_kmajor_sw128(st + 24576 + (ks >> 2) * 4096) + 2 * (ks & 3);
-          const uint32_t ts = tSb + 16 * ks;                             // S_hi +0, S_lo +8
-          mma_ts(tGa, ts, dBh, id2, (ks > 0 || !chain_start) ? 1u : 0u);
-#if !defined(TC_EXP) || TC_EXP < 2
-          mma_ts(tGa, ts, dBl, id2, 1);
-#endif
+          const uint64_t dBc = desc_kmajor_sw128(st + 24576 + (ks >> 2) * 4096) + 2 * (ks & 3);
+          const uint32_t ts = tSb + 16 * ks;                             // S_hi +0, S_c +8
+          mma_ts(tGa, ts, dBh, id2, (ks > 0 || !chain_start) ? 1u : 0u); // hi . hi, tf32
 #if !defined(TC_EXP) || TC_EXP < 1
-          mma_ts(tGa, ts + 8, dBh, id2, 1);
+          mma_ts_bf16(tGa, ts + 8, dBc, id2b, 1);                        // hi.lo + lo.hi, bf16
 #endif
         }
         commit(&bar_sfree[g]);
@@ -584,7 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
             w_entry(__uint_as_float(v[8 * w + e]), bits.x, bits.y, 1u << (16 * u + 8 * w + e), eps, sv, qb);
             const float hi = tf32_trunc(sv);
             out[e] = __float_as_uint(hi);
-            out[8 + e] = __float_as_uint(sv - hi);
+            out[8 + e] = pack_bf16x2(hi, sv - hi);                       // (hi, lo) of s in one column
           }
           if (u == 0 && w == 0) {                                      // MMA2(b-2) must be done reading S[g]
             if (!ok_sfree) mbar_wait(&bar_sfree[g], (ob - 1) & 1);

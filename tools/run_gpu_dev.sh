@@ -1,5 +1,5 @@
+tools/bin/tc_trace 512 > gpurun_out/tc_trace.log 2>&1; echo rc=$?; head -8 gpurun_out/tc_trace.log
 timeout 1500 python -m pytest tests/test_gpu_tensor_engine.py -x -q > gpurun_out/pytest_tc.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_tc.log
-timeout 900 python tools/compare_engines.py 200000 20000 32 6 > gpurun_out/compare_engines.log 2>&1; echo "compare rc=$?"; head -3 gpurun_out/compare_engines.log
 timeout 1500 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_full_tc5.log 2> gpurun_out/bench_full_tc5.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_full_tc5.err
 python - <<'PY'
 import json
