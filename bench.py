@@ -278,6 +278,13 @@ def run_ours(a):
         "hbm_context": {"algorithmic_bytes_per_entry_iteration": 0.375, "hbm_gbs_used": 0.375 * value / world * 1e-9,
                         "hbm_peak_gbs": mp.get("hbm_gbs")},
     }
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact shape
+        tr = json.loads((ROOT / "profiles" / "dram_traffic.json").read_text()).get(f"{m_local}x{N}x{K}:{engine}")
+    except Exception:
+        tr = None
+    if tr:
+        common["traffic"] = tr["h_pass"]
+        common["traffic_detail"] = dict(tr, unit="bytes per launch", source="profiles/r01_ncu_dram_traffic_full_size.csv")
     if engine == "tensor":
         # kind::tf32 runs at half the bf16 rate; the kernels are timed inside a long step -> sustained figure
         bf16 = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")

@@ -127,19 +127,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a lost arrival traps (CUDA error) instead of hanging the GPU.  try_wait suspends the thread in
-// hardware for a while before it reports failure, so 2^24 failed probes are far beyond any legitimate wait.
+// Non-blocking probe of a phase (used where the result is only needed later).
 __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   return ok != 0;
 }
+// Bounded wait: a lost arrival traps (CUDA error) instead of hanging the GPU.  try_wait suspends the warp in
+// hardware until the phase completes or the time hint (ns) expires, so a waiting warp leaves the issue slots
+// to the warps that have work; 2^22 expired hints are far beyond any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  if (mbar_try(addr, parity)) return;
-  for (uint32_t spin = 0; !mbar_try(addr, parity); ++spin)
-    if (spin > (1u << 24)) __trap();
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"(4000u) : "memory");
+    if (ok) return;
+    if (spin > (1u << 22)) __trap();
+  }
 }
 // 1-D bulk copy global -> shared (TMA engine, no tensor map), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -1,8 +1,2 @@
-tools/bin/tc_trace 512 > gpurun_out/tc_trace.log 2>&1; echo rc=$?; head -8 gpurun_out/tc_trace.log
-timeout 1500 python -m pytest tests/test_gpu_tensor_engine.py -x -q > gpurun_out/pytest_tc.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_tc.log
-timeout 1500 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_full_tc5.log 2> gpurun_out/bench_full_tc5.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_full_tc5.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_full_tc5.log').read().strip().splitlines()[-1]); r=d['roofline']
-print('h_ms=%.2f w_ms=%.2f step=%.2f ms value=%.3e frac=%.3f frac_exec=%.3f loss=%s clocks=%s'%(r['avg_launch_ms'], r['w_pass']['avg_launch_ms'], d['ms_per_step'], d['value'], r['frac'], r.get('frac_executed',0), d['config']['loss_first_last'], d['clocks']))
-PY
+CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu"
+$CMD > gpurun_out/plain.log 2>&1 && ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:pass_tc -s 2 -c 2 --csv --log-file gpurun_out/traffic_full.csv $CMD > gpurun_out/ncu_traffic.log 2>&1; echo "ncu rc=$?"; cat gpurun_out/traffic_full.csv | tail -8
