@@ -40,9 +40,11 @@ extern "C" {
 #define NBMF_F32 0
 #define NBMF_F64 1
 #define NBMF_U8 2
+#define NBMF_F16 3      /* storage only: dense V*mask of the NBMF_V_DENSE_F16 layout */
 
 #define NBMF_V_BITS 0   /* binary V: planes P = V & mask and M = mask, 1 bit per entry each */
 #define NBMF_V_DENSE 1  /* probabilistic V in [0,1]: dense V*mask in `dtype` + mask bit plane */
+#define NBMF_V_DENSE_F16 2 /* same, V*mask stored as fp16 (half the HBM bytes; float32 arithmetic only) */
 
 #define NBMF_MASK_REFERENCE 0 /* H step / loss treat unobserved entries as observed zeros (_solver.py:43,153-154) */
 #define NBMF_MASK_STRICT 1    /* only observed entries contribute (README / paper); unpinned */
@@ -62,7 +64,7 @@ typedef struct nbmf_config {
   int64_t n;             /* columns */
   int32_t k;             /* n_components, 1..64 */
   int32_t dtype;         /* NBMF_F32 | NBMF_F64 */
-  int32_t vkind;         /* NBMF_V_BITS | NBMF_V_DENSE */
+  int32_t vkind;         /* NBMF_V_BITS | NBMF_V_DENSE | NBMF_V_DENSE_F16 */
   int32_t mask_semantics;
   int32_t projection;
   int32_t has_mask;      /* 0: everything observed (mask=None) */

@@ -13,8 +13,8 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libnbmf_b200.so"
 
-NBMF_F32, NBMF_F64, NBMF_U8 = 0, 1, 2
-NBMF_V_BITS, NBMF_V_DENSE = 0, 1
+NBMF_F32, NBMF_F64, NBMF_U8, NBMF_F16 = 0, 1, 2, 3
+NBMF_V_BITS, NBMF_V_DENSE, NBMF_V_DENSE_F16 = 0, 1, 2
 NBMF_MASK_REFERENCE, NBMF_MASK_STRICT = 0, 1
 NBMF_PROJ_NORMALIZE, NBMF_PROJ_DUCHI = 0, 1
 NBMF_ENGINE_AUTO, NBMF_ENGINE_SIMT, NBMF_ENGINE_TENSOR = 0, 1, 2

@@ -16,11 +16,13 @@
 namespace nbmf {
 bool lookup_f32_bits(int strict, int k, PassLaunch* out);
 bool lookup_f32_dense(int strict, int k, PassLaunch* out);
+bool lookup_f32_dense16(int strict, int k, PassLaunch* out);
 bool lookup_f64_bits(int strict, int k, PassLaunch* out);
 bool lookup_f64_dense(int strict, int k, PassLaunch* out);
 
 bool lookup_pass(int dtype, int dense, int strict, int k, PassLaunch* out) {
   if (k < 1) return false;
+  if (dtype == 0 && dense == 2) return lookup_f32_dense16(strict, k, out);
   if (dtype == 0) return dense ? lookup_f32_dense(strict, k, out) : lookup_f32_bits(strict, k, out);
   if (dtype == 1) return dense ? lookup_f64_dense(strict, k, out) : lookup_f64_bits(strict, k, out);
   return false;
@@ -165,10 +167,12 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   if (c.m < 1 || c.n < 1) return fail(NBMF_ERR_ARG, "m and n must be positive");
   if (c.k < 1 || c.k > 64) return fail(NBMF_ERR_UNSUPPORTED, "n_components must be in 1..64");
   if (c.dtype != NBMF_F32 && c.dtype != NBMF_F64) return fail(NBMF_ERR_ARG, "dtype must be NBMF_F32 or NBMF_F64");
-  if (c.vkind != NBMF_V_BITS && c.vkind != NBMF_V_DENSE) return fail(NBMF_ERR_ARG, "bad vkind");
+  if (c.vkind != NBMF_V_BITS && c.vkind != NBMF_V_DENSE && c.vkind != NBMF_V_DENSE_F16) return fail(NBMF_ERR_ARG, "bad vkind");
+  if (c.vkind == NBMF_V_DENSE_F16 && c.dtype != NBMF_F32)
+    return fail(NBMF_ERR_UNSUPPORTED, "the fp16 layout of probabilistic V needs float32 arithmetic");
   if (c.mask_semantics == NBMF_MASK_STRICT && !c.has_mask) { /* strict == reference when everything is observed */ }
   const int strict = (c.mask_semantics == NBMF_MASK_STRICT && c.has_mask) ? 1 : 0;
-  if (!lookup_pass(c.dtype, c.vkind == NBMF_V_DENSE, strict, c.k, &p->pl))
+  if (!lookup_pass(c.dtype, c.vkind == NBMF_V_DENSE_F16 ? 2 : (c.vkind == NBMF_V_DENSE ? 1 : 0), strict, c.k, &p->pl))
     return fail(NBMF_ERR_UNSUPPORTED, "no kernel variant for this (dtype, vkind, k)");
   // engine: 0 = auto, 1 = SIMT (packed FFMA2), 2 = tensor (tcgen05, 3xTF32); NBMF_ENGINE overrides
   int engine = c.engine;
@@ -244,7 +248,7 @@ extern "C" int64_t nbmf_launch_count(int reset) {
 }
 extern "C" int nbmf_variant_info(int dtype, int vkind, int k, int32_t* h_cols, int32_t* w_rows, int32_t* kp) {
   PassLaunch pl;
-  if (!lookup_pass(dtype, vkind == NBMF_V_DENSE, 0, k, &pl)) return fail(NBMF_ERR_UNSUPPORTED, "no variant");
+  if (!lookup_pass(dtype, vkind == NBMF_V_DENSE_F16 ? 2 : (vkind == NBMF_V_DENSE ? 1 : 0), 0, k, &pl)) return fail(NBMF_ERR_UNSUPPORTED, "no variant");
   if (h_cols) *h_cols = pl.h_bn;
   if (w_rows) *w_rows = pl.w_bmr;
   if (kp) *kp = pl.kp;
@@ -369,7 +373,7 @@ extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t
 }
 extern "C" int nbmf_set_data_dense(nbmf_ctx* c, const void* Vm, const uint32_t* M) {
   if (!c || !Vm) return fail(NBMF_ERR_ARG, "nbmf_set_data_dense: null argument");
-  if (c->cfg.vkind != NBMF_V_DENSE) return fail(NBMF_ERR_ARG, "context was created for bit-packed V");
+  if (c->cfg.vkind != NBMF_V_DENSE && c->cfg.vkind != NBMF_V_DENSE_F16) return fail(NBMF_ERR_ARG, "context was created for bit-packed V");
   if (c->cfg.has_mask && !M) return fail(NBMF_ERR_ARG, "has_mask is set but no mask plane given");
   c->Vm = Vm;
   c->M = c->cfg.has_mask ? M : nullptr;

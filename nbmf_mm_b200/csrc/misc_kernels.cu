@@ -1,5 +1,6 @@
 // Epilogue, reduction and data-layer kernels around the two pass kernels.
 // Reference arithmetic: src/nbmf_mm/_solver.py (line numbers cited per kernel).
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -354,7 +355,9 @@ void launch_pack_dense(int in_dtype, const void* X, int64_t ldx, const void* mas
   int64_t nb = (m * ldv + 255) / 256;
   if (nb > 148 * 32) nb = 148 * 32;
   if (nb < 1) nb = 1;
-  if (out_dtype == 0)
+  if (out_dtype == 3)        // NBMF_F16: fp16 storage layout
+    pack_dense_kernel<__half><<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, ldv, (__half*)Vm);
+  else if (out_dtype == 0)
     pack_dense_kernel<float><<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, ldv, (float*)Vm);
   else
     pack_dense_kernel<double><<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, ldv, (double*)Vm);

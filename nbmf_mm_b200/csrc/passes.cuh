@@ -12,6 +12,7 @@
 // dot products are combined with log2(S) xor-shuffles.  Accumulators are (k, k+1) pairs so
 // that fp32 issues packed FFMA2 (one issue slot per two FMAs).
 #pragma once
+#include <cuda_fp16.h>
 #include "args.h"
 #include "common.cuh"
 
@@ -40,9 +41,10 @@ __device__ __forceinline__ void load_pairs(const Real* __restrict__ src, typenam
 // pos = V&mask; neg = 1 - pos (reference quirk) or mask - pos (STRICT).
 // A thread owns C contiguous columns x KH values of k; rows stream through shared memory.
 // =====================================================================================
-template <typename Real_, int KP_, int S_, int C_, int NW_, int MINB_, bool DENSE_, bool STRICT_>
+template <typename Real_, int KP_, int S_, int C_, int NW_, int MINB_, bool DENSE_, bool STRICT_, typename VT_ = Real_>
 struct HCfg {
   using Real = Real_;
+  using VT = VT_;                            // storage type of dense V*mask: Real, or __half (fp16 layout)
   static constexpr int KP = KP_, S = S_, C = C_, NW = NW_, MINB = MINB_;
   static constexpr bool DENSE = DENSE_, STRICT = STRICT_;
   static constexpr int KH = KP / S;
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
   for (int cc = 0; cc < C; ++cc) lld[cc] = 0.0;
 
   const unsigned char* __restrict__ Wg = reinterpret_cast<const unsigned char*>(a.W);
-  const Real* __restrict__ Vg = reinterpret_cast<const Real*>(a.Vm);
+  using VT = typename Cfg::VT;
+  const VT* __restrict__ Vg = reinterpret_cast<const VT*>(a.Vm);
   const int64_t ntiles = (r1 > r0) ? (r1 - r0 + BM - 1) / BM : 0;
 
   auto issue_tile = [&](int64_t t) {
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     Real vnext[C];
     if constexpr (DENSE) {
 #pragma unroll
-      for (int cc = 0; cc < C; ++cc) vnext[cc] = Vg[(size_t)rb * a.ldv + j0 + cc];
+      for (int cc = 0; cc < C; ++cc) vnext[cc] = (Real)Vg[(size_t)rb * a.ldv + j0 + cc];
     }
 
 #pragma unroll 2
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
         for (int cc = 0; cc < C; ++cc) vcur[cc] = vnext[cc];
         const int64_t rn = min(rb + r + 1, a.m - 1);
 #pragma unroll
-        for (int cc = 0; cc < C; ++cc) vnext[cc] = Vg[(size_t)rn * a.ldv + j0 + cc];
+        for (int cc = 0; cc < C; ++cc) vnext[cc] = (Real)Vg[(size_t)rn * a.ldv + j0 + cc];
       }
 
       // ---- masked ratios in registers, loss term, second contraction
@@ -288,9 +291,10 @@ void launch_h_pass(const HPassArgs& a, int nsplit, cudaStream_t st) {
 // For binary V exactly one of p, q is non-zero, so p - q is exact.
 // A thread owns C rows x KH values of k; columns stream through shared memory (Ht tiles).
 // =====================================================================================
-template <typename Real_, int KP_, int S_, int C_, int NW_, int MINB_, bool DENSE_>
+template <typename Real_, int KP_, int S_, int C_, int NW_, int MINB_, bool DENSE_, typename VT_ = Real_>
 struct WCfg {
   using Real = Real_;
+  using VT = VT_;
   static constexpr int KP = KP_, S = S_, C = C_, NW = NW_, MINB = MINB_;
   static constexpr bool DENSE = DENSE_;
   static constexpr int KH = KP / S;
@@ -350,7 +354,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
   }
 
   const unsigned char* __restrict__ Htg = reinterpret_cast<const unsigned char*>(a.Ht);
-  const Real* __restrict__ Vg = reinterpret_cast<const Real*>(a.Vm);
+  using VT = typename Cfg::VT;
+  const VT* __restrict__ Vg = reinterpret_cast<const VT*>(a.Vm);
   const int64_t ntiles = (c1 > c0) ? (c1 - c0 + BNT - 1) / BNT : 0;
 
   auto issue_tile = [&](int64_t t) {
@@ -402,9 +407,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
 #pragma unroll
           for (int rr = 0; rr < C; ++rr) {
             const int64_t row = min(ib + il + rr, a.m - 1);
-            const Real* src = Vg + (size_t)row * a.ldv + colw + 8 * u;
+            const VT* src = Vg + (size_t)row * a.ldv + colw + 8 * u;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) vv[rr][e] = src[e];
+            for (int e = 0; e < 8; ++e) vv[rr][e] = (Real)src[e];
           }
         }
 #pragma unroll

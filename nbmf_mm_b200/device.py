@@ -89,11 +89,13 @@ def pack_dense_device(X_dev, mask_dev, dtype):
     X_dev = X_dev.contiguous()
     if mask_dev is not None:
         mask_dev = mask_dev.contiguous()
+    half = np.dtype(dtype) == np.float16                      # fp16 storage layout (NBMF_V_DENSE_F16)
     Vm = torch.empty((m, ldv), dtype=getattr(torch, np.dtype(dtype).name), device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.nbmf_pack_dense(_ptr(X_dev), _elem_code(X_dev), n, _ptr(mask_dev),
                                        _elem_code(mask_dev) if mask_dev is not None else 0, n,
-                                       m, n, dtype_code(dtype), _ptr(Vm), _stream(dev)), "nbmf_pack_dense")
+                                       m, n, _lib.NBMF_F16 if half else dtype_code(dtype), _ptr(Vm), _stream(dev)),
+                   "nbmf_pack_dense")
     return Vm
 
 
@@ -201,7 +203,9 @@ class DeviceProblem:
         cfg = _lib.NbmfConfig()
         cfg.m, cfg.n, cfg.k = self.m, self.n, self.k
         cfg.dtype = dtype_code(dtype)
-        cfg.vkind = _lib.NBMF_V_BITS if vkind == "bits" else _lib.NBMF_V_DENSE
+        if vkind not in ("bits", "dense", "dense16"):
+            raise ValueError(f"vkind must be 'bits', 'dense' or 'dense16', got {vkind!r}")
+        cfg.vkind = {"bits": _lib.NBMF_V_BITS, "dense": _lib.NBMF_V_DENSE, "dense16": _lib.NBMF_V_DENSE_F16}[vkind]
         cfg.mask_semantics = _lib.NBMF_MASK_STRICT if mask_semantics == "strict" else _lib.NBMF_MASK_REFERENCE
         cfg.projection = _lib.NBMF_PROJ_DUCHI if projection == "duchi" else _lib.NBMF_PROJ_NORMALIZE
         cfg.has_mask = 1 if has_mask else 0

@@ -79,6 +79,8 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         round-robin to the ranks (restart r on rank r % world, whole problem on that rank's GPU, no
         data-path collective); the final losses are compared across ranks and the winner's factors are
         broadcast, so every rank ends with the same fitted estimator.
+    dense_storage : {None, "float16"}: device layout of probabilistic X (values strictly inside (0,1)); None = the
+        compute dtype, "float16" halves the bytes each pass reads (float32 arithmetic only).
     engine : {"auto", "simt", "tensor"}: CUDA-core (packed FFMA2) kernels or the tcgen05/TMEM 3xTF32
         kernels (float32, binary X, K <= 32 only); "auto" picks tensor when eligible and m, n >= 512.
     """
@@ -86,7 +88,8 @@ class NBMFMM(BaseEstimator, TransformerMixin):
     def __init__(self, n_components=10, alpha=1.2, beta=1.2, max_iter=2000, tol=1e-5,
                  W_init=None, H_init=None, init=None, random_state=None, verbose=0,
                  orientation="beta-dir", projection_method="normalize", n_init=1,
-                 dtype="float64", mask_semantics="reference", device=None, distributed=False, engine="auto"):
+                 dtype="float64", mask_semantics="reference", device=None, distributed=False, engine="auto",
+                 dense_storage=None):
         self.n_components = n_components
         self.alpha = alpha
         self.beta = beta
@@ -105,6 +108,7 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         self.device = device
         self.distributed = distributed
         self.engine = engine
+        self.dense_storage = dense_storage
 
     # ------------------------------------------------------------------ helpers
     def _normalize_orientation(self, orientation):
@@ -153,7 +157,7 @@ class NBMFMM(BaseEstimator, TransformerMixin):
                 random_state=seed, verbose=self.verbose, orientation=orientation,
                 projection_method=self.projection_method, mask_semantics=self.mask_semantics,
                 dtype=self.dtype, device=self.device, distributed=row_sharded, stats=stats,
-                engine=self.engine)
+                engine=self.engine, dense_storage=self.dense_storage)
             if best is None or out[2][-1] < best[0][2][-1]:
                 best = (out, stats, r)
         if by_restart and world > 1:

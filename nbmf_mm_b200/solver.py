@@ -55,7 +55,7 @@ def _as_bool_mask(mask, shape):
     return mask
 
 
-def prepare_data(Y, mask, *, transpose, dtype, device, defer=False) -> PreparedData:
+def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storage=None) -> PreparedData:
     """Validate, orient, pack and upload V and the observation mask.
 
     Binary V goes to two 1-bit planes (packed on the host, so the H2D copy is 32-64x smaller
@@ -135,6 +135,12 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False) -> PreparedD
         md = torch.from_numpy(np.ascontiguousarray(mk).view(np.uint8)).to(dev)
         h2d += mk.nbytes
         M, _ = pack_bits_device(md, None)
+    if dense_storage not in (None, "float16", "float32", "float64"):
+        raise ValueError(f"dense_storage must be None, 'float16', 'float32' or 'float64', got {dense_storage!r}")
+    if dense_storage == "float16":                             # fp16 layout: half the HBM bytes per pass
+        if np.dtype(dtype) != np.float32:
+            raise ValueError("dense_storage='float16' needs dtype='float32'")
+        return PreparedData(m, n, "dense16", None, M, pack_dense_device(Yd, md, np.float16), n_obs, h2d)
     Vm = pack_dense_device(Yd, md, dtype)
     return PreparedData(m, n, "dense", None, M, Vm, n_obs, h2d)
 
@@ -186,7 +192,7 @@ def _row_shard(m, rank, world):
 def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2, W_init=None, H_init=None,
                    mask=None, random_state=None, verbose=0, orientation="beta-dir", eps=1e-8, *,
                    projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
-                   distributed=False, shard=None, stats=None, engine="auto"):
+                   distributed=False, shard=None, stats=None, engine="auto", dense_storage=None):
     """NBMF-MM solver, drop-in for ``nbmf_mm._solver.nbmf_mm_solver`` (``_solver.py:61-216``).
 
     Returns ``(W (m x k), H (k x n), losses, 0.0, n_iter)`` exactly as the reference does
@@ -198,7 +204,8 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     ``distributed``: ``Y``/``mask`` are already this rank's row block of an ``m_total``-row
     problem in internal orientation; the returned W is the local block, H is global),
     ``engine`` ("auto" | "simt" | "tensor": packed-FFMA2 CUDA-core kernels or the tcgen05/TMEM
-    3xTF32 kernels; the tensor engine needs float32, binary V, K <= 32).
+    split-precision kernels; the tensor engine needs float32, binary V, K <= 32), ``dense_storage`` ("float16":
+    probabilistic V is stored as fp16 on the device, float32 arithmetic; default = the compute dtype).
     """
     if orientation not in _CANON:
         raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
@@ -210,7 +217,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     transpose = orientation == "dir-beta"
     # bit-packed host inputs: the H2D copies are asynchronous (pinned memory); the inits are drawn on the
     # host while they are in flight and the device-side preparation runs afterwards (data.finish())
-    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True)
+    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage)
     m, n, k = data.m, data.n, int(n_components)
     if shard is not None:
         if transpose or not distributed:

@@ -91,3 +91,24 @@ def test_held_out_evaluation_matches_the_experiment_driver_formula(dtype, tol):
         assert out["n_entries"] == (X.size if mk is None else np.count_nonzero(mk))
     out = est.evaluate(sp.csr_matrix(X), mask=sp.csr_matrix(val))   # sparse in, same number
     assert abs(out["perplexity"] - perplexity(val)) < tol * perplexity(val)
+
+
+@pytest.mark.parametrize("orientation", ["beta-dir", "dir-beta"])
+def test_fp16_layout_of_probabilistic_v(orientation):
+    """dense_storage='float16' stores V*mask as fp16 (half the bytes per pass), arithmetic stays float32: values
+    that are exact in fp16 give bit-identical factors, arbitrary values differ by the storage rounding only."""
+    rng = np.random.default_rng(11)
+    X = rng.integers(0, 65, (150, 260)) / 64.0                  # exact in fp16
+    mask = (rng.random(X.shape) < 0.85).astype(np.float64)
+    kw = dict(n_components=9, max_iter=25, tol=0.0, random_state=4, orientation=orientation, dtype="float32")
+    a = NBMF(**kw).fit(X, mask=mask)
+    b = NBMF(dense_storage="float16", **kw).fit(X, mask=mask)
+    assert np.array_equal(a.W_, b.W_) and np.array_equal(a.components_, b.components_)
+    assert np.array_equal(a.loss_curve_, b.loss_curve_)
+    Xr = rng.random(X.shape)
+    c = NBMF(**kw).fit(Xr, mask=mask)
+    d = NBMF(dense_storage="float16", **kw).fit(Xr, mask=mask)
+    assert abs(c.loss_curve_[-1] - d.loss_curve_[-1]) < 1e-3 * abs(c.loss_curve_[-1])
+    assert np.max(np.abs(c.components_ - d.components_)) < 5e-3
+    with pytest.raises(ValueError, match="float32"):
+        NBMF(n_components=3, max_iter=2, dtype="float64", dense_storage="float16").fit(Xr)
