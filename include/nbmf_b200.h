@@ -116,6 +116,11 @@ int nbmf_set_data_dense(nbmf_ctx* ctx, const void* vm_dev, const uint32_t* m_bit
  * (_solver.py:132-136).  Either pointer may be NULL to keep the current factor.  Resets the loop state. */
 int nbmf_set_factors(nbmf_ctx* ctx, const void* w_dev, const void* h_dev, int normalize_w);
 int nbmf_get_factors(nbmf_ctx* ctx, void* w_dev, void* h_dev);
+/* tail of the reference solver on the device (_solver.py:192-213): worst |rowsum(W) - 1| in fp64 (NaN if a row sum is
+ * not finite; synchronises), and the export of W (m x k) / H (k x n) as fp64 with W's rows optionally divided by their
+ * sums (rows with sum <= 1e-12 are left alone).  The caller applies the reference's rule: normalise iff dev > 1e-9. */
+int nbmf_simplex_deviation(nbmf_ctx* ctx, double* dev_host);
+int nbmf_get_factors_f64(nbmf_ctx* ctx, double* w_dev, double* h_dev, int normalize_w);
 
 /* ---- single steps (replace nbmf_mm_update_beta_dir, _solver.py:5-59) ---- */
 int nbmf_h_half_step(nbmf_ctx* ctx);            /* H <- H' (_solver.py:39-47) */

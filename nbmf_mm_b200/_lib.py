@@ -52,6 +52,8 @@ SIGNATURES = {
     "nbmf_set_data_dense": (_INT, [_P, _P, _P]),
     "nbmf_set_factors": (_INT, [_P, _P, _P, _INT]),
     "nbmf_get_factors": (_INT, [_P, _P, _P]),
+    "nbmf_simplex_deviation": (_INT, [_P, C.POINTER(_DBL)]),
+    "nbmf_get_factors_f64": (_INT, [_P, _P, _P, _INT]),
     "nbmf_h_half_step": (_INT, [_P]),
     "nbmf_w_half_step": (_INT, [_P]),
     "nbmf_objective": (_INT, [_P, C.POINTER(_DBL)]),

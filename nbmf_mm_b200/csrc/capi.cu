@@ -407,6 +407,26 @@ extern "C" int nbmf_get_factors(nbmf_ctx* c, void* w, void* h) {
   return NBMF_OK;
 }
 
+extern "C" int nbmf_simplex_deviation(nbmf_ctx* c, double* dev_host) {
+  if (!c || !dev_host) return fail(NBMF_ERR_ARG, "nbmf_simplex_deviation: null argument");
+  unsigned long long* scratch = c->at<unsigned long long>(c->p.oLoss);     // 64 bytes of scratch
+  launch_simplex_deviation(c->cfg.dtype, c->W(), c->cfg.m, c->cfg.k, c->p.pl.kp, scratch, c->st);
+  CHECK_LAUNCH(1);
+  unsigned long long h[2];
+  CUDA_TRY(cudaMemcpyAsync(h, scratch, 16, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  double d;
+  memcpy(&d, &h[0], 8);
+  *dev_host = h[1] ? NAN : d;
+  return NBMF_OK;
+}
+extern "C" int nbmf_get_factors_f64(nbmf_ctx* c, double* w, double* h, int normalize_w) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  launch_export_f64(c->cfg.dtype, c->W(), c->H(), c->cfg.m, c->cfg.n, c->cfg.k, c->p.pl.kp, c->p.ldh, normalize_w, w, h, c->st);
+  CHECK_LAUNCH((w ? 1 : 0) + (h ? 1 : 0));
+  return NBMF_OK;
+}
+
 // ------------------------------------------------------------------------------------ steps
 static int format_w(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;

@@ -41,6 +41,9 @@ void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64
 void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nsplit, int64_t m, int64_t n,
                        int k, int kp, int projection, const void* rowcount, void* W, const FitState* state,
                        cudaStream_t st);
+void launch_simplex_deviation(int dtype, const void* W, int64_t m, int k, int kp, unsigned long long* out, cudaStream_t st);
+void launch_export_f64(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, int kp, int64_t ldh,
+                       int normalize_w, double* W_out, double* H_out, cudaStream_t st);
 void launch_clip_rows(int dtype, void* W, int64_t m, int k, int kp, double lo, double hi, cudaStream_t st);
 
 // ---- tensor-core engine (K <= 32, fp32, bit-packed V): operand formatting + pass launchers

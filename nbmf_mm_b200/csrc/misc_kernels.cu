@@ -276,6 +276,70 @@ void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nspl
     w_epilogue_kernel<double><<<grid, 128, 0, st>>>((const double*)Gpart, (const double*)Qpart, nsplit, m, n, k, kp, projection, (const double*)rowcount, (double*)W, state);
 }
 
+// ------------------------------------------------------------------------------------
+// Tail of the reference solver on the device (_solver.py:192-213): the simplex factor (internal W, rows) is
+// renormalised in fp64 only when its worst deviation from 1 exceeds 1e-9; rows with sum <= 1e-12 are left alone.
+// Pass 1 reduces max |rowsum - 1| (integer atomicMax on the bits of a non-negative double: order-independent,
+// deterministic) and flags non-finite sums; pass 2 exports W as fp64, optionally divided by the row sums.
+// ------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void simplex_deviation_kernel(const Real* __restrict__ W, int64_t m, int k, int kp,
+                                         unsigned long long* __restrict__ out /* [0] max dev bits, [1] non-finite */) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double dev = 0.0;
+  bool bad = false;
+  if (row < m) {
+    double rs = 0.0;
+    for (int kk = 0; kk < k; ++kk) rs += (double)W[row * kp + kk];
+    dev = fabs(rs - 1.0);
+    bad = !isfinite(dev);
+    if (bad) dev = 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+  const bool any_bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(dev));
+    if (any_bad) atomicMax(&out[1], 1ull);
+  }
+}
+template <typename Real>
+__global__ void export_w_f64_kernel(const Real* __restrict__ W, int64_t m, int k, int kp, int normalize,
+                                    double* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  double rs = 0.0;
+  for (int kk = 0; kk < k; ++kk) rs += (double)W[row * kp + kk];
+  const bool div = normalize && rs > 1e-12;
+  for (int kk = 0; kk < k; ++kk) {
+    const double v = (double)W[row * kp + kk];
+    out[row * k + kk] = div ? v / rs : v;
+  }
+}
+template <typename Real>
+__global__ void export_h_f64_kernel(const Real* __restrict__ H, int64_t n, int k, int64_t ldh, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * k) return;
+  out[e] = (double)H[(e / n) * ldh + (e % n)];
+}
+void launch_simplex_deviation(int dtype, const void* W, int64_t m, int k, int kp, unsigned long long* out, cudaStream_t st) {
+  cudaMemsetAsync(out, 0, 16, st);
+  const unsigned grid = (unsigned)((m + 255) / 256);
+  if (dtype == 0) simplex_deviation_kernel<float><<<grid, 256, 0, st>>>((const float*)W, m, k, kp, out);
+  else simplex_deviation_kernel<double><<<grid, 256, 0, st>>>((const double*)W, m, k, kp, out);
+}
+void launch_export_f64(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, int kp, int64_t ldh,
+                       int normalize_w, double* W_out, double* H_out, cudaStream_t st) {
+  const unsigned gw = (unsigned)((m + 127) / 128), gh = (unsigned)((n * k + 255) / 256);
+  if (dtype == 0) {
+    if (W_out) export_w_f64_kernel<float><<<gw, 128, 0, st>>>((const float*)W, m, k, kp, normalize_w, W_out);
+    if (H_out) export_h_f64_kernel<float><<<gh, 256, 0, st>>>((const float*)H, n, k, ldh, H_out);
+  } else {
+    if (W_out) export_w_f64_kernel<double><<<gw, 128, 0, st>>>((const double*)W, m, k, kp, normalize_w, W_out);
+    if (H_out) export_h_f64_kernel<double><<<gh, 256, 0, st>>>((const double*)H, n, k, ldh, H_out);
+  }
+}
+
 // transform() tail: clip to [lo, hi] then row renormalisation (_base.py:196-198)
 template <typename Real>
 __global__ void clip_rows_kernel(Real* __restrict__ W, int64_t m, int k, int kp, Real lo, Real hi) {

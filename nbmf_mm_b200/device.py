@@ -297,6 +297,21 @@ class DeviceProblem:
         W, H = self.get_factors_device()
         return W.cpu().numpy().astype(np.float64), H.cpu().numpy().astype(np.float64)
 
+    def simplex_deviation(self) -> float:
+        """max_i |sum_k W[i,k] - 1| in fp64 (NaN if a row sum is not finite): the test of ``_solver.py:195-199``."""
+        dev = C.c_double(0.0)
+        self._call("nbmf_simplex_deviation", C.byref(dev))
+        return float(dev.value)
+
+    def get_factors_f64(self, normalize_w=False):
+        """Host fp64 copies of W (m x k) and H (k x n); conversion to fp64 and the optional row renormalisation
+        of the solver tail (``_solver.py:200-204``) run on the device."""
+        torch = _torch()
+        W = torch.empty((self.m, self.k), dtype=torch.float64, device=self.dev)
+        H = torch.empty((self.k, self.n), dtype=torch.float64, device=self.dev)
+        self._call("nbmf_get_factors_f64", _ptr(W), _ptr(H), 1 if normalize_w else 0)
+        return W.cpu().numpy(), H.cpu().numpy()      # (pinned staging was measured slower: the allocation dominates)
+
     # -- steps
     def h_half_step(self):
         self._call("nbmf_h_half_step")

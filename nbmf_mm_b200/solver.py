@@ -269,7 +269,17 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
             prob.init_comm()
         prob.set_factors(W_local, H_init, normalize_w=True)
         losses_arr, n_iter, converged = prob.fit(max_iter, tol)
-        W_loc, H = prob.get_factors()
+        # tail of the reference solver (_solver.py:192-213) on the device: the simplex factor is the internal W in
+        # both orientations; it is renormalised (fp64) only when its worst deviation exceeds 1e-9 -- the worst over
+        # ALL rows, so row shards agree on the decision first
+        dev = prob.simplex_deviation()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([dev if np.isfinite(dev) else np.inf], dtype=torch.float64, device=require_cuda(device))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev = float(t.item())
+        W_loc, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dev) and dev > 1e-9))
     finally:
         prob.close()
 
@@ -299,7 +309,6 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     W_final, H_final = W, H                                # (m x k), (k x n) internal
     if transpose:                                          # _solver.py:182-184
         W_final, H_final = np.ascontiguousarray(H_final.T), np.ascontiguousarray(W_final.T)
-    W_final, H_final = final_simplex_cleanup(W_final, H_final, orientation)
     return W_final, H_final, losses, 0.0, n_iter
 
 

@@ -112,3 +112,26 @@ def test_fp16_layout_of_probabilistic_v(orientation):
     assert np.max(np.abs(c.components_ - d.components_)) < 5e-3
     with pytest.raises(ValueError, match="float32"):
         NBMF(n_components=3, max_iter=2, dtype="float64", dense_storage="float16").fit(Xr)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_solver_tail_on_device_equals_the_host_rule(dtype):
+    """fp64 export + final simplex clean-up (_solver.py:192-213) run on the device; same result as the host
+    statement of the rule applied to the plain export."""
+    from nbmf_mm_b200.solver import final_simplex_cleanup, make_problem, prepare_data
+    X, mask = _xy(257, 130, seed=8)
+    data = prepare_data(X, mask, transpose=False, dtype=dtype, device=None)
+    rs = np.random.RandomState(1)
+    W0, H0 = rs.uniform(0.1, 0.9, (257, 5)), rs.uniform(0.1, 0.9, (5, 130))
+    with make_problem(data, 5, dtype=dtype, alpha=1.2, beta=1.2, eps=1e-8, mask_semantics="reference",
+                      projection="normalize", max_iter_cap=10, device=None) as prob:
+        prob.set_factors(W0, H0, normalize_w=True)
+        prob.fit(10, 0.0)
+        W, H = prob.get_factors()
+        dev = prob.simplex_deviation()
+        assert abs(dev - np.max(np.abs(W.sum(axis=1) - 1.0))) < 1e-15
+        want_W, want_H = final_simplex_cleanup(W.copy(), H.copy(), "beta-dir")
+        got_W, got_H = prob.get_factors_f64(normalize_w=bool(dev > 1e-9))
+    assert (dev > 1e-9) == (dtype == "float32")                  # fp64 keeps the simplex to ~1e-16: no renormalisation
+    assert np.max(np.abs(got_W - want_W)) < 1e-15 and np.array_equal(got_H, want_H)
+    assert np.max(np.abs(got_W.sum(axis=1) - 1.0)) < (1e-15 if dtype == "float32" else 1e-12)
