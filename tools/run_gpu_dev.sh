@@ -1,1 +1,1 @@
-timeout 900 python tools/e2e_breakdown.py > gpurun_out/e2e_breakdown.log 2>&1; echo rc=$?; tail -3 gpurun_out/e2e_breakdown.log
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -8 gpurun_out/smoke.log
