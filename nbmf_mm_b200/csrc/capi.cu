@@ -109,7 +109,8 @@ struct Plan {
   int64_t mpad;          // tensor engine: rows padded to 128
   // workspace offsets
   size_t oW, oH, oHt, oCDpart, oCDsum, oLLpart, oLLsum, oPrior, oG, oQ, oRowcount, oHist, oState, oLoss, total;
-  size_t oWf, oHf, oPc, oPM;   // tensor engine: formatted factor blocks and re-tiled bit planes
+  size_t oWf, oHf, oPc, oMc, oPM;   // tensor engine: formatted factor blocks and re-tiled bit planes
+  bool strict;
 };
 
 struct nbmf_ctx {
@@ -182,10 +183,10 @@ static int make_plan(const nbmf_config& c, Plan* p) {
     else if (!strcmp(e, "auto")) engine = NBMF_ENGINE_AUTO;
   }
   // eps >= 1e-9: the tensor H pass takes one log per product of four x >= eps (no underflow)
-  const bool eligible = c.dtype == NBMF_F32 && c.vkind == NBMF_V_BITS && !strict && c.k <= 32 && c.eps >= 1e-9;
+  const bool eligible = c.dtype == NBMF_F32 && c.vkind == NBMF_V_BITS && c.k <= 32 && c.eps >= 1e-9;
   if (engine == NBMF_ENGINE_TENSOR && !eligible)
-    return fail(NBMF_ERR_UNSUPPORTED,
-                "tensor engine needs float32, bit-packed V, reference mask semantics, k <= 32 and eps >= 1e-9");
+    return fail(NBMF_ERR_UNSUPPORTED, "tensor engine needs float32, bit-packed V, k <= 32 and eps >= 1e-9");
+  p->strict = strict != 0;
   p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR || (engine == NBMF_ENGINE_AUTO && c.m >= 512 && c.n >= 512));
   if (p->tensor) { p->pl.kp = 32; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
   const int occ = 1;
@@ -225,11 +226,12 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   p->oState = take(sizeof(FitState));
   p->oLoss = take(64);
   p->mpad = (c.m + 127) / 128 * 128;
-  p->oWf = p->oHf = p->oPc = p->oPM = 0;
+  p->oWf = p->oHf = p->oPc = p->oMc = p->oPM = 0;
   if (p->tensor) {
     p->oWf = take((size_t)p->mpad * 128 * 4);
     p->oHf = take((size_t)p->ldh * 128 * 4);
     p->oPc = take((size_t)p->ldh * p->mpad / 8);
+    if (p->strict) p->oMc = take((size_t)p->ldh * p->mpad / 8);
     p->oPM = take((size_t)p->mpad * p->wpr * 8);
   }
   p->total = o;
@@ -366,8 +368,9 @@ extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
   if (c->p.tensor) {   // the tensor kernels read planes re-tiled per TMEM lane (format_factors.cu)
-    launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, c->at<uint32_t>(c->p.oPc), c->ws + c->p.oPM, c->st);
-    CHECK_LAUNCH(2);
+    launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, c->at<uint32_t>(c->p.oPc),
+                       c->p.strict ? c->at<uint32_t>(c->p.oMc) : nullptr, c->ws + c->p.oPM, c->st);
+    CHECK_LAUNCH(c->p.strict ? 3 : 2);
   }
   return NBMF_OK;
 }
@@ -477,7 +480,8 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd) {
   a.eps = c->cfg.eps; a.done = &c->state()->done; a.compute_cd = compute_cd;
   prof_mark(c, c->prof_h);
   if (p.tensor)
-    launch_h_pass_tensor(a, c->ws + p.oWf, c->at<uint32_t>(p.oPc), p.mpad / 32, p.h_nsplit, c->st);
+    launch_h_pass_tensor(a, c->ws + p.oWf, c->at<uint32_t>(p.oPc), p.strict ? c->at<uint32_t>(p.oMc) : nullptr, p.mpad / 32,
+                         p.h_nsplit, c->st);
   else
     p.pl.h_launch(a, p.h_nsplit, c->st);
   prof_mark(c, c->prof_h);

@@ -122,10 +122,11 @@ __global__ void tile_pm_kernel(const uint32_t* __restrict__ P, const uint32_t* _
 }
 
 void launch_tile_planes(const uint32_t* P, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, int64_t mpad,
-                        uint32_t* Pc, void* PM, cudaStream_t st) {
+                        uint32_t* Pc, uint32_t* Mc, void* PM, cudaStream_t st) {
   const int64_t nrb = mpad / 32;
   dim3 g1((unsigned)nrb, (unsigned)((wpr + 7) / 8));
   tile_pc_kernel<<<g1, 256, 0, st>>>(P, m, wpr, nrb, Pc);
+  if (Mc && M) tile_pc_kernel<<<g1, 256, 0, st>>>(M, m, wpr, nrb, Mc);       // strict mask semantics: the H pass needs M too
   dim3 g2((unsigned)(mpad / 128), (unsigned)((wpr + 7) / 8));
   tile_pm_kernel<<<g2, 256, 0, st>>>(P, M, m, n, wpr, (uint2*)PM);
 }

@@ -50,10 +50,10 @@ void launch_clip_rows(int dtype, void* W, int64_t m, int k, int kp, double lo, d
 void launch_format_w(const void* W, int64_t m, int64_t mpad, void* Wf, const FitState* state, cudaStream_t st);
 void launch_format_h(const void* H, int64_t ldh, void* Hf, const FitState* state, cudaStream_t st);
 void launch_tile_planes(const uint32_t* P, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, int64_t mpad,
-                        uint32_t* Pc, void* PM, cudaStream_t st);
+                        uint32_t* Pc, uint32_t* Mc, void* PM, cudaStream_t st);
 void launch_w_pass_tensor(const WPassArgs& a, const void* Hf, const void* PM, int nsplit, cudaStream_t st);
-void launch_h_pass_tensor(const HPassArgs& a, const void* Wf, const uint32_t* Pc, int64_t nrb, int nsplit,
-                          cudaStream_t st);
+void launch_h_pass_tensor(const HPassArgs& a, const void* Wf, const uint32_t* Pc, const uint32_t* Mc, int64_t nrb,
+                          int nsplit, cudaStream_t st);
 
 // ---- data layer
 void launch_pack_bits(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,

@@ -70,6 +70,28 @@ __device__ __forceinline__ void h_entry(float theta, uint32_t bits, uint32_t bit
       : "=f"(x), "=r"(hi), "=r"(c), "=r"(phi), "=r"(pc)
       : "f"(theta), "r"(bits), "r"(bit), "f"(eps));
 }
+//   H pass, strict mask semantics (unobserved entries contribute nothing: _solver.py with the README/paper mask):
+//   additionally the unmasked outputs are zeroed and x is replaced by 1 (log 1 = 0) where the entry is unobserved.
+__device__ __forceinline__ void h_entry_strict(float theta, uint32_t bits, uint32_t obits, uint32_t bit, float eps, float& x,
+                                               uint32_t& hi, uint32_t& c, uint32_t& phi, uint32_t& pc) {
+  asm("{\n\t.reg .pred p, o;\n\t.reg .b32 t, hh, cc;\n\t.reg .f32 y, r, h, l;\n\t"
+      "and.b32 t, %6, %8;\n\tsetp.ne.b32 p, t, 0;\n\t"
+      "and.b32 t, %7, %8;\n\tsetp.ne.b32 o, t, 0;\n\t"
+      "mov.f32 y, %5;\n\t@!p sub.f32 y, 0f3F800000, y;\n\t"
+      "add.f32 y, y, %9;\n\t"
+      "rcp.approx.ftz.f32 r, y;\n\t"
+      "and.b32 h, r, 0xffffe000;\n\t"
+      "sub.f32 l, r, h;\n\t"
+      "cvt.rn.bf16x2.f32 cc, l, h;\n\t"
+      "mov.b32 hh, h;\n\t"
+      "selp.b32 %3, hh, 0, p;\n\t"
+      "selp.b32 %4, cc, 0, p;\n\t"
+      "selp.b32 %1, hh, 0, o;\n\t"
+      "selp.b32 %2, cc, 0, o;\n\t"
+      "selp.f32 %0, y, 0f3F800000, o;\n\t}\n"
+      : "=f"(x), "=r"(hi), "=r"(c), "=r"(phi), "=r"(pc)
+      : "f"(theta), "r"(bits), "r"(obits), "r"(bit), "f"(eps));
+}
 //   W pass: signed ratio s = 1/(theta + eps) on ones, -1/((1 - theta) + eps) on observed zeros, 0 on unobserved
 //   entries; q accumulates the zeros' 1/x (= -s) with one predicated subtract.
 __device__ __forceinline__ void w_entry(float theta, uint32_t pbits, uint32_t obits, uint32_t bit, float eps, float& s,
@@ -91,6 +113,7 @@ struct HTcArgs {
   const float* H;            // [32][ldh] k-major factor (pad rows/columns 0.5): source of the resident A tile
   const float* Wf;           // [mpad/32][4][1024]  W rows hi | lo | W^T hi | lo   (format_factors.cu)
   const uint32_t* Pc;        // [ldh/128][nrb][128] bit r of word (jt, rb, jj) = P[32 rb + r][128 jt + jj]
+  const uint32_t* Mc;        // same tiling of the observation mask (strict mask semantics only)
   int64_t m, n, ldh, nrb;
   int64_t rows_per_split;    // multiple of 32
   float* CD;                 // [nsplit][2][32][ldh]
@@ -133,6 +156,7 @@ constexpr int HTC_STAGE_BYTES = 16384;
 constexpr int HTC_OFF_ACC = HTC_STAGES * HTC_STAGE_BYTES;        // fp32 accumulators [32][512 SIMT threads]
 constexpr int HTC_SMEM = HTC_OFF_ACC + 32 * 512 * 4 + 1024;
 
+template <bool STRICT>
 __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs a) {
   using namespace tc;
   if (*a.done) return;
@@ -293,14 +317,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
     };
     const uint32_t* __restrict__ pc = a.Pc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
     uint32_t word = g < nb ? pc[(size_t)g * 128] : 0u;
+    const uint32_t* __restrict__ mc = nullptr;
+    uint32_t mword = 0u;
+    if constexpr (STRICT) {
+      mc = a.Mc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
+      mword = g < nb ? mc[(size_t)g * 128] : 0u;
+    }
     float ll = 0.f, ll_sum = 0.f, ll_c = 0.f;                          // fp64 is slow here: compensated fp32 sum
     // A probe of an mbarrier costs ~200 clk even when its phase completed long ago, so every wait of the
     // loop is probed early and only checked where it is needed: the latency hides behind the arithmetic.
     bool ok_theta = false;
     for (int b = g; b < nb; b += 2) {
       const int ob = b >> 1;
-      const uint32_t bits = word >> (16 * h);
-      if (b + 2 < nb) word = pc[(size_t)(b + 2) * 128];                // prefetch the next block's bits
+      const uint32_t bits = word >> (16 * h), obits = mword >> (16 * h);
+      if (b + 2 < nb) {                                                // prefetch the next block's bits
+        word = pc[(size_t)(b + 2) * 128];
+        if constexpr (STRICT) mword = mc[(size_t)(b + 2) * 128];
+      }
       TC_EV(1 + g, b, 0);
       if (!ok_theta) mbar_wait(&bar_theta[g], ob & 1);
       TC_EV(1 + g, b, 1);
@@ -327,7 +360,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
 #pragma unroll
         for (int e = 0; e < 8; ++e) {                                  // out: Rp_hi | R_hi | Rp_c | R_c, 8 columns each
           float x;
-          h_entry(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
+          if constexpr (STRICT)
+            h_entry_strict(__uint_as_float(v[8 * u + e]), bits, obits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
+          else
+            h_entry(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
           prod = (e & 3) ? prod * x : x;
           if ((e & 3) == 3) llb += logu_(prod);                        // eps >= 1e-9: four factors cannot underflow
         }
@@ -624,11 +660,13 @@ inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
 inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(h_pass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
+    cudaFuncSetAttribute(h_pass_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
+    cudaFuncSetAttribute(h_pass_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
     attr_set = true;
   }
   dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit);
-  h_pass_tc_kernel<<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+  if (a.Mc) h_pass_tc_kernel<true><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+  else h_pass_tc_kernel<false><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
 }
 
 }  // namespace nbmf

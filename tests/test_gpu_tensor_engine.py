@@ -41,6 +41,28 @@ def test_one_step_against_oracle(m, n, k, masked):
     assert rel_err(H1, Hs) < 2e-5 and rel_err(W1, Ws) < 2e-5
 
 
+@pytest.mark.parametrize("m,n,k", [(517, 1300, 32), (130, 70, 10), (900, 600, 17)])
+def test_strict_mask_semantics_on_the_tensor_engine(m, n, k):
+    """README / paper mask semantics (unobserved entries contribute nothing to the H step and the loss): the strict
+    variant of the tensor H pass against the oracle, one step, the fused objective and a short monotone fit."""
+    Y, mask, W, H = problem(m, n, k, seed=3 * m + n)
+    Wo, Ho = orc.mm_step(Y, W, H, mask, 1.3, 1.1, mask_semantics="strict")
+    W1, H1 = nbmf_mm_update_beta_dir(Y, W, H, mask, 1.3, 1.1, mask_semantics="strict", dtype="float32", engine="tensor")
+    assert rel_err(H1, Ho) < 5e-5 and rel_err(W1, Wo) < 5e-5
+    Wr, Hr = orc.mm_step(Y, W, H, mask, 1.3, 1.1)                    # the reference quirk gives a different H
+    assert rel_err(Hr, Ho) > 1e-3
+    want = orc.map_objective(Y, W, H, mask, 1.3, 1.1, mask_semantics="strict")
+    data = prepare_data(Y, mask, transpose=False, dtype="float32", device=None)
+    with make_problem(data, k, dtype="float32", alpha=1.3, beta=1.1, eps=1e-8, mask_semantics="strict",
+                      projection="normalize", max_iter_cap=30, device=None, engine="tensor") as prob:
+        assert prob.engine == "tensor"
+        prob.set_factors(np.ascontiguousarray(W.T), H, normalize_w=False)
+        got = prob.objective()
+        assert abs(got - want) < 5e-6 * abs(want)
+        losses, n_iter, _ = prob.fit(30, 0.0)
+    assert n_iter == 30 and np.all(np.diff(losses) <= 2e-6 * np.abs(losses[:-1]))   # strict semantics is a true MM
+
+
 @pytest.mark.parametrize("m,n,k", [(517, 1300, 32), (130, 70, 10)])
 def test_fused_objective(m, n, k):
     Y, mask, W, H = problem(m, n, k, seed=5)
@@ -89,7 +111,7 @@ def test_auto_engine_selection_and_ineligible_requests():
     with make_problem(data, 8, dtype="float32", mask_semantics="reference", **kw) as p:
         assert p.engine == "tensor"
     with make_problem(data, 8, dtype="float32", mask_semantics="strict", **kw) as p:
-        assert p.engine == "simt"
+        assert p.engine == "tensor"                                  # strict H pass variant reads the mask plane too
     with make_problem(data, 40, dtype="float32", mask_semantics="reference", **kw) as p:
         assert p.engine == "simt"
     d64 = prepare_data(Y, mask, transpose=False, dtype="float64", device=None)

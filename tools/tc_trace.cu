@@ -28,7 +28,7 @@ int main(int argc, char** argv) {
   CK(cudaMemset(done, 0, 4)); CK(cudaMemset(tr, 0, 3 * TC_TRACE_BLOCKS * 8 * 8));
   fill<<<1024, 256>>>(H, 32 * ldh, 0.9f); fill<<<1024, 256>>>(Wf, mpad * 128, 0.03f); fillu<<<1024, 256>>>(Pc, ldh * mpad / 32);
   set_trace<<<1, 1>>>(tr);
-  HTcArgs a; a.H = H; a.Wf = Wf; a.Pc = Pc; a.m = m; a.n = n; a.ldh = ldh; a.nrb = mpad / 32; a.rows_per_split = mpad;
+  HTcArgs a; a.H = H; a.Wf = Wf; a.Pc = Pc; a.Mc = nullptr; a.m = m; a.n = n; a.ldh = ldh; a.nrb = mpad / 32; a.rows_per_split = mpad;
   a.CD = CD; a.LL = LL; a.eps = 1e-8f; a.done = done; a.compute_cd = 1;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   launch_h_pass_tc(a, 1, 0);
