@@ -292,7 +292,7 @@ def run_ours(a):
         src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (the file has no TF32 entry; kind::tf32 is half the bf16 rate)"
                if bf16 else "fallback 1.59 PFLOP/s bf16 / 2 (B200_PROFILING.md); MEASURED_PEAKS.json absent")
         roofline = dict(common, **{
-            "bound": "tensor", "kernel": "h_pass_tc_kernel (H half-step + fused NLL, tcgen05 3xTF32)",
+            "bound": "tensor", "kernel": "h_pass_tc_kernel (H half-step + fused NLL, tcgen05 TF32 + bf16 split precision)",
             "achieved": h_ach, "peak": tpeak, "frac": (h_ach / tpeak) if h_ach else None, "peak_source": src,
             "executed_tensor_tflops": H_EXEC * h_ach if h_ach else None,
             "frac_executed": (H_EXEC * h_ach / tpeak) if h_ach else None,

@@ -54,7 +54,7 @@ extern "C" {
 
 #define NBMF_ENGINE_AUTO 0   /* tensor engine when eligible and m, n >= 512, else SIMT */
 #define NBMF_ENGINE_SIMT 1   /* packed-FFMA2 CUDA-core kernels: every dtype / K <= 64 / layout */
-#define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, 3xTF32 split: float32, bit-packed V, K <= 32, reference mask semantics */
+#define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, TF32 + bf16 split precision: float32, bit-packed V, K <= 32, eps >= 1e-9 */
 
 typedef struct nbmf_ctx nbmf_ctx;
 

@@ -175,7 +175,7 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   const int strict = (c.mask_semantics == NBMF_MASK_STRICT && c.has_mask) ? 1 : 0;
   if (!lookup_pass(c.dtype, c.vkind == NBMF_V_DENSE_F16 ? 2 : (c.vkind == NBMF_V_DENSE ? 1 : 0), strict, c.k, &p->pl))
     return fail(NBMF_ERR_UNSUPPORTED, "no kernel variant for this (dtype, vkind, k)");
-  // engine: 0 = auto, 1 = SIMT (packed FFMA2), 2 = tensor (tcgen05, 3xTF32); NBMF_ENGINE overrides
+  // engine: 0 = auto, 1 = SIMT (packed FFMA2), 2 = tensor (tcgen05, TF32 + bf16 split precision); NBMF_ENGINE overrides
   int engine = c.engine;
   if (const char* e = getenv("NBMF_ENGINE")) {
     if (!strcmp(e, "simt")) engine = NBMF_ENGINE_SIMT;

@@ -81,7 +81,7 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         broadcast, so every rank ends with the same fitted estimator.
     dense_storage : {None, "float16"}: device layout of probabilistic X (values strictly inside (0,1)); None = the
         compute dtype, "float16" halves the bytes each pass reads (float32 arithmetic only).
-    engine : {"auto", "simt", "tensor"}: CUDA-core (packed FFMA2) kernels or the tcgen05/TMEM 3xTF32
+    engine : {"auto", "simt", "tensor"}: CUDA-core (packed FFMA2) kernels or the tcgen05/TMEM split-precision (TF32 + bf16)
         kernels (float32, binary X, K <= 32 only); "auto" picks tensor when eligible and m, n >= 512.
     """
 

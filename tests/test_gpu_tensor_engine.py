@@ -1,4 +1,4 @@
-"""The tcgen05/TMEM engine (tc_passes.cuh; float32, bit-packed V, K <= 32, 3xTF32 split) against the
+"""The tcgen05/TMEM engine (tc_passes.cuh; float32, bit-packed V, K <= 32, TF32 + bf16 split precision) against the
 oracle, the golden reference trajectories and the SIMT engine.  Same FP32-mode bars as the SIMT
 kernels: one step <= 5e-5 relative, final NLL <= 1e-4 relative after the same iteration count,
 simplex <= 1e-6, monotone objective."""
