@@ -5,7 +5,8 @@ Drop-in for the fit path of ``siddC/nbmf_mm``: same public names (``NBMFMM``, ``
 """
 from .bits import BitMatrix
 from .estimator import NBMF, NBMFMM
+from .multifit import nbmf_mm_multifit
 from .solver import nbmf_mm_solver, nbmf_mm_update_beta_dir
 
 __version__ = "0.1.0"
-__all__ = ["NBMFMM", "NBMF", "nbmf_mm_solver", "nbmf_mm_update_beta_dir", "BitMatrix"]
+__all__ = ["NBMFMM", "NBMF", "nbmf_mm_solver", "nbmf_mm_update_beta_dir", "nbmf_mm_multifit", "BitMatrix"]

@@ -196,7 +196,9 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   const int kp = p->pl.kp;
   // H pass: column blocks x row splits
   p->h_ncb = (int)((c.n + p->pl.h_bn - 1) / p->pl.h_bn);
+  // row splits of at least 128 rows, or 32 rows when the problem is too small to fill the GPU otherwise
   int64_t max_split = std::min<int64_t>(64, (c.m + 127) / 128);
+  if ((int64_t)p->h_ncb * max_split < 148) max_split = std::min<int64_t>(64, (c.m + 31) / 32);
   const size_t cd_one = (size_t)2 * kp * p->ldh * p->sz;
   while (max_split > 1 && cd_one * (size_t)max_split > ((size_t)2 << 30)) --max_split;
   p->h_nsplit = choose_split(p->h_ncb, max_split, occ);

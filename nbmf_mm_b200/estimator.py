@@ -15,6 +15,7 @@ from sklearn.utils import check_array
 from ._utils import check_is_fitted
 from .bits import BitMatrix
 from .device import reconstruct_device
+from .multifit import nbmf_mm_multifit
 from .solver import make_problem, nbmf_mm_solver, prepare_data
 
 # exact-key alias table of the reference (_base.py:127-137); keys are NOT case-folded
@@ -148,7 +149,22 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         row_sharded = self.distributed in (True, "rows")
 
         best = None
-        for r in (partition_restarts(n_init, rank, world) if by_restart else range(n_init)):
+        mine = partition_restarts(n_init, rank, world) if by_restart else list(range(n_init))
+        if n_init > 1 and not row_sharded:
+            # restarts share ONE upload of X / mask and run concurrently on separate streams (multifit.py)
+            stats = {}
+            jobs = [dict(n_components=self.n_components, alpha=self.alpha, beta=self.beta, W_init=self.W_init,
+                         H_init=self.H_init, random_state=None if self.random_state is None else self.random_state + r)
+                    for r in mine]
+            outs = nbmf_mm_multifit(X, jobs, mask=mask, orientation=orientation, max_iter=self.max_iter, tol=self.tol,
+                                    projection_method=self.projection_method, mask_semantics=self.mask_semantics,
+                                    dtype=self.dtype, device=self.device, engine=self.engine,
+                                    dense_storage=self.dense_storage, stats=stats)
+            for r, out in zip(mine, outs):
+                if best is None or out[2][-1] < best[0][2][-1]:
+                    best = (out, stats, r)
+            mine = []
+        for r in mine:
             seed = self.random_state if (self.random_state is None or n_init == 1) else self.random_state + r
             stats = {}
             out = nbmf_mm_solver(

@@ -1,0 +1,100 @@
+"""Many independent fits of ONE data set on one GPU: restarts (``n_init``), alpha/beta grids, K sweeps.
+
+The reference runs such sweeps as a Python loop of full solver calls (``examples/reproduce_magron2022.py:87-117,
+252-285``; README.md:133,144 for ``n_init``).  Here the data planes are validated, packed and uploaded ONCE and the
+fits run concurrently, each on its own CUDA stream with its own device-resident loop (loss, stop rule and ``n_iter``
+live on the device, so a fit never needs the host between its first and last kernel): small problems, whose kernels
+occupy a few of the 148 SMs, overlap instead of queueing behind each other.  Every job returns exactly what
+``nbmf_mm_solver`` returns for the same arguments (same RNG stream per job, bit-identical factors)."""
+from __future__ import annotations
+
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from .device import require_cuda
+from .solver import _CANON, make_problem, prepare_data
+
+
+def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
+    """RNG side effects and draw order of ``_solver.py:102-103,122-129`` (internal orientation m, n)."""
+    if random_state is not None:
+        np.random.seed(random_state)
+    if transpose and W_init is not None and H_init is not None:
+        W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
+    if W_init is None:
+        W_init = np.random.uniform(0.1, 0.9, (m, k))
+    if H_init is None:
+        H_init = np.random.uniform(0.1, 0.9, (k, n))
+    return np.asarray(W_init, dtype=np.float64), np.asarray(H_init, dtype=np.float64)
+
+
+def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500, tol=1e-5, eps=1e-8,
+                     projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
+                     engine="auto", dense_storage=None, n_streams=None, stats=None):
+    """Fit ``len(jobs)`` models to the same ``Y`` / ``mask``.
+
+    ``jobs``: sequence of dicts with ``n_components`` and optionally ``alpha``, ``beta`` (default 1.2),
+    ``random_state``, ``W_init``, ``H_init``, ``max_iter``, ``tol`` (defaults: the keyword arguments).  Returns a
+    list of ``(W, H, losses, 0.0, n_iter)`` in job order, each identical to
+    ``nbmf_mm_solver(Y, mask=mask, orientation=orientation, **job)``.  ``n_streams``: concurrent fits
+    (default: 8 for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own)."""
+    import torch
+    if orientation not in _CANON:
+        raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
+    jobs = [dict(j) for j in jobs]
+    if not jobs:
+        return []
+    dev = require_cuda(device)
+    transpose = orientation == "dir-beta"
+    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, dense_storage=dense_storage)
+    m, n = data.m, data.n
+    if n_streams is None:
+        n_streams = 8 if m * n <= (1 << 24) else 1
+    n_streams = max(1, min(int(n_streams), len(jobs)))
+    # inits are drawn on this thread, in job order: the global NumPy RNG is not thread-safe and every job must see
+    # the stream the reference would give it
+    prepared = []
+    for j in jobs:
+        k = int(j["n_components"])
+        mi = int(j.get("max_iter", max_iter))
+        if mi < 1:
+            raise UnboundLocalError("max_iter must be >= 1")
+        W0, H0 = _draw_inits(j.get("random_state"), m, n, k, j.get("W_init"), j.get("H_init"), transpose)
+        prepared.append((k, float(j.get("alpha", 1.2)), float(j.get("beta", 1.2)), mi, float(j.get("tol", tol)), W0, H0))
+
+    main_stream = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(main_stream)                                # the data planes were produced on this stream
+    local = threading.local()
+
+    def run(idx):
+        k, alpha, beta, mi, tl, W0, H0 = prepared[idx]
+        if not hasattr(local, "stream"):
+            local.stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(local.stream):
+            local.stream.wait_event(ready)
+            prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
+                                projection=projection_method, max_iter_cap=mi, device=device, engine=engine)
+            try:
+                prob.set_factors(W0, H0, normalize_w=True)
+                losses_arr, n_iter, converged = prob.fit(mi, tl)
+                dv = prob.simplex_deviation()                # solver tail, _solver.py:192-213
+                W, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dv) and dv > 1e-9))
+                eng = prob.engine
+            finally:
+                prob.close()
+        if transpose:                                        # _solver.py:182-184
+            W, H = np.ascontiguousarray(H.T), np.ascontiguousarray(W.T)
+        return W, H, [np.float64(v) for v in losses_arr], 0.0, n_iter, converged, eng
+
+    if n_streams == 1:
+        results = [run(i) for i in range(len(jobs))]
+    else:
+        with ThreadPoolExecutor(max_workers=n_streams) as pool:
+            results = list(pool.map(run, range(len(jobs))))
+    if stats is not None:
+        stats.update(h2d_bytes=data.h2d_bytes, n_streams=n_streams, engine=results[0][6],
+                     converged=[r[5] for r in results])
+    return [r[:5] for r in results]

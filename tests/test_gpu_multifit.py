@@ -1,0 +1,46 @@
+"""Many independent fits of one data set (restarts, alpha/beta grids, K sweeps): one
+upload, concurrent device-resident loops on separate CUDA streams.  Every job must equal the corresponding
+``nbmf_mm_solver`` call bit for bit."""
+import numpy as np
+import pytest
+
+from nbmf_mm_b200 import NBMF, nbmf_mm_multifit, nbmf_mm_solver
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(m=226, n=285, seed=0):
+    rng = np.random.default_rng(seed)
+    X = (rng.random((m, n)) < 0.05).astype(np.float64)          # lastfm-like sparsity
+    mask = (rng.random((m, n)) < 0.85).astype(np.float64)
+    return X, mask
+
+
+@pytest.mark.parametrize("orientation,dtype", [("beta-dir", "float64"), ("dir-beta", "float64"), ("beta-dir", "float32")])
+def test_grid_of_jobs_equals_sequential_solver_calls(orientation, dtype):
+    X, mask = _data()
+    jobs = [dict(n_components=k, alpha=a, beta=b, random_state=s)
+            for k, a, b, s in [(6, 1.2, 1.2, 0), (10, 1.0, 1.4, 1), (10, 2.0, 1.0, 2), (16, 1.2, 1.2, 3), (33, 1.1, 1.3, 4),
+                               (6, 1.2, 1.2, 0), (8, 1.5, 1.5, 7), (12, 1.2, 1.0, 8), (4, 1.0, 1.0, 9)]]
+    stats = {}
+    got = nbmf_mm_multifit(X, jobs, mask=mask, orientation=orientation, max_iter=40, tol=1e-4, dtype=dtype, n_streams=4,
+                           stats=stats)
+    assert stats["n_streams"] == 4 and len(got) == len(jobs)
+    for j, out in zip(jobs, got):
+        W, H, losses, _, n_iter = nbmf_mm_solver(X, mask=mask, orientation=orientation, max_iter=40, tol=1e-4, dtype=dtype, **j)
+        assert n_iter == out[4] and np.array_equal(losses, out[2])
+        assert np.array_equal(W, out[0]) and np.array_equal(H, out[1])
+    assert np.array_equal(got[0][0], got[5][0])                  # identical jobs give identical results
+
+
+def test_n_init_uses_one_upload_and_keeps_the_best_restart():
+    X, mask = _data(seed=3)
+    kw = dict(n_components=7, max_iter=30, tol=0.0, random_state=11)
+    est = NBMF(n_init=6, **kw).fit(X, mask=mask)
+    singles = [NBMF(n_components=7, max_iter=30, tol=0.0, random_state=11 + r).fit(X, mask=mask) for r in range(6)]
+    best = int(np.argmin([s.loss_curve_[-1] for s in singles]))
+    assert est.best_init_ == best
+    assert np.array_equal(est.W_, singles[best].W_) and np.array_equal(est.components_, singles[best].components_)
+    assert est.transfer_stats_["n_streams"] >= 1
+    # restart 0 of an n_init run is the n_init=1 run with the same random_state
+    assert np.array_equal(singles[0].W_, NBMF(**kw).fit(X, mask=mask).W_)
