@@ -150,13 +150,15 @@ static int format_w(nbmf_ctx* c, bool guarded);
 static int format_h(nbmf_ctx* c, bool guarded);
 
 static int choose_split(int64_t blocks, int64_t max_split, int occ = 1) {
+  // fraction of the SM slots the grid keeps busy over its waves, times a mild preference for few splits
+  // (every split costs a partial buffer and a term in the fixed-order reduction)
   if (max_split < 1) max_split = 1;
   const double sms = 148.0 * occ;
   int best = 1;
   double best_score = -1.0;
   for (int s = 1; s <= max_split; ++s) {
     const double ctas = (double)blocks * s, waves = ctas / sms;
-    double score = waves / ceil(waves) * std::min(1.0, ctas / sms) - 0.01 * s;
+    const double score = ctas / (ceil(waves) * sms) * (1.0 - 0.01 * s);
     if (score > best_score + 1e-9) { best = s; best_score = score; }
   }
   return best;
@@ -238,6 +240,29 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   }
   p->total = o;
   return NBMF_OK;
+}
+
+// Pinned FitState snapshots are pooled: cudaMallocHost / cudaFreeHost cost ~0.1-1 ms and synchronise the device,
+// which matters when many small fits are created and destroyed (restarts, grids) or run concurrently.
+#include <mutex>
+static std::mutex g_pin_mu;
+static std::vector<FitState*> g_pin_free;
+static FitState* pinned_state_get() {
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (!g_pin_free.empty()) { FitState* s = g_pin_free.back(); g_pin_free.pop_back(); return s; }
+  }
+  FitState* block = nullptr;
+  constexpr int kSlots = 64;
+  if (cudaMallocHost((void**)&block, sizeof(FitState) * kSlots) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  for (int i = 1; i < kSlots; ++i) g_pin_free.push_back(block + i);
+  return block;
+}
+static void pinned_state_put(FitState* s) {
+  if (!s) return;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pin_free.push_back(s);
 }
 
 // ------------------------------------------------------------------------------------ small API
@@ -341,10 +366,10 @@ extern "C" int nbmf_create(const nbmf_config* cfg, void* ws, int64_t ws_bytes, v
   if ((uintptr_t)ws % 256) { delete c; return fail(NBMF_ERR_ARG, "workspace must be 256-byte aligned"); }
   c->ws = (unsigned char*)ws;
   c->st = (cudaStream_t)stream;
-  cudaError_t e = cudaMallocHost((void**)&c->host_state, sizeof(FitState));
-  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMallocHost"); }
-  e = cudaEventCreateWithFlags(&c->poll_ev, cudaEventDisableTiming);
-  if (e != cudaSuccess) { cudaFreeHost(c->host_state); delete c; return cuda_fail(e, "cudaEventCreate"); }
+  c->host_state = pinned_state_get();
+  if (!c->host_state) { delete c; return cuda_fail(cudaGetLastError(), "cudaMallocHost"); }
+  cudaError_t e = cudaEventCreateWithFlags(&c->poll_ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) { pinned_state_put(c->host_state); delete c; return cuda_fail(e, "cudaEventCreate"); }
   reset_state_kernel<<<1, 1, 0, c->st>>>(c->state());
   g_launches += 1;
   *out = c;
@@ -357,7 +382,7 @@ extern "C" int nbmf_destroy(nbmf_ctx* c) {
   prof_clear(c->prof_h);
   prof_clear(c->prof_w);
   if (c->poll_ev) cudaEventDestroy(c->poll_ev);
-  if (c->host_state) cudaFreeHost(c->host_state);
+  pinned_state_put(c->host_state);
   delete c;
   return NBMF_OK;
 }
