@@ -51,13 +51,14 @@ __device__ long long* g_tc_trace = nullptr;       // [4 warp slots][TC_TRACE_BLO
 // Per-entry ratio arithmetic of the tensor kernels, written as PTX so that ONE predicate per entry (the data
 // bit) drives both the choice of x and the masking of the outputs: ptxas otherwise rebuilds a 32-bit mask
 // per entry with two shifts, and the ALU pipe (shifts, logic, selects) is the busiest SIMT pipe here.
-//   H pass: x = (p ? theta : 1 - theta) + eps, r = 1/x, hi = tf32(r), c = bf16x2(hi, r - hi) in one 32-bit
+//   H pass: x = (p ? theta : 1 - theta) + eps (1 - theta saturated to [0, 1]: a Theta that rounding pushed past 1
+//   must not turn x negative; free), r = 1/x, hi = tf32(r), c = bf16x2(hi, r - hi) in one 32-bit
 //   word (low half = hi: the K order of the bf16 correction MMA), and the copies of hi and c masked by p.
 __device__ __forceinline__ void h_entry(float theta, uint32_t bits, uint32_t bit, float eps, float& x, uint32_t& hi,
                                         uint32_t& c, uint32_t& phi, uint32_t& pc) {
   asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f32 y, r, h, l;\n\t"
       "and.b32 t, %6, %7;\n\tsetp.ne.b32 p, t, 0;\n\t"
-      "mov.f32 y, %5;\n\t@!p sub.f32 y, 0f3F800000, y;\n\t"
+      "mov.f32 y, %5;\n\t@!p sub.sat.f32 y, 0f3F800000, y;\n\t"
       "add.f32 y, y, %8;\n\t"
       "rcp.approx.ftz.f32 r, y;\n\t"
       "and.b32 h, r, 0xffffe000;\n\t"
@@ -77,7 +78,7 @@ __device__ __forceinline__ void h_entry_strict(float theta, uint32_t bits, uint3
   asm("{\n\t.reg .pred p, o;\n\t.reg .b32 t, hh, cc;\n\t.reg .f32 y, r, h, l;\n\t"
       "and.b32 t, %6, %8;\n\tsetp.ne.b32 p, t, 0;\n\t"
       "and.b32 t, %7, %8;\n\tsetp.ne.b32 o, t, 0;\n\t"
-      "mov.f32 y, %5;\n\t@!p sub.f32 y, 0f3F800000, y;\n\t"
+      "mov.f32 y, %5;\n\t@!p sub.sat.f32 y, 0f3F800000, y;\n\t"
       "add.f32 y, y, %9;\n\t"
       "rcp.approx.ftz.f32 r, y;\n\t"
       "and.b32 h, r, 0xffffe000;\n\t"
