@@ -13,18 +13,16 @@
 // The streamed operand blocks are pre-split and pre-swizzled in global memory by format_factors.cu, so
 // each pipeline stage is ONE 1-D bulk copy (cp.async.bulk + mbarrier complete_tx): no tensor maps.
 //
-// CTA = 21 warps, one CTA per SM (it owns all 512 TMEM columns).  The streamed blocks are dealt to two
-// independent pipelines ("groups"): group g owns blocks b = g, g+2, .., its own Theta and ratio regions
-// and its own accumulators in TMEM, eight SIMT warps and two issuing warps.  While one group sits in the
-// fixed latencies of a block (barrier round trips, TMEM loads and stores, MMA completion) the other one
-// computes, which is what keeps both the issue slots and the tensor pipe busy.
+// CTA = 20 warps (640 threads, 96 registers each), one CTA per SM (it owns all 512 TMEM columns).  The streamed
+// blocks are dealt to two independent pipelines ("groups"): group g owns blocks b = g, g+2, .., its own Theta and
+// ratio regions and its own accumulators in TMEM, eight SIMT warps and two issuing warps.
 //   warps 0..15   SIMT.  Warp w works on TMEM lane quarter (w & 3) -- the hardware restricts a warp to
 //                 lanes 32*(w % 4).. --, group g = (w >> 2) & 1 and half h = w >> 3 of the block's columns.
-//   warps 16, 17  MMA1 issuer of group 0 / 1;  warps 18, 19  MMA2 issuer of group 0 / 1.  The whole warp runs
+//   warps 16, 17  MMA1 issuer of group 0 / 1, which also produces the group's shared-memory stages (one bulk copy
+//                 per block, a few blocks ahead);  warps 18, 19  MMA2 issuer of group 0 / 1.  The whole warp runs
 //                 the loop (uniform control flow, operands in uniform registers); one elected lane executes
-//                 the tcgen05.mma / commit instructions.  One warp cannot issue everything: its barrier waits
-//                 and commits are serial and cost ~200 clk each (measured with tools/tc_trace.cu).
-//   warp 20       bulk-copy producer for the shared-memory stages (shared by both groups).
+//                 the tcgen05.mma / commit / bulk-copy instructions.  One warp cannot issue everything: its barrier
+//                 waits and commits are serial and cost ~200 clk each (measured with tools/tc_trace.cu).
 // The tensor core's fp32 accumulate truncates, so an unbroken chain of 3e4 accumulations drifts by ~1e-4
 // relative (measured); each group's TMEM accumulators are flushed into fp32 registers by the group's own
 // SIMT warps every kFlush blocks, just before they release the first block of the next chain.
@@ -139,8 +137,7 @@ struct WTcArgs {
 constexpr int TC_SIMT_WARPS = 16;
 constexpr int TC_MMA1_WARP = 16;                        // + group
 constexpr int TC_MMA2_WARP = 18;                        // + group
-constexpr int TC_TMA_WARP = 20;
-constexpr int TC_THREADS = 21 * 32;
+constexpr int TC_THREADS = 20 * 32;                     // 640 threads: 96 registers each
 constexpr int kFlush = 8;                                // own blocks per TMEM accumulation chain
 
 // =====================================================================================
@@ -152,7 +149,8 @@ constexpr int kFlush = 8;                                // own blocks per TMEM 
 // TMEM: A hi 0..31, bf16 [hi|lo] 32..63 | Theta[g] 64..127 | R[g] 128..383 (per 8 rows: Rp_hi R_hi Rp_c R_c)
 //       | {C, S}[g] 384..511
 // =====================================================================================
-constexpr int HTC_STAGES = 6;
+constexpr int HTC_STAGES = 8;
+constexpr int HTC_LOOK = 2;                              // stages are produced this many own blocks ahead
 constexpr int HTC_STAGE_BYTES = 16384;
 constexpr int HTC_OFF_ACC = HTC_STAGES * HTC_STAGE_BYTES;        // fp32 accumulators [32][512 SIMT threads]
 constexpr int HTC_SMEM = HTC_OFF_ACC + 32 * 512 * 4 + 1024;
@@ -178,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   const int nb = r1 > r0 ? (int)((r1 - r0 + 31) / 32) : 0;
   const bool cd = a.compute_cd != 0;
 
-  if (warp == TC_TMA_WARP) tmem_alloc(&tmem_base_s, 512);
+  if (warp == TC_MMA1_WARP) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < HTC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_a, TC_SIMT_WARPS);
@@ -196,24 +194,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   constexpr uint32_t id = idesc_tf32(128, 32), idb = idesc_bf16(128, 32);
 
   double ll_total = 0.0;
-  if (warp == TC_TMA_WARP) {
-    // ------------------------------------------------------------- producer: one 16 KB bulk copy per block
-    const bool leader = elect_one();
-    const float* src = a.Wf + (size_t)(r0 >> 5) * 4096;
-    for (int b = 0; b < nb; ++b) {
-      const int s = b % HTC_STAGES;
-      if (b >= HTC_STAGES) mbar_wait(&bar_empty[s], ((b / HTC_STAGES) - 1) & 1);
-      if (leader) {
-        mbar_expect_tx(&bar_full[s], HTC_STAGE_BYTES);
-        bulk_g2s(smem + s * HTC_STAGE_BYTES, src + (size_t)b * 4096, HTC_STAGE_BYTES, &bar_full[s]);
-      }
-      __syncwarp();
-    }
-  } else if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
-    // ------------------------------------------------------------- MMA1 issuer of group g
+  if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
+    // ------------------------------------------------------------- MMA1 issuer of group g, and producer of the
+    // group's shared-memory stages: one 16 KB bulk copy per block, HTC_LOOK own blocks ahead.  The stage of block
+    // b + 2 LOOK was last read by MMA2(b + 2 LOOK - STAGES) = MMA2(b - 4), which has completed by the time
+    // MMA1(b) is issued (the SIMT warps are already working on block b - 2), so the wait does not stall the issue.
     const int g = warp - TC_MMA1_WARP;
     const bool leader = elect_one();
     const uint32_t tT = tTheta + 32 * g;
+    const float* src = a.Wf + (size_t)(r0 >> 5) * 4096;
+    auto produce = [&](int bp) {
+      if (bp >= nb) return;
+      const int s = bp % HTC_STAGES;
+      if (bp >= HTC_STAGES) mbar_wait(&bar_empty[s], ((bp / HTC_STAGES) - 1) & 1);
+      if (leader) {
+        mbar_expect_tx(&bar_full[s], HTC_STAGE_BYTES);
+        bulk_g2s(smem + s * HTC_STAGE_BYTES, src + (size_t)bp * 4096, HTC_STAGE_BYTES, &bar_full[s]);
+      }
+      __syncwarp();
+    };
+#pragma unroll
+    for (int i = 0; i < HTC_LOOK; ++i) produce(g + 2 * i);
     mbar_wait(&bar_a, 0);
     fence_after_sync();
     for (int b = g; b < nb; b += 2) {
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       }
       __syncwarp();
       TC_EV(0, b, 1);
+      produce(b + 2 * HTC_LOOK);
     }
   } else if (warp == TC_MMA2_WARP || warp == TC_MMA2_WARP + 1) {
     // ------------------------------------------------------------- MMA2 issuer of group g
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == TC_TMA_WARP) tmem_dealloc(tb, 512);
+  if (warp == TC_MMA1_WARP) tmem_dealloc(tb, 512);
   const double tot = block_sum<TC_THREADS>(ll_total, red_scratch);
   if (tid == 0) a.LL[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<float>();
 }
@@ -427,10 +429,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
 //   MMA2: G[128 i x 32 k] += S[128 x 64 j] . H[32 k x 64 j]^T
 // TMEM: A hi 0..31, bf16 [hi|lo] 32..63 | Theta[g] 64..191 | S[g] 192..447 (per 8 columns: S_hi S_c) | G[g] 448..511
 // =====================================================================================
-constexpr int WTC_STAGES = 5;
+constexpr int WTC_STAGES = 6;
+constexpr int WTC_LOOK = 1;
 constexpr int WTC_STAGE_BYTES = 32768;
-constexpr int WTC_OFF_ACC = WTC_STAGES * WTC_STAGE_BYTES;         // fp32 accumulators [16][512 SIMT threads]
-constexpr int WTC_OFF_Q = WTC_OFF_ACC + 16 * 512 * 4;
+constexpr int WTC_OFF_X = WTC_STAGES * WTC_STAGE_BYTES;           // group 1 -> group 0 accumulator exchange [16][256]
+constexpr int WTC_OFF_Q = WTC_OFF_X + 16 * 256 * 4;
 constexpr int WTC_SMEM = WTC_OFF_Q + 4 * 128 * 4 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs a) {
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   if (*a.done) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* sAcc = reinterpret_cast<float*>(smem + WTC_OFF_ACC);       // thread t: 16 G sums at [e * 512 + t]
+  float* sX = reinterpret_cast<float*>(smem + WTC_OFF_X);           // [16 accumulators][256 threads of group 1]
   float* sQ = reinterpret_cast<float*>(smem + WTC_OFF_Q);           // [4 (group, half)][128 lanes]
   __shared__ uint64_t bar_full[WTC_STAGES], bar_empty[WTC_STAGES];
   __shared__ uint64_t bar_a, bar_theta[2], bar_tfree[2], bar_s[2], bar_sfree[2], bar_g[2];
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   const int64_t c1 = min(a.n, c0 + a.cols_per_split);
   const int nb = c1 > c0 ? (int)((c1 - c0 + 63) / 64) : 0;
 
-  if (warp == TC_TMA_WARP) tmem_alloc(&tmem_base_s, 512);
+  if (warp == TC_MMA1_WARP) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < WTC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_a, TC_SIMT_WARPS);
@@ -468,24 +471,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   const uint32_t tA = tb, tTheta = tb + 64, tS = tb + 192, tG = tb + 448;
   constexpr uint32_t id1 = idesc_tf32(128, 64), id1b = idesc_bf16(128, 64), id2 = idesc_tf32(128, 32), id2b = idesc_bf16(128, 32);
 
-  if (warp == TC_TMA_WARP) {
-    // ------------------------------------------------------------- producer: one 32 KB bulk copy per block
-    const bool leader = elect_one();
-    const float* src = a.Hf + (size_t)(c0 >> 6) * 8192;
-    for (int b = 0; b < nb; ++b) {
-      const int s = b % WTC_STAGES;
-      if (b >= WTC_STAGES) mbar_wait(&bar_empty[s], ((b / WTC_STAGES) - 1) & 1);
-      if (leader) {
-        mbar_expect_tx(&bar_full[s], WTC_STAGE_BYTES);
-        bulk_g2s(smem + s * WTC_STAGE_BYTES, src + (size_t)b * 8192, WTC_STAGE_BYTES, &bar_full[s]);
-      }
-      __syncwarp();
-    }
-  } else if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
-    // ------------------------------------------------------------- MMA1 issuer of group g
+  if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
+    // ------------------------------------------------------------- MMA1 issuer of group g + producer of its stages
+    // (one 32 KB bulk copy per block, one own block ahead; see the H pass)
     const int g = warp - TC_MMA1_WARP;
     const bool leader = elect_one();
     const uint32_t tT = tTheta + 64 * g;
+    const float* src = a.Hf + (size_t)(c0 >> 6) * 8192;
+    auto produce = [&](int bp) {
+      if (bp >= nb) return;
+      const int s = bp % WTC_STAGES;
+      if (bp >= WTC_STAGES) mbar_wait(&bar_empty[s], ((bp / WTC_STAGES) - 1) & 1);
+      if (leader) {
+        mbar_expect_tx(&bar_full[s], WTC_STAGE_BYTES);
+        bulk_g2s(smem + s * WTC_STAGE_BYTES, src + (size_t)bp * 8192, WTC_STAGE_BYTES, &bar_full[s]);
+      }
+      __syncwarp();
+    };
+#pragma unroll
+    for (int i = 0; i < WTC_LOOK; ++i) produce(g + 2 * i);
     mbar_wait(&bar_a, 0);
     fence_after_sync();
     for (int b = g; b < nb; b += 2) {
@@ -503,6 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
         commit(&bar_theta[g]);
       }
       __syncwarp();
+      produce(b + 2 * WTC_LOOK);
     }
   } else if (warp == TC_MMA2_WARP || warp == TC_MMA2_WARP + 1) {
     // ------------------------------------------------------------- MMA2 issuer of group g
@@ -567,18 +572,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);
     }
-    float* __restrict__ myacc = sAcc + tid;                            // k = 16 h .. 16 h + 15 of the group's G
+    float accG[16];                                                    // k = 16 h .. 16 h + 15 of the group's G, fp32
 #pragma unroll
-    for (int e = 0; e < 16; ++e) myacc[e * 512] = 0.f;
+    for (int e = 0; e < 16; ++e) accG[e] = 0.f;
     int flushed = 0;
-    auto flush = [&]() {
+    auto flush = [&]() {                                               // TMEM chain -> fp32 register accumulators
       mbar_wait(&bar_g[g], flushed & 1);
       fence_after_sync();
       uint32_t c[16];
       tmem_ld16(tG + 32 * g + lane_off + 16 * h, c);
       wait_ld();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) myacc[e * 512] += __uint_as_float(c[e]);
+      for (int e = 0; e < 16; ++e) accG[e] += __uint_as_float(c[e]);
       ++flushed;
     };
     const uint2* __restrict__ pm = a.PM + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5) + h) * 128 + tl;
@@ -632,21 +637,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     }
     if (g < nb) flush();
     sQ[w4 * 128 + tl] = qsum;
+    const int t = h * 128 + tl;                                        // same (lane, k range) in both groups
+    if (g == 1) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sX[e * 256 + t] = accG[e];
+    }
     asm volatile("bar.sync 1, 512;" ::: "memory");                     // the 16 SIMT warps only
-    if (g == 0 && row < a.m) {                                         // group 0 + group 1 (thread tid + 128), fixed order
+    if (g == 0 && row < a.m) {                                         // group 0 + group 1, fixed order
       float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * 32 + 16 * h;
 #pragma unroll
       for (int e = 0; e < 16; e += 4)
         *reinterpret_cast<float4*>(Gg + e) =
-            make_float4(myacc[e * 512] + myacc[e * 512 + 128], myacc[(e + 1) * 512] + myacc[(e + 1) * 512 + 128],
-                        myacc[(e + 2) * 512] + myacc[(e + 2) * 512 + 128], myacc[(e + 3) * 512] + myacc[(e + 3) * 512 + 128]);
+            make_float4(accG[e] + sX[e * 256 + t], accG[e + 1] + sX[(e + 1) * 256 + t],
+                        accG[e + 2] + sX[(e + 2) * 256 + t], accG[e + 3] + sX[(e + 3) * 256 + t]);
       if (h == 0)
         a.Q[(size_t)blockIdx.y * a.m + row] = ((sQ[tl] + sQ[128 + tl]) + sQ[256 + tl]) + sQ[384 + tl];
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == TC_TMA_WARP) tmem_dealloc(tb, 512);
+  if (warp == TC_MMA1_WARP) tmem_dealloc(tb, 512);
 }
 
 inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
