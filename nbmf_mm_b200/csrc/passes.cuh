@@ -34,6 +34,27 @@ __device__ __forceinline__ void load_pairs(const Real* __restrict__ src, typenam
   }
 }
 
+// N consecutive elements of the dense V*mask layout (storage type VT: Real or __half), 16 bytes per load where the
+// run is long enough; p is aligned to the run (column offsets are multiples of N, rows of 1024 elements).
+template <typename VT, typename Real, int N>
+__device__ __forceinline__ void load_v(const VT* __restrict__ p, Real (&out)[N]) {
+  constexpr int B = (int)sizeof(VT) * N;
+  VT tmp[N];
+  if constexpr (B % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < B / 16; ++i) reinterpret_cast<uint4*>(tmp)[i] = reinterpret_cast<const uint4*>(p)[i];
+  } else if constexpr (B == 8) {
+    *reinterpret_cast<uint2*>(tmp) = *reinterpret_cast<const uint2*>(p);
+  } else if constexpr (B == 4) {
+    *reinterpret_cast<uint32_t*>(tmp) = *reinterpret_cast<const uint32_t*>(p);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) tmp[i] = p[i];
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = (Real)tmp[i];
+}
+
 // =====================================================================================
 // H pass:  C[k][j] = sum_i W[i][k] * pos[i][j] / (Theta[i][j] + eps)
 //          D[k][j] = sum_i W[i][k] * neg[i][j] / ((1 - Theta[i][j]) + eps)
@@ -164,7 +185,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     Real vnext[C];
     if constexpr (DENSE) {
 #pragma unroll
-      for (int cc = 0; cc < C; ++cc) vnext[cc] = (Real)Vg[(size_t)rb * a.ldv + j0 + cc];
+      for (int cc = 0; cc < C; ++cc) vnext[cc] = Real(0);
+      load_v<VT, Real, C>(Vg + (size_t)rb * a.ldv + j0, vnext);
     }
 
 #pragma unroll 2
@@ -196,8 +218,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) vcur[cc] = vnext[cc];
         const int64_t rn = min(rb + r + 1, a.m - 1);
-#pragma unroll
-        for (int cc = 0; cc < C; ++cc) vnext[cc] = (Real)Vg[(size_t)rn * a.ldv + j0 + cc];
+        load_v<VT, Real, C>(Vg + (size_t)rn * a.ldv + j0, vnext);
       }
 
       // ---- masked ratios in registers, loss term, second contraction
@@ -372,6 +393,13 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
     }
   };
 
+  constexpr bool VPREF = DENSE && sizeof(Real) == 4;              // fp64 variants are short of registers: no lookahead
+  Real vnext[VPREF ? C : 1][8];                                   // dense V: the chunk after the one being worked on
+  if constexpr (VPREF) {
+#pragma unroll
+    for (int rr = 0; rr < C; ++rr)
+      load_v<VT, Real, 8>(Vg + (size_t)min(ib + il + rr, a.m - 1) * a.ldv + min(c0, a.ldv - 8), vnext[rr]);
+  }
   if (ntiles > 0) issue_tile(0);
   cp_async_commit();
 
@@ -402,15 +430,21 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
       }
 #pragma unroll 1
       for (int u = 0; u < 4; ++u) {
-        Real vv[C][8];
-        if constexpr (DENSE) {
+        Real vv[DENSE ? C : 1][8];
+        if constexpr (VPREF) {
+          // this chunk was loaded while the previous one was being worked on; start the next one now (the chunks
+          // of a column split are consecutive runs of 8 columns, whatever tile / word they fall in)
 #pragma unroll
           for (int rr = 0; rr < C; ++rr) {
-            const int64_t row = min(ib + il + rr, a.m - 1);
-            const VT* src = Vg + (size_t)row * a.ldv + colw + 8 * u;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) vv[rr][e] = (Real)src[e];
+            for (int e = 0; e < 8; ++e) vv[rr][e] = vnext[rr][e];
+            const int64_t row = min(ib + il + rr, a.m - 1);
+            load_v<VT, Real, 8>(Vg + (size_t)row * a.ldv + min(colw + 8 * u + 8, a.ldv - 8), vnext[rr]);
           }
+        } else if constexpr (DENSE) {
+#pragma unroll
+          for (int rr = 0; rr < C; ++rr)
+            load_v<VT, Real, 8>(Vg + (size_t)min(ib + il + rr, a.m - 1) * a.ldv + colw + 8 * u, vv[rr]);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {

@@ -1,10 +1,8 @@
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1_final.log 2> gpurun_out/bench_n1_final.err; echo "bench n1 rc=$?"
-for n in 2 4 8; do
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_n${n}_final.log 2> gpurun_out/bench_n${n}_final.err; echo "bench n$n rc=$?"; tail -1 gpurun_out/bench_n${n}_final.err | cut -c1-200
-done
+timeout 1500 python -m pytest tests/test_gpu_estimator.py tests/test_gpu_onestep.py tests/test_gpu_trajectory.py tests/test_gpu_ingest_eval.py -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest.log
+timeout 900 python tools/dense_bench.py > gpurun_out/dense_bench.log 2> gpurun_out/dense_bench.err; echo rc=$?; tail -3 gpurun_out/dense_bench.err
 python - <<'PY'
 import json
-for n in (1,2,4,8):
-    d=json.loads(open(f'gpurun_out/bench_n{n}_final.log').read().strip().splitlines()[-1]); r=d['roofline']
-    print('N=%d: h_ms=%.2f w_ms=%.2f step=%.2f ms value=%.3e frac=%.3f clocks=%s e2e=%s'%(n, r['avg_launch_ms'], r['w_pass']['avg_launch_ms'], d['ms_per_step'], d['value'], r['frac'], d['clocks'], d['e2e'] and (d['e2e']['value'], d['e2e']['seconds'])))
+for l in open('gpurun_out/dense_bench.log'):
+    d=json.loads(l); r=d['roofline']
+    print(d['config']['workload'], '| value %.3e | W pass %.2f ms %.0f GB/s (%.2f) | H pass %.2f ms %.0f GB/s (%.2f) | loss %s'%(d['value'], r['avg_launch_ms'], r['achieved'], r['frac'], r['h_pass']['avg_launch_ms'], r['h_pass']['achieved'], r['h_pass']['frac'], d['loss_first_last']))
 PY
