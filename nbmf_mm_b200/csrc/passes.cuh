@@ -73,13 +73,14 @@ struct HCfg {
   static constexpr int CW = G * C;          // columns per warp
   static constexpr int BN = NW * CW;        // columns per CTA
   static constexpr int WPT = BN / 32;       // bit words per tile row
-  static constexpr int BM = 32;             // rows per stage
+  static constexpr int BM = DENSE ? 16 : 32;   // rows per stage (dense: the V tile rides in the stage too)
   static constexpr int NSTAGE = 3;
   static constexpr int NT = NW * 32;
   static constexpr int W_BYTES = BM * KP * (int)sizeof(Real);
   static constexpr int P_BYTES = DENSE ? 0 : BM * WPT * 4;
   static constexpr int M_BYTES = STRICT ? BM * WPT * 4 : 0;
-  static constexpr int STAGE_BYTES = W_BYTES + P_BYTES + M_BYTES;
+  static constexpr int V_BYTES = DENSE ? BM * BN * (int)sizeof(VT) : 0;   // dense V*mask tile, staged by cp.async
+  static constexpr int STAGE_BYTES = W_BYTES + P_BYTES + M_BYTES + V_BYTES;
   static constexpr int SMEM = NSTAGE * STAGE_BYTES;
   static_assert(KP % S == 0 && KH % 2 == 0, "K slice per lane must be even");
   static_assert((KP * sizeof(Real)) % 16 == 0, "W rows must be 16-byte multiples");
@@ -158,6 +159,18 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
                    a.M + (size_t)(rb + r) * a.wpr + (size_t)blockIdx.x * WPT + 4 * q);
       }
     }
+    if constexpr (DENSE) {
+      // the V*mask tile: rows of BN elements, NSTAGE - 1 tiles (2 x 16 rows) ahead of the arithmetic -- a register
+      // prefetch one row ahead left the DRAM latency exposed (52 % of the stall samples on the load's first use)
+      constexpr int CPR = Cfg::BN * (int)sizeof(VT) / 16;         // 16-byte chunks per tile row
+      const int vchunks = nrows * CPR;
+      const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(Vg + (size_t)blockIdx.x * Cfg::BN);
+      for (int c = tid; c < vchunks; c += NT) {
+        const int r = c / CPR, q = c % CPR;
+        cp_async16(st + Cfg::W_BYTES + Cfg::P_BYTES + Cfg::M_BYTES + 16 * c,
+                   vsrc + ((size_t)(rb + r) * a.ldv) * sizeof(VT) + 16 * (size_t)q);
+      }
+    }
   };
 
 #pragma unroll
@@ -182,12 +195,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     Real ll[C];
 #pragma unroll
     for (int cc = 0; cc < C; ++cc) ll[cc] = Real(0);
-    Real vnext[C];
-    if constexpr (DENSE) {
-#pragma unroll
-      for (int cc = 0; cc < C; ++cc) vnext[cc] = Real(0);
-      load_v<VT, Real, C>(Vg + (size_t)rb * a.ldv + j0, vnext);
-    }
+    const VT* Vt = reinterpret_cast<const VT*>(st + Cfg::W_BYTES + Cfg::P_BYTES + Cfg::M_BYTES) + jw;   // dense V tile
 
 #pragma unroll 2
     for (int r = 0; r < nrows; ++r) {
@@ -214,12 +222,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
       if constexpr (!DENSE) pb = Pb[r * WPT + (jw >> 5)] >> (jw & 31);
       if constexpr (STRICT) mb = Mb[r * WPT + (jw >> 5)] >> (jw & 31);
       Real vcur[C];
-      if constexpr (DENSE) {
-#pragma unroll
-        for (int cc = 0; cc < C; ++cc) vcur[cc] = vnext[cc];
-        const int64_t rn = min(rb + r + 1, a.m - 1);
-        load_v<VT, Real, C>(Vg + (size_t)rn * a.ldv + j0, vnext);
-      }
+      if constexpr (DENSE) load_v<VT, Real, C>(Vt + r * Cfg::BN, vcur);
 
       // ---- masked ratios in registers, loss term, second contraction
 #pragma unroll

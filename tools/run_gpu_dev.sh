@@ -1,4 +1,4 @@
-timeout 1500 python -m pytest tests/test_gpu_estimator.py tests/test_gpu_onestep.py tests/test_gpu_trajectory.py tests/test_gpu_ingest_eval.py -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest.log
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest.log
 timeout 900 python tools/dense_bench.py > gpurun_out/dense_bench.log 2> gpurun_out/dense_bench.err; echo rc=$?; tail -3 gpurun_out/dense_bench.err
 python - <<'PY'
 import json
