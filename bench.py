@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-warmup", type=int, default=1, help="untimed end-to-end calls before the timed one")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
     return ap.parse_args()
@@ -323,18 +324,22 @@ def run_ours(a):
         prob.close()
         del P, Mk, W0, H0
         torch.cuda.empty_cache()
+        def e2e_call(st):
+            return nbmf_mm_solver(BitMatrix(Ph, (m_local, N)), K, max_iter=steps, tol=0.0, alpha=1.2, beta=1.2,
+                                  mask=BitMatrix(Mh, (m_local, N)), random_state=0, dtype=a.dtype, device=dev,
+                                  distributed=True, shard=(r0, M_rows), stats=st, engine=a.engine)
+        for _ in range(max(0, a.e2e_warmup)):              # untimed, like the W warm-up steps of the device-timed figure:
+            e2e_call({})                                   # page-locked factor staging and allocator pools exist afterwards
         stats = {}
         barrier()
         t0 = time.perf_counter()
-        out = nbmf_mm_solver(BitMatrix(Ph, (m_local, N)), K, max_iter=steps, tol=0.0, alpha=1.2, beta=1.2,
-                             mask=BitMatrix(Mh, (m_local, N)), random_state=0, dtype=a.dtype, device=dev,
-                             distributed=True, shard=(r0, M_rows), stats=stats, engine=a.engine)
+        out = e2e_call(stats)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         assert out[4] == steps
         e2e = {"value": M_rows * N * steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": stats["h2d_bytes"] / steps, "d2h_bytes_per_step": stats["d2h_bytes"] / steps,
-               "seconds": dt, "api": "nbmf_mm_b200.nbmf_mm_solver(BitMatrix(pinned host), mask=BitMatrix(pinned host), "
+               "seconds": dt, "warmup_calls": max(0, a.e2e_warmup), "api": "nbmf_mm_b200.nbmf_mm_solver(BitMatrix(pinned host), mask=BitMatrix(pinned host), "
                                     "max_iter=steps, tol=0, dtype=float32): H2D of both bit planes and the inits, "
                                     "the fit loop, D2H of W, H and the loss history",
                "final_loss": float(out[2][-1])}

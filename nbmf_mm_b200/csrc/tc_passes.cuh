@@ -91,6 +91,27 @@ __device__ __forceinline__ void h_entry_strict(float theta, uint32_t bits, uint3
       : "=f"(x), "=r"(hi), "=r"(c), "=r"(phi), "=r"(pc)
       : "f"(theta), "r"(bits), "r"(obits), "r"(bit), "f"(eps));
 }
+//   Loss-only H pass (the objective of the final factors, score / evaluate): only x is needed.
+__device__ __forceinline__ float h_x(float theta, uint32_t bits, uint32_t bit, float eps) {
+  float x;
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f32 y;\n\t"
+      "and.b32 t, %2, %3;\n\tsetp.ne.b32 p, t, 0;\n\t"
+      "mov.f32 y, %1;\n\t@!p sub.sat.f32 y, 0f3F800000, y;\n\t"
+      "add.f32 %0, y, %4;\n\t}\n"
+      : "=f"(x) : "f"(theta), "r"(bits), "r"(bit), "f"(eps));
+  return x;
+}
+__device__ __forceinline__ float h_x_strict(float theta, uint32_t bits, uint32_t obits, uint32_t bit, float eps) {
+  float x;
+  asm("{\n\t.reg .pred p, o;\n\t.reg .b32 t;\n\t.reg .f32 y;\n\t"
+      "and.b32 t, %2, %4;\n\tsetp.ne.b32 p, t, 0;\n\t"
+      "and.b32 t, %3, %4;\n\tsetp.ne.b32 o, t, 0;\n\t"
+      "mov.f32 y, %1;\n\t@!p sub.sat.f32 y, 0f3F800000, y;\n\t"
+      "add.f32 y, y, %5;\n\t"
+      "selp.f32 %0, y, 0f3F800000, o;\n\t}\n"
+      : "=f"(x) : "f"(theta), "r"(bits), "r"(obits), "r"(bit), "f"(eps));
+  return x;
+}
 //   W pass: signed ratio s = 1/(theta + eps) on ones, -1/((1 - theta) + eps) on observed zeros, 0 on unobserved
 //   entries; q accumulates the zeros' 1/x (= -s) with one predicated subtract.
 __device__ __forceinline__ void w_entry(float theta, uint32_t pbits, uint32_t obits, uint32_t bit, float eps, float& s,
@@ -155,7 +176,7 @@ constexpr int HTC_STAGE_BYTES = 16384;
 constexpr int HTC_OFF_ACC = HTC_STAGES * HTC_STAGE_BYTES;        // fp32 accumulators [32][512 SIMT threads]
 constexpr int HTC_SMEM = HTC_OFF_ACC + 32 * 512 * 4 + 1024;
 
-template <bool STRICT>
+template <bool STRICT, bool CD>      // CD = false: loss-only pass (no ratio planes, no MMA2, no C / D output)
 __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs a) {
   using namespace tc;
   if (*a.done) return;
@@ -174,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   const int64_t r0 = (int64_t)split * a.rows_per_split;
   const int64_t r1 = min(a.m, r0 + a.rows_per_split);
   const int nb = r1 > r0 ? (int)((r1 - r0 + 31) / 32) : 0;
-  const bool cd = a.compute_cd != 0;
+  constexpr bool cd = CD;
 
   if (warp == TC_MMA1_WARP) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -302,8 +323,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
     // fp32 sums of this thread's accumulator slice (k = 16 h .. 16 h + 15 of the group's C and S) live in
     // shared memory: they are touched once per chain, registers are what the hot loop is short of
     float* __restrict__ myacc = sAcc + tid;
+    if constexpr (CD) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) myacc[e * 512] = 0.f;
+      for (int e = 0; e < 32; ++e) myacc[e * 512] = 0.f;
+    }
     int flushed = 0;                                                   // chains of this group already flushed
     auto flush = [&]() {                                               // TMEM chain -> fp32 accumulators
       mbar_wait(&bar_cd[g], flushed & 1);
@@ -363,7 +386,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
 #pragma unroll
         for (int e = 0; e < 8; ++e) {                                  // out: Rp_hi | R_hi | Rp_c | R_c, 8 columns each
           float x;
-          if constexpr (STRICT)
+          if constexpr (!CD)
+            x = STRICT ? h_x_strict(__uint_as_float(v[8 * u + e]), bits, obits, 1u << (8 * u + e), eps)
+                       : h_x(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps);
+          else if constexpr (STRICT)
             h_entry_strict(__uint_as_float(v[8 * u + e]), bits, obits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
           else
             h_entry(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
@@ -671,13 +697,20 @@ inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
 inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(h_pass_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
-    cudaFuncSetAttribute(h_pass_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
+    cudaFuncSetAttribute(h_pass_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
+    cudaFuncSetAttribute(h_pass_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
+    cudaFuncSetAttribute(h_pass_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
+    cudaFuncSetAttribute(h_pass_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
     attr_set = true;
   }
   dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit);
-  if (a.Mc) h_pass_tc_kernel<true><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
-  else h_pass_tc_kernel<false><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+  if (a.compute_cd) {
+    if (a.Mc) h_pass_tc_kernel<true, true><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+    else h_pass_tc_kernel<false, true><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+  } else {
+    if (a.Mc) h_pass_tc_kernel<true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+    else h_pass_tc_kernel<false, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+  }
 }
 
 }  // namespace nbmf

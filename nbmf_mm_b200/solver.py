@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 from .bits import BitMatrix
-from .device import DeviceProblem, pack_bits_device, pack_csr_device, pack_dense_device, require_cuda
+from .device import (PIN_THRESHOLD, DeviceProblem, pack_bits_device, pack_csr_device, pack_dense_device,
+                     pinned_factor_buffers, require_cuda)
 
 _CANON = ("beta-dir", "dir-beta")
 
@@ -215,14 +216,38 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     if random_state is not None:
         np.random.seed(random_state)                      # global legacy stream, as _solver.py:102-103
     transpose = orientation == "dir-beta"
-    # bit-packed host inputs: the H2D copies are asynchronous (pinned memory); the inits are drawn on the
-    # host while they are in flight and the device-side preparation runs afterwards (data.finish())
-    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage)
-    m, n, k = data.m, data.n, int(n_components)
+    k = int(n_components)
+    rank, world = 0, 1
+    if distributed:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    shape = tuple(getattr(Y, "shape", None) or np.shape(Y))
+    if len(shape) != 2:
+        raise ValueError("Y must be 2-D")
+    m, n = (shape[1], shape[0]) if transpose else shape          # internal orientation (_solver.py:113-123)
     if shard is not None:
         if transpose or not distributed:
             raise ValueError("shard=(row0, m_total) needs distributed=True and the internal (beta-dir) orientation")
         shard_row0, m = int(shard[0]), int(shard[1])
+        r0, r1 = shard_row0, shard_row0 + shape[0]
+    elif world > 1:
+        r0, r1 = _row_shard(m, rank, world)
+        if r1 <= r0:
+            raise ValueError(f"rank {rank} of {world} has no rows (m={m}); use fewer ranks")
+    else:
+        r0, r1 = 0, m
+    # large problems: the inits go up from, and the results come back into, pinned host memory (plain DMA instead of
+    # staged pageable copies and page faults of a fresh array).  Page-lock BEFORE the big copies start: cudaHostAlloc
+    # stalls DMA submission while it runs (measured: 0.4 s lost when it overlapped the bit-plane upload).
+    pinned = None
+    if (r1 - r0) * k + k * n >= PIN_THRESHOLD:
+        require_cuda(device)
+        pinned = pinned_factor_buffers(r1 - r0, k, n, dtype)
+    # bit-packed host inputs: the H2D copies are asynchronous (pinned memory); the inits are drawn on the
+    # host while they are in flight and the device-side preparation runs afterwards (data.finish())
+    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage)
+    assert (data.m, data.n) == ((r1 - r0) if shard is not None else m, n)
     if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
         W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
     if W_init is None:
@@ -231,35 +256,30 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         H_init = np.random.uniform(0.1, 0.9, (k, n))
     W_init = np.asarray(W_init, dtype=np.float64)
     H_init = np.asarray(H_init, dtype=np.float64)
+    if tuple(W_init.shape) != (m, k) or tuple(H_init.shape) != (k, n):
+        raise ValueError(f"W_init / H_init have shapes {W_init.shape} / {H_init.shape}, expected {(m, k)} / {(k, n)}")
+
+    W_local = W_init[r0:r1]
+    W_up, H_up, result_buffers = W_local, H_init, None
+    if pinned is not None:
+        (W_up, H_up), result_buffers = pinned
+        W_up.numpy()[...] = W_local                        # fp64 -> compute dtype on the host, copies still in flight
+        H_up.numpy()[...] = H_init
     data.finish()
 
-    rank, world = 0, 1
-    if distributed:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            rank, world = dist.get_rank(), dist.get_world_size()
     n_obs_global = data.n_obs
     if shard is not None:
-        r0, r1 = shard_row0, shard_row0 + data.m
         if world > 1:
             import torch
             import torch.distributed as dist
             t = torch.tensor([data.n_obs], dtype=torch.float64, device=require_cuda(device))
             dist.all_reduce(t)
             n_obs_global = float(t.item())
-        W_local = W_init[r0:r1]
     elif world > 1:
-        r0, r1 = _row_shard(m, rank, world)
-        if r1 <= r0:
-            raise ValueError(f"rank {rank} of {world} has no rows (m={m}); use fewer ranks")
         data = PreparedData(r1 - r0, n, data.vkind,
                             None if data.P is None else data.P.rows(r0, r1),
                             None if data.M is None else data.M.rows(r0, r1),
                             None if data.Vm is None else data.Vm[r0:r1], n_obs_global, data.h2d_bytes)
-        W_local = W_init[r0:r1]
-    else:
-        r0, r1 = 0, m
-        W_local = W_init
 
     prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
                         projection=projection_method, max_iter_cap=max_iter, device=device, n_obs=n_obs_global,
@@ -267,7 +287,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     try:
         if world > 1:
             prob.init_comm()
-        prob.set_factors(W_local, H_init, normalize_w=True)
+        prob.set_factors(W_up, H_up, normalize_w=True)
         losses_arr, n_iter, converged = prob.fit(max_iter, tol)
         # tail of the reference solver (_solver.py:192-213) on the device: the simplex factor is the internal W in
         # both orientations; it is renormalised (fp64) only when its worst deviation exceeds 1e-9 -- the worst over
@@ -279,7 +299,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
             t = torch.tensor([dev if np.isfinite(dev) else np.inf], dtype=torch.float64, device=require_cuda(device))
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dev = float(t.item())
-        W_loc, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dev) and dev > 1e-9))
+        W_loc, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dev) and dev > 1e-9), out=result_buffers)
     finally:
         prob.close()
 
