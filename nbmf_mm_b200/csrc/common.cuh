@@ -41,17 +41,6 @@ __device__ __forceinline__ float  rcp_(float x)  {   // bare MUFU.RCP: x >= eps 
 __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
 __device__ __forceinline__ float  div_(float a, float b)  { return a * rcp_(b); }
 __device__ __forceinline__ double div_(double a, double b) { return a / b; }
-// a / xp and b / xn for probabilistic V.  fp32: ONE reciprocal of the product (1/xp = xn / (xp xn)): the dense passes
-// are bound by the MUFU unit (16 results per clock and SM), not by HBM, so a reciprocal is worth three multiplies.
-__device__ __forceinline__ void div2_(float a, float xp, float b, float xn, float& ra, float& rb) {
-  const float rc = rcp_(xp * xn);
-  ra = a * (rc * xn);
-  rb = b * (rc * xp);
-}
-__device__ __forceinline__ void div2_(double a, double xp, double b, double xn, double& ra, double& rb) {
-  ra = a / xp;
-  rb = b / xn;
-}
 __device__ __forceinline__ float  logu_(float x)  {   // bare MUFU.LG2 (log2 units)
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

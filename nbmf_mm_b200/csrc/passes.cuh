@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
           Real neg;
           if constexpr (STRICT) neg = (((mb >> cc) & 1u) ? Real(1) : Real(0)) - v;
           else neg = Real(1) - v;
-          div2_(v, xp, neg, xn, rp, rn_);
+          rp = div_(v, xp);
+          rn_ = div_(neg, xn);
           ll[cc] += v * logu_(xp) + neg * logu_(xn);
         }
         if (a.compute_cd) {
@@ -476,8 +477,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
               qacc[rr] += p ? Real(0) : r_;
             } else {
               const Real v = vv[rr][e];
-              Real pa, qb;
-              div2_(v, theta + eps, (ob ? Real(1) : Real(0)) - v, (Real(1) - theta) + eps, pa, qb);
+              const Real pa = div_(v, theta + eps);
+              const Real qb = div_((ob ? Real(1) : Real(0)) - v, (Real(1) - theta) + eps);
               s = pa - qb;
               qacc[rr] += qb;
             }

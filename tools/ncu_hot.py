@@ -9,7 +9,12 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) == len(hdr)]
+data = []
+for r in rows[2:]:                                    # first matching launch only (the report may hold several)
+    if r and r[0] == "Kernel Name":
+        break
+    if len(r) == len(hdr) and r[0] != "Address":
+        data.append(r)
 tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 print(f"total samples {tot}; instructions {len(data)}")
