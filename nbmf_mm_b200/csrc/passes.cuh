@@ -195,6 +195,28 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     Real ll[C];
 #pragma unroll
     for (int cc = 0; cc < C; ++cc) ll[cc] = Real(0);
+    // fp64, binary V: log() is ~100 instructions, as much as the rest of an entry.  The log of a product of LOGG
+    // factors replaces LOGG logs (x >= eps, so 8 factors stay far above the fp64 underflow threshold; the product's
+    // rounding error is ~1e-15 relative).  Negative factors are flagged so that a negative x still gives NaN, as
+    // the reference's log(x) would, instead of cancelling against another negative factor.
+    constexpr bool LOGPROD = !DENSE && sizeof(Real) == 8;
+    constexpr int LOGG = 8;
+    Real px[LOGPROD ? C : 1];
+    uint32_t negm = 0u;                                   // bit cc: a factor of column cc was negative
+    if constexpr (LOGPROD) {
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) px[cc] = Real(1);
+    }
+    auto flush_logs = [&]() {
+      if constexpr (LOGPROD) {
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+          ll[cc] += logu_(((negm >> cc) & 1u) ? Real(NAN) : px[cc]);
+          px[cc] = Real(1);
+        }
+        negm = 0u;
+      }
+    };
     const VT* Vt = reinterpret_cast<const VT*>(st + Cfg::W_BYTES + Cfg::P_BYTES + Cfg::M_BYTES) + jw;   // dense V tile
 
 #pragma unroll 2
@@ -232,13 +254,24 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
           const bool p = (pb >> cc) & 1u;
           const Real x = (p ? theta[cc] : (Real(1) - theta[cc])) + eps;
           Real r_ = rcp_(x);
-          Real lg = logu_(x);
-          if constexpr (STRICT) {
-            const bool o = (mb >> cc) & 1u;
-            r_ = o ? r_ : Real(0);
-            lg = o ? lg : Real(0);
+          if constexpr (LOGPROD) {
+            Real xf = x;
+            if constexpr (STRICT) {
+              const bool o = (mb >> cc) & 1u;
+              r_ = o ? r_ : Real(0);
+              xf = o ? x : Real(1);
+            }
+            px[cc] *= xf;
+            negm |= (xf < Real(0)) ? (1u << cc) : 0u;
+          } else {
+            Real lg = logu_(x);
+            if constexpr (STRICT) {
+              const bool o = (mb >> cc) & 1u;
+              r_ = o ? r_ : Real(0);
+              lg = o ? lg : Real(0);
+            }
+            ll[cc] += lg;
           }
-          ll[cc] += lg;
           rp = p ? r_ : Real(0);
           rn_ = p ? Real(0) : r_;
         } else {
@@ -261,6 +294,12 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
           }
         }
       }
+      if constexpr (LOGPROD) {
+        if ((r & (LOGG - 1)) == LOGG - 1) flush_logs();
+      }
+    }
+    if constexpr (LOGPROD) {
+      if (nrows & (LOGG - 1)) flush_logs();
     }
 #pragma unroll
     for (int cc = 0; cc < C; ++cc) lld[cc] += (double)ll[cc];
