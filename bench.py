@@ -305,6 +305,18 @@ def run_ours(a):
                        "share_of_step": w_ms / ms_total if ms_total else None},
             "iteration_frac": (10.0 * K * entries_local * steps / (ms_total * 1e-3) * 1e-12 / tpeak),
         })
+        # what actually bounds the two kernels: warp-instruction issue slots of the SIMT stage between the two MMAs
+        # (ratio arithmetic, tf32 / bf16 splits, masking, TMEM traffic, barrier code).  Executed warp instructions per
+        # entry from the committed ncu capture x entries / launch time, against 4 issue slots per SM and clock.
+        clk = (sampler.summary().get("sm_mhz") or sampler.max_mhz or 1965) * 1e6
+        wi = {"h_pass": 1038796792 / (65536.0 * 32768.0), "w_pass": 955308628 / (65536.0 * 32768.0)}
+        roofline["issue_slots"] = {
+            "warp_instructions_per_entry": wi,
+            "source": "smsp__inst_executed.sum in profiles/r01_ncu_full_tensor_pass_kernels_final_65536x32768_k32.txt",
+            "peak": "4 warp instructions per clock and SM x 148 SMs at the median SM clock of the timed region",
+            "h_pass_frac": (wi["h_pass"] * entries_local / (h_avg_ms * 1e-3) / (4 * 148 * clk)) if h_cnt else None,
+            "w_pass_frac": (wi["w_pass"] * entries_local / (w_avg_ms * 1e-3) / (4 * 148 * clk)) if w_cnt else None,
+        }
     else:
         roofline = dict(common, **{
             "bound": "fp32" if a.dtype == "float32" else "fp64", "kernel": "h_pass_kernel (H half-step + fused NLL)",

@@ -111,6 +111,18 @@ int nbmf_create(const nbmf_config* cfg, void* workspace_dev, int64_t workspace_b
 int nbmf_destroy(nbmf_ctx* ctx);
 /* borrow the data planes (must outlive the context) */
 int nbmf_set_data_bits(nbmf_ctx* ctx, const uint32_t* p_bits_dev, const uint32_t* m_bits_dev);
+/* Streamed ingestion of HOST planes (the check_array / densify / `Y * mask` front end of _base.py:83-93 and
+ * _solver.py:106-110, for inputs that are already bit-packed on the host).  The caller copies rows [row0, row1) of the
+ * V plane into p_bits_dev (and of the mask into m_bits_dev) on its own copy stream, orders the context's stream after
+ * the copy (event) and calls nbmf_ingest_bits_rows: P &= M in place, the mask count (count_nonzero(mask),
+ * _solver.py:155) and the re-tiling for the tensor engine then run while later chunks are still crossing PCIe.  Chunks
+ * are consecutive, start on multiples of 128 rows and the last one ends at m.  nbmf_ingest_bits_end synchronises the
+ * stream and returns the mask count (m * n without a mask); nbmf_set_n_obs installs the normaliser of the objective
+ * (the count itself, or its sum over the row shards of a multi-GPU fit). */
+int nbmf_ingest_bits_begin(nbmf_ctx* ctx, uint32_t* p_bits_dev, const uint32_t* m_bits_dev);
+int nbmf_ingest_bits_rows(nbmf_ctx* ctx, int64_t row0, int64_t row1);
+int nbmf_ingest_bits_end(nbmf_ctx* ctx, double* mask_count_host);
+int nbmf_set_n_obs(nbmf_ctx* ctx, double n_obs);
 int nbmf_set_data_dense(nbmf_ctx* ctx, const void* vm_dev, const uint32_t* m_bits_dev);
 /* W_init (m x k) / H_init (k x n) in cfg.dtype; normalize_w != 0 divides every W row by its sum
  * (_solver.py:132-136).  Either pointer may be NULL to keep the current factor.  Resets the loop state. */

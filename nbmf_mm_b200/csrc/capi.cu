@@ -122,6 +122,7 @@ struct nbmf_ctx {
   const uint32_t* M = nullptr;
   const void* Vm = nullptr;
   bool rowcount_ready = false;
+  int64_t ingest_rows = 0;          // rows handed over by nbmf_ingest_bits_rows so far
   // loop
   int max_iter = 0;
   double tol = 0.0;
@@ -395,10 +396,59 @@ extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
   if (c->p.tensor) {   // the tensor kernels read planes re-tiled per TMEM lane (format_factors.cu)
-    launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, c->at<uint32_t>(c->p.oPc),
+    launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, 0, c->cfg.m, c->at<uint32_t>(c->p.oPc),
                        c->p.strict ? c->at<uint32_t>(c->p.oMc) : nullptr, c->ws + c->p.oPM, c->st);
     CHECK_LAUNCH(c->p.strict ? 3 : 2);
   }
+  return NBMF_OK;
+}
+
+// Streamed ingestion: the caller copies the host planes to the device chunk by chunk on its own copy stream, orders
+// the context's stream after each chunk (event) and calls nbmf_ingest_bits_rows for it, so that P &= M, the mask
+// count and the re-tiling for the tensor engine run while later chunks are still crossing PCIe.
+static unsigned long long* ingest_counter(nbmf_ctx* c) { return c->at<unsigned long long>(c->p.oLoss) + 4; }
+extern "C" int nbmf_ingest_bits_begin(nbmf_ctx* c, uint32_t* P, const uint32_t* M) {
+  if (!c || !P) return fail(NBMF_ERR_ARG, "nbmf_ingest_bits_begin: null argument");
+  if (c->cfg.vkind != NBMF_V_BITS) return fail(NBMF_ERR_ARG, "context was created for dense V");
+  if (c->cfg.has_mask && !M) return fail(NBMF_ERR_ARG, "has_mask is set but no mask plane given");
+  c->P = P;
+  c->M = c->cfg.has_mask ? M : nullptr;
+  c->rowcount_ready = false;
+  c->ingest_rows = 0;
+  CUDA_TRY(cudaMemsetAsync(ingest_counter(c), 0, sizeof(unsigned long long), c->st));
+  return NBMF_OK;
+}
+extern "C" int nbmf_ingest_bits_rows(nbmf_ctx* c, int64_t row0, int64_t row1) {
+  if (!c || !c->P) return fail(NBMF_ERR_ARG, "nbmf_ingest_bits_begin was not called");
+  if (row0 != c->ingest_rows || row1 <= row0 || row1 > c->cfg.m || (row0 % 128) != 0)
+    return fail(NBMF_ERR_ARG, "nbmf_ingest_bits_rows: chunks must be consecutive, start on multiples of 128 rows and end at <= m");
+  uint32_t* P = const_cast<uint32_t*>(c->P);
+  int launches = 0;
+  if (c->M) {
+    launch_and_count(P + row0 * c->p.wpr, c->M + row0 * c->p.wpr, (row1 - row0) * c->p.wpr, ingest_counter(c), c->st);
+    ++launches;
+  }
+  if (c->p.tensor) {
+    launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, row0, row1, c->at<uint32_t>(c->p.oPc),
+                       c->p.strict ? c->at<uint32_t>(c->p.oMc) : nullptr, c->ws + c->p.oPM, c->st);
+    launches += c->p.strict ? 3 : 2;
+  }
+  CHECK_LAUNCH(launches);
+  c->ingest_rows = row1;
+  return NBMF_OK;
+}
+extern "C" int nbmf_ingest_bits_end(nbmf_ctx* c, double* mask_count_host) {
+  if (!c || !c->P) return fail(NBMF_ERR_ARG, "nbmf_ingest_bits_begin was not called");
+  if (c->ingest_rows != c->cfg.m) return fail(NBMF_ERR_ARG, "nbmf_ingest_bits_end: not all rows were ingested");
+  unsigned long long h = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h, ingest_counter(c), 8, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  if (mask_count_host) *mask_count_host = c->M ? (double)h : (double)c->cfg.m * (double)c->cfg.n;
+  return NBMF_OK;
+}
+extern "C" int nbmf_set_n_obs(nbmf_ctx* c, double n_obs) {
+  if (!c || !(n_obs > 0)) return fail(NBMF_ERR_ARG, "nbmf_set_n_obs: bad arguments");
+  c->cfg.n_obs = n_obs;
   return NBMF_OK;
 }
 extern "C" int nbmf_set_data_dense(nbmf_ctx* c, const void* Vm, const uint32_t* M) {

@@ -79,11 +79,11 @@ void launch_format_h(const void* H, int64_t ldh, void* Hf, const FitState* state
 // One warp per 32 x 32 bit tile: lane r holds the word of row 32 rb + r, 32 ballots transpose it, lane c
 // writes the word of column 32 cw + c.  The 8 warps of a block take 8 adjacent column words, so the
 // strided row reads share their 32-byte sectors and every write is a full 128-byte line.
-__global__ void tile_pc_kernel(const uint32_t* __restrict__ P, int64_t m, int64_t wpr, int64_t nrb,
+__global__ void tile_pc_kernel(const uint32_t* __restrict__ P, int64_t m, int64_t wpr, int64_t nrb, int64_t rb0,
                                uint32_t* __restrict__ Pc) {
   const int lane = threadIdx.x & 31;
   const int64_t cw = (int64_t)blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int64_t rb = blockIdx.x;
+  const int64_t rb = rb0 + blockIdx.x;
   if (cw >= wpr) return;
   const int64_t row = rb * 32 + lane;
   const uint32_t w = row < m ? P[row * wpr + cw] : 0u;
@@ -99,9 +99,9 @@ __global__ void tile_pc_kernel(const uint32_t* __restrict__ P, int64_t m, int64_
 // Block = 128 rows x 8 column words: read with 8 consecutive words per row (one sector), written with 128
 // consecutive rows per column word.
 __global__ void tile_pm_kernel(const uint32_t* __restrict__ P, const uint32_t* __restrict__ M, int64_t m, int64_t n,
-                               int64_t wpr, uint2* __restrict__ PM) {
+                               int64_t wpr, int64_t it0, uint2* __restrict__ PM) {
   __shared__ uint2 tile[8][129];
-  const int64_t it = blockIdx.x, cw0 = (int64_t)blockIdx.y * 8;
+  const int64_t it = it0 + blockIdx.x, cw0 = (int64_t)blockIdx.y * 8;
   for (int t = threadIdx.x; t < 1024; t += blockDim.x) {
     const int ii = t >> 3, c = t & 7;
     const int64_t row = it * 128 + ii, cw = cw0 + c;
@@ -121,14 +121,18 @@ __global__ void tile_pm_kernel(const uint32_t* __restrict__ P, const uint32_t* _
   }
 }
 
+// Rows [row0, row1) of the planes (row0 a multiple of 128; the chunk that ends at m also writes the zero padding up to
+// mpad): the whole matrix at once, or chunk by chunk while later rows are still crossing PCIe.
 void launch_tile_planes(const uint32_t* P, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, int64_t mpad,
-                        uint32_t* Pc, uint32_t* Mc, void* PM, cudaStream_t st) {
+                        int64_t row0, int64_t row1, uint32_t* Pc, uint32_t* Mc, void* PM, cudaStream_t st) {
   const int64_t nrb = mpad / 32;
-  dim3 g1((unsigned)nrb, (unsigned)((wpr + 7) / 8));
-  tile_pc_kernel<<<g1, 256, 0, st>>>(P, m, wpr, nrb, Pc);
-  if (Mc && M) tile_pc_kernel<<<g1, 256, 0, st>>>(M, m, wpr, nrb, Mc);       // strict mask semantics: the H pass needs M too
-  dim3 g2((unsigned)(mpad / 128), (unsigned)((wpr + 7) / 8));
-  tile_pm_kernel<<<g2, 256, 0, st>>>(P, M, m, n, wpr, (uint2*)PM);
+  const int64_t end = row1 >= m ? mpad : row1;
+  if (end <= row0) return;
+  dim3 g1((unsigned)((end - row0 + 31) / 32), (unsigned)((wpr + 7) / 8));
+  tile_pc_kernel<<<g1, 256, 0, st>>>(P, m, wpr, nrb, row0 / 32, Pc);
+  if (Mc && M) tile_pc_kernel<<<g1, 256, 0, st>>>(M, m, wpr, nrb, row0 / 32, Mc);   // strict mask semantics: the H pass needs M too
+  dim3 g2((unsigned)((end - row0 + 127) / 128), (unsigned)((wpr + 7) / 8));
+  tile_pm_kernel<<<g2, 256, 0, st>>>(P, M, m, n, wpr, row0 / 128, (uint2*)PM);
 }
 
 }  // namespace nbmf

@@ -50,7 +50,7 @@ void launch_clip_rows(int dtype, void* W, int64_t m, int k, int kp, double lo, d
 void launch_format_w(const void* W, int64_t m, int64_t mpad, void* Wf, const FitState* state, cudaStream_t st);
 void launch_format_h(const void* H, int64_t ldh, void* Hf, const FitState* state, cudaStream_t st);
 void launch_tile_planes(const uint32_t* P, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, int64_t mpad,
-                        uint32_t* Pc, uint32_t* Mc, void* PM, cudaStream_t st);
+                        int64_t row0, int64_t row1, uint32_t* Pc, uint32_t* Mc, void* PM, cudaStream_t st);
 void launch_w_pass_tensor(const WPassArgs& a, const void* Hf, const void* PM, int nsplit, cudaStream_t st);
 void launch_h_pass_tensor(const HPassArgs& a, const void* Wf, const uint32_t* Pc, const uint32_t* Mc, int64_t nrb,
                           int nsplit, cudaStream_t st);
@@ -67,6 +67,8 @@ void launch_transpose_bits(const uint32_t* src, int64_t m, int64_t n, int64_t wp
                            int64_t wpr_dst, cudaStream_t st);
 void launch_rowcount(int dtype, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, void* out, cudaStream_t st);
 void launch_popcount(const uint32_t* B, int64_t m, int64_t wpr, unsigned long long* out, cudaStream_t st);
+// streamed ingestion of host planes: P &= M in place and *count += popcount(M) over `words` words
+void launch_and_count(uint32_t* P, const uint32_t* M, int64_t words, unsigned long long* count, cudaStream_t st);
 void launch_synth_bits(uint64_t seed, int64_t row0, int64_t m, int64_t n, int64_t wpr, const float* Wstar,
                        const float* Hstar, int kstar, float obs_frac, uint32_t* P, uint32_t* M, cudaStream_t st);
 double run_fma_peak(int dtype, int iters, cudaStream_t st, float* scratch);

@@ -552,6 +552,26 @@ void launch_popcount(const uint32_t* B, int64_t m, int64_t wpr, unsigned long lo
   popcount_kernel<<<(unsigned)nb, 256, 0, st>>>(B, m * wpr, out);
 }
 
+__global__ void and_count_kernel(uint32_t* __restrict__ P, const uint32_t* __restrict__ M, int64_t total,
+                                 unsigned long long* count) {
+  unsigned long long c = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const uint32_t mw = M[e];
+    P[e] &= mw;
+    c += __popc(mw);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);           // integer atomics: order-independent
+}
+void launch_and_count(uint32_t* P, const uint32_t* M, int64_t words, unsigned long long* count, cudaStream_t st) {
+  int64_t nb = (words + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  and_count_kernel<<<(unsigned)nb, 256, 0, st>>>(P, M, words, count);
+}
+
 // ------------------------------------------------------------------------------------
 // counter-based synthetic generator (config 4): V ~ Bernoulli(W* H*), mask ~ Bernoulli(obs)
 // keyed on (seed, global row, column) so any row block can be regenerated independently.

@@ -263,6 +263,51 @@ class DeviceProblem:
         self._keep = [P.words, None if M is None else M.words]
         self._call("nbmf_set_data_bits", _ptr(P.words), _ptr(None if M is None else M.words))
 
+    def stream_bits_from_host(self, P: BitMatrix, M: BitMatrix | None = None, n_chunks=8):
+        """Upload HOST bit planes chunk by chunk on a copy stream; the context's stream processes each chunk as it
+        lands (P &= M, mask count, re-tiling for the tensor engine: ``nbmf_ingest_bits_rows``) while the next ones are
+        still crossing PCIe.  Everything is enqueued at once; call ``finish_bits()`` for the mask count."""
+        torch = _torch()
+        if P.shape != (self.m, self.n) or (M is not None and M.shape != P.shape):
+            raise ValueError(f"planes have shapes {P.shape} / {None if M is None else M.shape}, expected {(self.m, self.n)}")
+        if P.is_device or (M is not None and M.is_device):
+            raise ValueError("stream_bits_from_host takes host planes; use set_bits for device planes")
+        host = lambda w: torch.from_numpy(np.ascontiguousarray(w).view(np.int32)) if isinstance(w, np.ndarray) else w
+        Ph, Mh = host(P.words), (None if M is None else host(M.words))
+        wpr = Ph.shape[1]
+        with torch.cuda.device(self.dev):
+            compute = torch.cuda.current_stream(self.dev)
+            Pd = torch.empty((self.m, wpr), dtype=torch.int32, device=self.dev)
+            Md = None if Mh is None else torch.empty((self.m, wpr), dtype=torch.int32, device=self.dev)
+            self._keep = [Pd, Md]
+            self._call("nbmf_ingest_bits_begin", _ptr(Pd), _ptr(Md))
+            copy = torch.cuda.Stream(self.dev)
+            copy.wait_stream(compute)
+            step = max(128, (-(-self.m // max(1, int(n_chunks))) + 127) // 128 * 128)
+            for r0 in range(0, self.m, step):
+                r1 = min(self.m, r0 + step)
+                with torch.cuda.stream(copy):
+                    Pd[r0:r1].copy_(Ph[r0:r1], non_blocking=True)
+                    if Md is not None:
+                        Md[r0:r1].copy_(Mh[r0:r1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                compute.wait_event(ev)
+                self._call("nbmf_ingest_bits_rows", r0, r1)
+            Pd.record_stream(copy)
+            if Md is not None:
+                Md.record_stream(copy)
+        return Ph.numel() * 4 + (0 if Mh is None else Mh.numel() * 4)
+
+    def finish_bits(self) -> float:
+        """Wait for the streamed ingestion; returns count_nonzero(mask) (m * n without a mask)."""
+        cnt = C.c_double(0.0)
+        self._call("nbmf_ingest_bits_end", C.byref(cnt))
+        return float(cnt.value)
+
+    def set_n_obs(self, n_obs):
+        self._call("nbmf_set_n_obs", float(n_obs))
+
     def set_dense(self, Vm, M: BitMatrix | None = None):
         if M is not None:
             M = M if M.is_device else M.to_device(self.dev)

@@ -244,10 +244,26 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     if (r1 - r0) * k + k * n >= PIN_THRESHOLD:
         require_cuda(device)
         pinned = pinned_factor_buffers(r1 - r0, k, n, dtype)
-    # bit-packed host inputs: the H2D copies are asynchronous (pinned memory); the inits are drawn on the
-    # host while they are in flight and the device-side preparation runs afterwards (data.finish())
-    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage)
-    assert (data.m, data.n) == ((r1 - r0) if shard is not None else m, n)
+    # Host bit planes in the internal orientation are STREAMED: row chunks go up on a copy stream and each chunk is
+    # prepared on the compute stream as it lands (P &= M, mask count, re-tiling for the tensor engine) while the next
+    # ones are still crossing PCIe.  Other inputs: asynchronous H2D copies now, device-side preparation in
+    # data.finish().  Either way the inits are drawn on the host while the copies are in flight.
+    streamed = (isinstance(Y, BitMatrix) and not Y.is_device and not transpose
+                and (mask is None or (isinstance(mask, BitMatrix) and not mask.is_device))
+                and (world == 1 or shard is not None))
+    data = prob = None
+    if streamed:
+        prob = DeviceProblem(shape[0], n, k, dtype=dtype, vkind="bits", has_mask=mask is not None, alpha=alpha, beta=beta,
+                             eps=eps, n_obs=None, mask_semantics=mask_semantics, projection=projection_method,
+                             max_iter_cap=max_iter, device=device, engine=engine)
+        try:
+            data_h2d = prob.stream_bits_from_host(Y, mask)
+        except BaseException:
+            prob.close()
+            raise
+    else:
+        data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage)
+        assert (data.m, data.n) == ((r1 - r0) if shard is not None else m, n)
     if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
         W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
     if W_init is None:
@@ -265,29 +281,35 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         (W_up, H_up), result_buffers = pinned
         W_up.numpy()[...] = W_local                        # fp64 -> compute dtype on the host, copies still in flight
         H_up.numpy()[...] = H_init
-    data.finish()
+    def all_ranks_sum(x):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=require_cuda(device))
+        dist.all_reduce(t)
+        return float(t.item())
 
-    n_obs_global = data.n_obs
-    if shard is not None:
-        if world > 1:
-            import torch
-            import torch.distributed as dist
-            t = torch.tensor([data.n_obs], dtype=torch.float64, device=require_cuda(device))
-            dist.all_reduce(t)
-            n_obs_global = float(t.item())
-    elif world > 1:
-        data = PreparedData(r1 - r0, n, data.vkind,
-                            None if data.P is None else data.P.rows(r0, r1),
-                            None if data.M is None else data.M.rows(r0, r1),
-                            None if data.Vm is None else data.Vm[r0:r1], n_obs_global, data.h2d_bytes)
-
-    prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
-                        projection=projection_method, max_iter_cap=max_iter, device=device, n_obs=n_obs_global,
-                        engine=engine)
+    if not streamed:
+        data.finish()
+        data_h2d = data.h2d_bytes
+        n_obs_global = data.n_obs
+        if shard is not None:
+            if world > 1:
+                n_obs_global = all_ranks_sum(data.n_obs)
+        elif world > 1:
+            data = PreparedData(r1 - r0, n, data.vkind,
+                                None if data.P is None else data.P.rows(r0, r1),
+                                None if data.M is None else data.M.rows(r0, r1),
+                                None if data.Vm is None else data.Vm[r0:r1], n_obs_global, data.h2d_bytes)
+        prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
+                            projection=projection_method, max_iter_cap=max_iter, device=device, n_obs=n_obs_global,
+                            engine=engine)
     try:
         if world > 1:
             prob.init_comm()
         prob.set_factors(W_up, H_up, normalize_w=True)
+        if streamed:                                       # count_nonzero(mask) of this shard, _solver.py:151,155
+            n_obs_local = prob.finish_bits()
+            prob.set_n_obs(all_ranks_sum(n_obs_local) if world > 1 else n_obs_local)
         losses_arr, n_iter, converged = prob.fit(max_iter, tol)
         # tail of the reference solver (_solver.py:192-213) on the device: the simplex factor is the internal W in
         # both orientations; it is renormalised (fp64) only when its worst deviation exceeds 1e-9 -- the worst over
@@ -323,7 +345,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
             print(f"Converged at iteration {n_iter - 1}")
     if stats is not None:
         isz = np.dtype(dtype).itemsize                     # factors cross PCIe in the compute dtype
-        stats.update(h2d_bytes=data.h2d_bytes + isz * (W_local.size + H_init.size), converged=converged,
+        stats.update(h2d_bytes=data_h2d + isz * (W_local.size + H_init.size), converged=converged, streamed=streamed,
                      d2h_bytes=isz * (W_loc.size + H.size) + losses_arr.nbytes, world=world, engine=prob.engine)
 
     W_final, H_final = W, H                                # (m x k), (k x n) internal

@@ -135,3 +135,33 @@ def test_solver_tail_on_device_equals_the_host_rule(dtype):
     assert (dev > 1e-9) == (dtype == "float32")                  # fp64 keeps the simplex to ~1e-16: no renormalisation
     assert np.max(np.abs(got_W - want_W)) < 1e-15 and np.array_equal(got_H, want_H)
     assert np.max(np.abs(got_W.sum(axis=1) - 1.0)) < (1e-15 if dtype == "float32" else 1e-12)
+
+
+@pytest.mark.parametrize("m,n,k,masked,engine", [(1000, 1300, 8, True, "tensor"), (1000, 1300, 8, False, "tensor"),
+                                                  (777, 600, 5, True, "simt"), (130, 70, 3, True, "auto"),
+                                                  (2100, 520, 32, True, "tensor")])
+def test_streamed_host_planes_equal_device_planes(m, n, k, masked, engine):
+    """Host bit planes go up in row chunks while the device prepares the chunks that have landed
+    (nbmf_ingest_bits_rows); the fit must be bit-identical to the one on planes that were on the device before."""
+    import torch
+    from nbmf_mm_b200 import nbmf_mm_solver
+    from nbmf_mm_b200.device import DeviceProblem
+    X, mask = _xy(m, n, seed=m + k)
+    P, M = BitMatrix.from_dense(X), (BitMatrix.from_dense(mask) if masked else None)   # P is NOT pre-masked
+    kw = dict(max_iter=6, tol=0.0, random_state=3, dtype="float32", engine=engine)
+    st = {}
+    W1, H1, l1, _, n1 = nbmf_mm_solver(P, k, mask=M, stats=st, **kw)
+    assert st["streamed"] and st["h2d_bytes"] >= P.words.nbytes * (2 if masked else 1)
+    W2, H2, l2, _, n2 = nbmf_mm_solver(P.to_device("cuda"), k, mask=None if M is None else M.to_device("cuda"), stats=st, **kw)
+    assert not st["streamed"]
+    assert n1 == n2 and np.array_equal(W1, W2) and np.array_equal(H1, H2) and l1 == l2
+    # chunk boundaries: many small chunks, planes and count checked directly
+    with DeviceProblem(m, n, k, dtype="float32", has_mask=masked, engine=engine) as prob:
+        prob.stream_bits_from_host(P, M, n_chunks=5)
+        cnt = prob.finish_bits()
+        assert cnt == (np.count_nonzero(mask) if masked else m * n)
+        want = P.words & M.words if masked else P.words
+        assert np.array_equal(prob._keep[0].cpu().numpy().view(np.uint32), want)
+    with pytest.raises(ValueError, match="shapes"):
+        with DeviceProblem(m, n, k, dtype="float32", has_mask=True, engine=engine) as prob:
+            prob.stream_bits_from_host(P, BitMatrix.from_dense(mask[:-1]))
