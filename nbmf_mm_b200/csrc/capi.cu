@@ -123,6 +123,11 @@ struct nbmf_ctx {
   const void* Vm = nullptr;
   bool rowcount_ready = false;
   int64_t ingest_rows = 0;          // rows handed over by nbmf_ingest_bits_rows so far
+  // small problems: kGraphIters MM iterations captured once per fit into a CUDA graph (their ~7 launches per iteration
+  // are what bounds many concurrent small fits); 0 = not built, 1 = ready, -1 = capture not possible on this stream
+  int graph_state = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  long long graph_launches = 0;     // kernel launches per replay (for nbmf_launch_count)
   // loop
   int max_iter = 0;
   double tol = 0.0;
@@ -377,8 +382,16 @@ extern "C" int nbmf_create(const nbmf_config* cfg, void* ws, int64_t ws_bytes, v
   return NBMF_OK;
 }
 
+static void graph_drop(nbmf_ctx* c) {
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->graph_exec = nullptr;
+  c->graph_state = 0;
+}
+
 extern "C" int nbmf_destroy(nbmf_ctx* c) {
   if (!c) return NBMF_OK;
+  cudaStreamSynchronize(c->st);     // the caller frees the workspace next (not a device-wide sync: other streams may be capturing)
+  graph_drop(c);
   if (c->comm && c->owns_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   prof_clear(c->prof_h);
   prof_clear(c->prof_w);
@@ -395,6 +408,7 @@ extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t
   c->P = P;
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
+  graph_drop(c);
   if (c->p.tensor) {   // the tensor kernels read planes re-tiled per TMEM lane (format_factors.cu)
     launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, 0, c->cfg.m, c->at<uint32_t>(c->p.oPc),
                        c->p.strict ? c->at<uint32_t>(c->p.oMc) : nullptr, c->ws + c->p.oPM, c->st);
@@ -414,6 +428,7 @@ extern "C" int nbmf_ingest_bits_begin(nbmf_ctx* c, uint32_t* P, const uint32_t* 
   c->P = P;
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
+  graph_drop(c);
   c->ingest_rows = 0;
   CUDA_TRY(cudaMemsetAsync(ingest_counter(c), 0, sizeof(unsigned long long), c->st));
   return NBMF_OK;
@@ -449,6 +464,7 @@ extern "C" int nbmf_ingest_bits_end(nbmf_ctx* c, double* mask_count_host) {
 extern "C" int nbmf_set_n_obs(nbmf_ctx* c, double n_obs) {
   if (!c || !(n_obs > 0)) return fail(NBMF_ERR_ARG, "nbmf_set_n_obs: bad arguments");
   c->cfg.n_obs = n_obs;
+  graph_drop(c);
   return NBMF_OK;
 }
 extern "C" int nbmf_set_data_dense(nbmf_ctx* c, const void* Vm, const uint32_t* M) {
@@ -458,6 +474,7 @@ extern "C" int nbmf_set_data_dense(nbmf_ctx* c, const void* Vm, const uint32_t* 
   c->Vm = Vm;
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
+  graph_drop(c);
   return NBMF_OK;
 }
 
@@ -647,6 +664,7 @@ extern "C" int nbmf_fit_begin(nbmf_ctx* c, int32_t max_iter, double tol) {
   if (rc) return rc;
   if (max_iter < 1) return fail(NBMF_ERR_ARG, "max_iter must be >= 1");
   if (max_iter > c->cfg.max_iter_cap) return fail(NBMF_ERR_ARG, "max_iter exceeds cfg.max_iter_cap");
+  if (c->max_iter != max_iter || c->tol != tol) graph_drop(c);      // both are baked into the captured finalize launches
   c->max_iter = max_iter;
   c->tol = tol;
   c->enqueued = 0;
@@ -668,16 +686,64 @@ static int enqueue_finalize(nbmf_ctx* c) {
   return NBMF_OK;
 }
 
+static int enqueue_iteration(nbmf_ctx* c) {
+  int rc;
+  // H pass on (W_t, H_t): partial C, D and the log-likelihood of iteration t-1's factors
+  if ((rc = enqueue_h_pass(c, 1))) return rc;
+  if ((rc = enqueue_finalize(c))) return rc;        // loss_{t-1}, stop rule; may set done
+  if ((rc = enqueue_h_epilogue(c))) return rc;      // H_{t+1}
+  return enqueue_w_step(c);                         // W_{t+1} from H_{t+1}
+}
+
+// Small problems are bound by launch overhead (an iteration is ~7 kernels of a few microseconds each, and n_init /
+// grid sweeps run dozens of such fits at once): kGraphIters iterations are captured once per fit and replayed.  The
+// stop rule lives on the device (`done` turns every kernel into a no-op), so a replay never needs the host.
+constexpr int kGraphIters = 4;
+static bool graph_eligible(const nbmf_ctx* c) {
+  return c->graph_state >= 0 && c->world == 1 && !c->profile && (double)c->cfg.m * (double)c->cfg.n <= (double)(1 << 24);
+}
+static int graph_build(nbmf_ctx* c) {
+  if (cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();                              // e.g. the legacy default stream cannot be captured
+    c->graph_state = -1;
+    return NBMF_OK;
+  }
+  const long long before = g_launches.load();
+  int rc = NBMF_OK;
+  for (int i = 0; i < kGraphIters && !rc; ++i) rc = enqueue_iteration(c);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c->st, &g);
+  c->graph_launches = g_launches.load() - before;
+  g_launches -= c->graph_launches;                   // counted per replay instead
+  if (rc || e != cudaSuccess || !g || cudaGraphInstantiate(&c->graph_exec, g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    c->graph_exec = nullptr;
+    c->graph_state = -1;
+  } else {
+    c->graph_state = 1;
+  }
+  if (g) cudaGraphDestroy(g);
+  return rc;
+}
+
 extern "C" int nbmf_fit_enqueue(nbmf_ctx* c, int32_t n_iters) {
   if (!c || c->max_iter < 1) return fail(NBMF_ERR_ARG, "nbmf_fit_begin was not called");
   int rc;
-  for (int i = 0; i < n_iters && c->enqueued < c->max_iter; ++i) {
-    // H pass on (W_t, H_t): partial C, D and the log-likelihood of iteration t-1's factors
-    if ((rc = enqueue_h_pass(c, 1))) return rc;
-    if ((rc = enqueue_finalize(c))) return rc;        // loss_{t-1}, stop rule; may set done
-    if ((rc = enqueue_h_epilogue(c))) return rc;      // H_{t+1}
-    if ((rc = enqueue_w_step(c))) return rc;          // W_{t+1} from H_{t+1}
+  for (int i = 0; i < n_iters && c->enqueued < c->max_iter;) {
+    // the first iteration always runs uncaptured (lazy one-time setup: kernel attributes, row counts)
+    if (graph_eligible(c) && c->enqueued >= 1 && n_iters - i >= kGraphIters && c->max_iter - c->enqueued >= kGraphIters) {
+      if (c->graph_state == 0 && (rc = graph_build(c))) return rc;
+      if (c->graph_state == 1) {
+        CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->st));
+        g_launches += c->graph_launches;
+        c->enqueued += kGraphIters;
+        i += kGraphIters;
+        continue;
+      }
+    }
+    if ((rc = enqueue_iteration(c))) return rc;
     c->enqueued += 1;
+    ++i;
   }
   if (c->enqueued >= c->max_iter && !c->tail_enqueued) {
     // loss of the last iteration: one loss-only pass
@@ -742,8 +808,8 @@ extern "C" int nbmf_fit(nbmf_ctx* c, int32_t max_iter, double tol, double* histo
     n_iter = c->host_state->n_hist;
     if (done || all_enqueued) break;
   }
+  CUDA_TRY(cudaMemcpyAsync(c->host_state, c->state(), sizeof(FitState), cudaMemcpyDeviceToHost, c->st));
   CUDA_TRY(cudaStreamSynchronize(c->st));
-  CUDA_TRY(cudaMemcpy(c->host_state, c->state(), sizeof(FitState), cudaMemcpyDeviceToHost));
   n_iter = c->host_state->n_hist;
   if (n_iter_host) *n_iter_host = n_iter;
   return nbmf_fit_history(c, history_host, n_iter, converged_host);
@@ -806,6 +872,7 @@ extern "C" int nbmf_comm_attach(nbmf_ctx* c, void* comm, int32_t rank, int32_t w
   c->owns_comm = false;
   c->world = world;
   c->rank = rank;
+  graph_drop(c);
   return NBMF_OK;
 }
 extern "C" int nbmf_comm_destroy(void* comm) {
@@ -835,6 +902,7 @@ extern "C" int nbmf_profile_enable(nbmf_ctx* c, int enable) {
   prof_clear(c->prof_h);
   prof_clear(c->prof_w);
   c->profile = enable != 0;
+  graph_drop(c);
   return NBMF_OK;
 }
 extern "C" int nbmf_profile_read(nbmf_ctx* c, double* h_ms, int32_t* h_count, double* w_ms, int32_t* w_count) {

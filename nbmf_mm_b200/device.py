@@ -231,8 +231,7 @@ class DeviceProblem:
     # -- lifetime
     def close(self):
         if self._ctx:
-            _torch().cuda.synchronize(self.dev)
-            self.lib.nbmf_destroy(self._ctx)
+            self.lib.nbmf_destroy(self._ctx)         # synchronises the context's stream
             self._ctx = C.c_void_p(0)
             self._keep = []
             self.workspace = None
