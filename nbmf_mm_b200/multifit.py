@@ -39,7 +39,7 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     ``random_state``, ``W_init``, ``H_init``, ``max_iter``, ``tol`` (defaults: the keyword arguments).  Returns a
     list of ``(W, H, losses, 0.0, n_iter)`` in job order, each identical to
     ``nbmf_mm_solver(Y, mask=mask, orientation=orientation, **job)``.  ``n_streams``: concurrent fits
-    (default: 8 for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own)."""
+    (default: one per hardware queue, 8..32, for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own)."""
     import torch
     if orientation not in _CANON:
         raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
@@ -50,8 +50,13 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     transpose = orientation == "dir-beta"
     data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, dense_storage=dense_storage)
     m, n = data.m, data.n
-    if n_streams is None:
-        n_streams = 8 if m * n <= (1 << 24) else 1
+    if n_streams is None:                                    # one stream per hardware queue, see __init__.py
+        import os
+        try:
+            queues = int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8"))
+        except ValueError:
+            queues = 8
+        n_streams = max(8, min(queues, 32)) if m * n <= (1 << 24) else 1
     n_streams = max(1, min(int(n_streams), len(jobs)))
     # inits are drawn on this thread, in job order: the global NumPy RNG is not thread-safe and every job must see
     # the stream the reference would give it
