@@ -84,6 +84,12 @@ int64_t nbmf_padded_cols(int64_t n);            /* leading dimension of dense V*
 /* dense X (x_dtype F32|F64|U8, leading dim ldx) [+ mask] -> bit planes P (= X!=0 & mask) and M (nullable) */
 int nbmf_pack_bits(const void* x_dev, int x_dtype, int64_t ldx, const void* mask_dev, int mask_dtype, int64_t ldm,
                    int64_t m, int64_t n, uint32_t* p_bits_dev, uint32_t* m_bits_dev, void* stream);
+/* The same for a block of rows, with the value checks of the reference front end done on the device instead of by
+ * NumPy passes over X and the mask (check of _base.py:90-91 "X must be binary", binary mask): *flags_dev (int32,
+ * caller-zeroed, accumulated over calls) gets bit 0 = X holds a value that is not 0 or 1 (probabilistic V), bit 1 = X
+ * holds a value outside [0, 1] or a NaN, bit 2 = the mask holds a value that is not 0 or 1.  No synchronisation. */
+int nbmf_pack_bits_checked(const void* x_dev, int x_dtype, int64_t ldx, const void* mask_dev, int mask_dtype, int64_t ldm,
+                           int64_t m, int64_t n, uint32_t* p_bits_dev, uint32_t* m_bits_dev, int32_t* flags_dev, void* stream);
 /* dense X [+ mask] -> V*mask in out_dtype with leading dimension nbmf_padded_cols(n), zero padded */
 int nbmf_pack_dense(const void* x_dev, int x_dtype, int64_t ldx, const void* mask_dev, int mask_dtype, int64_t ldm,
                     int64_t m, int64_t n, int out_dtype, void* vm_dev, void* stream);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "nbmf_words_per_row": (_I64, [_I64]),
     "nbmf_padded_cols": (_I64, [_I64]),
     "nbmf_pack_bits": (_INT, [_P, _INT, _I64, _P, _INT, _I64, _I64, _I64, _P, _P, _P]),
+    "nbmf_pack_bits_checked": (_INT, [_P, _INT, _I64, _P, _INT, _I64, _I64, _I64, _P, _P, _P, _P]),
     "nbmf_pack_dense": (_INT, [_P, _INT, _I64, _P, _INT, _I64, _I64, _I64, _INT, _P, _P]),
     "nbmf_transpose_bits": (_INT, [_P, _I64, _I64, _P, _P]),
     "nbmf_pack_csr": (_INT, [_P, _P, _P, _INT, _I64, _I64, _P, _P, C.POINTER(_I32), _P]),

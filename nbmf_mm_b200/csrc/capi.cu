@@ -294,7 +294,14 @@ extern "C" int nbmf_variant_info(int dtype, int vkind, int k, int32_t* h_cols, i
 extern "C" int nbmf_pack_bits(const void* x, int xdt, int64_t ldx, const void* mask, int mdt, int64_t ldm, int64_t m,
                               int64_t n, uint32_t* P, uint32_t* M, void* stream) {
   if (!x || !P || m < 1 || n < 1) return fail(NBMF_ERR_ARG, "nbmf_pack_bits: bad arguments");
-  launch_pack_bits(xdt, x, ldx, mask, mdt, ldm, m, n, nbmf_words_per_row(n), P, M, (cudaStream_t)stream);
+  launch_pack_bits(xdt, x, ldx, mask, mdt, ldm, m, n, nbmf_words_per_row(n), P, M, nullptr, (cudaStream_t)stream);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
+}
+extern "C" int nbmf_pack_bits_checked(const void* x, int xdt, int64_t ldx, const void* mask, int mdt, int64_t ldm, int64_t m,
+                                      int64_t n, uint32_t* P, uint32_t* M, int32_t* flags_dev, void* stream) {
+  if (!x || !P || !flags_dev || m < 1 || n < 1) return fail(NBMF_ERR_ARG, "nbmf_pack_bits_checked: bad arguments");
+  launch_pack_bits(xdt, x, ldx, mask, mdt, ldm, m, n, nbmf_words_per_row(n), P, M, flags_dev, (cudaStream_t)stream);
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }

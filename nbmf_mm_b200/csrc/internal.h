@@ -57,7 +57,7 @@ void launch_h_pass_tensor(const HPassArgs& a, const void* Wf, const uint32_t* Pc
 
 // ---- data layer
 void launch_pack_bits(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
-                      int64_t m, int64_t n, int64_t wpr, uint32_t* P, uint32_t* M, cudaStream_t st);
+                      int64_t m, int64_t n, int64_t wpr, uint32_t* P, uint32_t* M, int* flags, cudaStream_t st);
 void launch_pack_dense(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
                        int64_t m, int64_t n, int out_dtype, int64_t ldv, void* Vm, cudaStream_t st);
 void launch_pack_csr(const int64_t* indptr, const int32_t* indices, const void* data, int data_dtype, int64_t m,

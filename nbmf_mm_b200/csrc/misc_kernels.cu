@@ -369,19 +369,29 @@ __device__ __forceinline__ double load_elem(const void* p, int dtype, int64_t id
   return (double)reinterpret_cast<const unsigned char*>(p)[idx];
 }
 
+// flags (optional, accumulated with integer atomics): bit 0 = X holds a value that is not 0 or 1, bit 1 = X holds a
+// value outside [0, 1] or a NaN, bit 2 = the mask holds a value that is not 0 or 1
 __global__ void pack_bits_kernel(const void* __restrict__ X, int xdt, int64_t ldx, const void* __restrict__ mask,
                                  int mdt, int64_t ldm, int64_t m, int64_t n, int64_t wpr, uint32_t* __restrict__ P,
-                                 uint32_t* __restrict__ M) {
+                                 uint32_t* __restrict__ M, int* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t total = m * wpr;
+  int f = 0;
   for (int64_t wi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < total; wi += nwarps) {
     const int64_t row = wi / wpr, w = wi % wpr;
     const int64_t col = w * 32 + lane;
     bool ob = col < n, pb = false;
     if (ob) {
-      if (mask) ob = load_elem(mask, mdt, row * ldm + col) != 0.0;
-      pb = ob && (load_elem(X, xdt, row * ldx + col) != 0.0);
+      if (mask) {
+        const double mv = load_elem(mask, mdt, row * ldm + col);
+        ob = mv != 0.0;
+        if (mv != 0.0 && mv != 1.0) f |= 4;
+      }
+      const double xv = load_elem(X, xdt, row * ldx + col);
+      if (xv != 0.0 && xv != 1.0) f |= 1;
+      if (!(xv >= 0.0 && xv <= 1.0)) f |= 2;
+      pb = ob && (xv != 0.0);
     }
     const uint32_t pw = __ballot_sync(0xffffffffu, pb), mw = __ballot_sync(0xffffffffu, ob);
     if (lane == 0) {
@@ -389,14 +399,19 @@ __global__ void pack_bits_kernel(const void* __restrict__ X, int xdt, int64_t ld
       if (M) M[wi] = mw;
     }
   }
+  if (flags) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, o);
+    if (lane == 0 && f) atomicOr(flags, f);
+  }
 }
 
 void launch_pack_bits(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,
-                      int64_t m, int64_t n, int64_t wpr, uint32_t* P, uint32_t* M, cudaStream_t st) {
+                      int64_t m, int64_t n, int64_t wpr, uint32_t* P, uint32_t* M, int* flags, cudaStream_t st) {
   int64_t nb = (m * wpr + 7) / 8;
   if (nb > 148 * 32) nb = 148 * 32;
   if (nb < 1) nb = 1;
-  pack_bits_kernel<<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, wpr, P, M);
+  pack_bits_kernel<<<(unsigned)nb, 256, 0, st>>>(X, in_dtype, ldx, mask, mask_dtype, ldm, m, n, wpr, P, M, flags);
 }
 
 template <typename Real>

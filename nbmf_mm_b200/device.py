@@ -79,6 +79,44 @@ def pack_bits_device(X_dev, mask_dev=None, want_mask_plane=True):
     return BitMatrix(P, (m, n)), (BitMatrix(M, (m, n)) if M is not None else None)
 
 
+def _packable(a):
+    """Host array in a dtype the packing kernels read (f32, f64, u8); bool is viewed as u8, the rest becomes f64."""
+    a = np.asarray(a)
+    if a.dtype == np.bool_:
+        return a.view(np.uint8)
+    if a.dtype in (np.float32, np.float64, np.uint8):
+        return a
+    return a.astype(np.float64)
+
+
+def pack_host_dense_checked(X, mask, device, chunk_bytes=256 << 20):
+    """Dense HOST X (m x n) [+ dense host mask] -> device bit planes (P = X != 0 & mask, M = mask != 0) and the value
+    flags of ``nbmf_pack_bits_checked``, without a NumPy pass over the data: row chunks are uploaded as they are
+    (fp64 / fp32 / u8) and checked + packed on the device.  At 20 000 x 5 000 the host front end it replaces (range
+    test, binary test, mask test, ``np.packbits``) costs 3.4 s; this costs the PCIe time of the raw arrays."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = require_cuda(device)
+    X = _packable(X)
+    mask = None if mask is None else _packable(mask)
+    m, n = X.shape
+    wpr = words_per_row(n)
+    P = torch.empty((m, wpr), dtype=torch.int32, device=dev)
+    M = None if mask is None else torch.empty((m, wpr), dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    rows = max(1, int(chunk_bytes) // max(1, n * X.dtype.itemsize))
+    with torch.cuda.device(dev):
+        for r0 in range(0, m, rows):
+            r1 = min(m, r0 + rows)
+            Xc = torch.from_numpy(np.ascontiguousarray(X[r0:r1])).to(dev)
+            Mc = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask[r0:r1])).to(dev)
+            _lib.check(lib.nbmf_pack_bits_checked(_ptr(Xc), _elem_code(Xc), n, _ptr(Mc), _elem_code(Mc) if Mc is not None else 0,
+                                                  n, r1 - r0, n, _ptr(P[r0:r1]), _ptr(None if M is None else M[r0:r1]),
+                                                  _ptr(flags), _stream(dev)), "nbmf_pack_bits_checked")
+    h2d = X.nbytes + (0 if mask is None else mask.nbytes)
+    return BitMatrix(P, (m, n)), (None if M is None else BitMatrix(M, (m, n))), int(flags.item()), h2d
+
+
 def pack_dense_device(X_dev, mask_dev, dtype):
     """Dense device matrix (+ mask) -> V*mask in ``dtype`` with the padded leading dimension."""
     torch = _torch()

@@ -32,7 +32,7 @@ def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
 
 def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500, tol=1e-5, eps=1e-8,
                      projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
-                     engine="auto", dense_storage=None, n_streams=None, stats=None):
+                     engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False):
     """Fit ``len(jobs)`` models to the same ``Y`` / ``mask``.
 
     ``jobs``: sequence of dicts with ``n_components`` and optionally ``alpha``, ``beta`` (default 1.2),
@@ -48,7 +48,8 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
         return []
     dev = require_cuda(device)
     transpose = orientation == "dir-beta"
-    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, dense_storage=dense_storage)
+    data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, dense_storage=dense_storage,
+                        check_range=check_range)
     m, n = data.m, data.n
     if n_streams is None:                                    # one stream per hardware queue, see __init__.py
         import os

@@ -14,7 +14,7 @@ import numpy as np
 
 from .bits import BitMatrix
 from .device import (PIN_THRESHOLD, DeviceProblem, pack_bits_device, pack_csr_device, pack_dense_device,
-                     pinned_factor_buffers, require_cuda)
+                     pack_host_dense_checked, pinned_factor_buffers, require_cuda)
 
 _CANON = ("beta-dir", "dir-beta")
 
@@ -56,7 +56,7 @@ def _as_bool_mask(mask, shape):
     return mask
 
 
-def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storage=None) -> PreparedData:
+def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storage=None, check_range=False) -> PreparedData:
     """Validate, orient, pack and upload V and the observation mask.
 
     Binary V goes to two 1-bit planes (packed on the host, so the H2D copy is 32-64x smaller
@@ -112,21 +112,35 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storag
         data = PreparedData(m, n, "bits", P, M, None, float("nan"), h2d, pending=device_part)
         return data if defer else data.finish()
 
-    Y = np.asarray(_densify(Y), dtype=np.float64)
+    Y = np.asarray(_densify(Y))
     if Y.ndim != 2:
         raise ValueError("Y must be 2-D")
-    mk = None if mask is None else _as_bool_mask(mask, Y.shape)
+    if mask is not None:
+        mask = np.asarray(_densify(mask))
+        if mask.shape != Y.shape:
+            raise ValueError(f"mask has shape {mask.shape}, expected {tuple(Y.shape)}")
+    # dense host arrays: the value checks and the packing run on the device, on row chunks of the arrays as they are
+    # (external orientation; dir-beta transposes the packed planes)
+    P, M, flags, h2d = pack_host_dense_checked(Y, mask, dev)
+    if flags & 4:
+        raise ValueError("mask must be binary (0/1 or bool): weighted masks are not supported by the bit-packed path")
+    if check_range and (flags & 2):
+        raise ValueError("X must be binary")                          # _base.py:90-91
+    if not (flags & 1):
+        if transpose:
+            P = P.transpose()
+            M = None if M is None else M.transpose()
+        m, n = P.shape
+        n_obs = float(m) * float(n) if M is None else float(M.count())
+        return PreparedData(m, n, "bits", P, M, None, n_obs, h2d)
+    del P, M
+    Y = np.asarray(Y, dtype=np.float64)
+    mk = None if mask is None else (mask != 0)
     if transpose:
         Y = Y.T
         mk = None if mk is None else mk.T
     m, n = Y.shape
     n_obs = float(Y.size) if mk is None else float(np.count_nonzero(mk))
-    if np.all((Y == 0) | (Y == 1)):
-        pos = (Y != 0) if mk is None else ((Y != 0) & mk)
-        P = BitMatrix.from_dense(pos)
-        M = None if mk is None else BitMatrix.from_dense(mk)
-        h2d = P.words.nbytes + (0 if M is None else M.words.nbytes)
-        return PreparedData(m, n, "bits", P.to_device(dev), None if M is None else M.to_device(dev), None, n_obs, h2d)
     # probabilistic V: dense V*mask in the compute dtype + mask bits
     Yd = torch.from_numpy(np.ascontiguousarray(Y)).to(dev)
     h2d = Y.nbytes
@@ -193,7 +207,7 @@ def _row_shard(m, rank, world):
 def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2, W_init=None, H_init=None,
                    mask=None, random_state=None, verbose=0, orientation="beta-dir", eps=1e-8, *,
                    projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
-                   distributed=False, shard=None, stats=None, engine="auto", dense_storage=None):
+                   distributed=False, shard=None, stats=None, engine="auto", dense_storage=None, check_range=False):
     """NBMF-MM solver, drop-in for ``nbmf_mm._solver.nbmf_mm_solver`` (``_solver.py:61-216``).
 
     Returns ``(W (m x k), H (k x n), losses, 0.0, n_iter)`` exactly as the reference does
@@ -206,7 +220,9 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     problem in internal orientation; the returned W is the local block, H is global),
     ``engine`` ("auto" | "simt" | "tensor": packed-FFMA2 CUDA-core kernels or the tcgen05/TMEM
     split-precision kernels; the tensor engine needs float32, binary V, K <= 32), ``dense_storage`` ("float16":
-    probabilistic V is stored as fp16 on the device, float32 arithmetic; default = the compute dtype).
+    probabilistic V is stored as fp16 on the device, float32 arithmetic; default = the compute dtype),
+    ``check_range`` (raise the estimator's ``ValueError("X must be binary")``, ``_base.py:90-91``, when a dense ``Y``
+    holds a value outside [0, 1]: the test runs on the device, in the pass that packs ``Y``).
     """
     if orientation not in _CANON:
         raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
@@ -262,7 +278,8 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
             prob.close()
             raise
     else:
-        data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage)
+        data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage,
+                            check_range=check_range)
         assert (data.m, data.n) == ((r1 - r0) if shard is not None else m, n)
     if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
         W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T

@@ -165,3 +165,49 @@ def test_streamed_host_planes_equal_device_planes(m, n, k, masked, engine):
     with pytest.raises(ValueError, match="shapes"):
         with DeviceProblem(m, n, k, dtype="float32", has_mask=True, engine=engine) as prob:
             prob.stream_bits_from_host(P, BitMatrix.from_dense(mask[:-1]))
+
+
+@pytest.mark.parametrize("xdt,mdt", [(np.float64, np.float64), (np.float32, np.bool_), (np.uint8, np.uint8),
+                                     (np.int64, np.float32), (np.bool_, None)])
+def test_dense_front_end_on_the_device_is_bit_exact(xdt, mdt):
+    """Dense host X / mask are uploaded in row chunks as they are and checked + packed on the device
+    (nbmf_pack_bits_checked): same planes as the host packing, same flags as the NumPy tests it replaces."""
+    from nbmf_mm_b200.device import pack_host_dense_checked
+    X, mask = _xy(301, 1100, seed=5)
+    Xa = X.astype(xdt)
+    Ma = None if mdt is None else mask.astype(mdt)
+    P, M, flags, h2d = pack_host_dense_checked(Xa, Ma, None, chunk_bytes=64 * 1100 * Xa.dtype.itemsize)   # 5 chunks
+    want_p = BitMatrix.from_dense((X != 0) & ((mask != 0) if Ma is not None else True))
+    assert flags == 0 and h2d == Xa.nbytes + (0 if Ma is None else Ma.nbytes)
+    assert np.array_equal(P.words.cpu().numpy().view(np.uint32), want_p.words)
+    if Ma is not None:
+        assert np.array_equal(M.words.cpu().numpy().view(np.uint32), BitMatrix.from_dense(mask).words)
+    else:
+        assert M is None
+    # flags: probabilistic values, out-of-range values, NaN, weighted mask
+    Xp = X.copy(); Xp[7, 3] = 0.25
+    assert pack_host_dense_checked(Xp, mask, None)[2] == 1
+    Xo = X.copy(); Xo[300, 1099] = 1.5
+    assert pack_host_dense_checked(Xo, None, None)[2] == 3
+    Xn = X.copy(); Xn[0, 0] = np.nan
+    assert pack_host_dense_checked(Xn, None, None)[2] & 2
+    assert pack_host_dense_checked(X, mask * 0.5, None)[2] == 4
+
+
+def test_dense_front_end_errors_and_large_x_range_check():
+    from nbmf_mm_b200 import nbmf_mm_solver
+    X, mask = _xy(60, 90, seed=2)
+    with pytest.raises(ValueError, match="mask must be binary"):
+        nbmf_mm_solver(X, 3, max_iter=2, mask=mask * 0.5)
+    with pytest.raises(ValueError, match="mask has shape"):
+        nbmf_mm_solver(X, 3, max_iter=2, mask=mask[:-1])
+    with pytest.raises(ValueError, match="X must be binary"):
+        nbmf_mm_solver(X * 2.0, 3, max_iter=2, check_range=True)
+    # a large X takes the device-side range check of the estimator (no NumPy passes over X)
+    big = np.zeros((2100, 2048)); big[5, 7] = 1.0; big[2099, 2047] = 1.0
+    NBMF(n_components=2, max_iter=2, dtype="float32").fit(big)
+    big[1000, 1000] = -0.5
+    with pytest.raises(ValueError, match="X must be binary"):
+        NBMF(n_components=2, max_iter=2, dtype="float32").fit(big)
+    with pytest.raises(ValueError, match="X must be binary"):            # reference order: X before orientation
+        NBMF(n_components=2, max_iter=2, orientation="nope").fit(big)
