@@ -281,23 +281,28 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage,
                             check_range=check_range)
         assert (data.m, data.n) == ((r1 - r0) if shard is not None else m, n)
-    if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
-        W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
-    if W_init is None:
-        W_init = np.random.uniform(0.1, 0.9, (m, k))      # W first, then H: _solver.py:126-129
-    if H_init is None:
-        H_init = np.random.uniform(0.1, 0.9, (k, n))
-    W_init = np.asarray(W_init, dtype=np.float64)
-    H_init = np.asarray(H_init, dtype=np.float64)
-    if tuple(W_init.shape) != (m, k) or tuple(H_init.shape) != (k, n):
-        raise ValueError(f"W_init / H_init have shapes {W_init.shape} / {H_init.shape}, expected {(m, k)} / {(k, n)}")
+    try:
+        if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
+            W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
+        if W_init is None:
+            W_init = np.random.uniform(0.1, 0.9, (m, k))      # W first, then H: _solver.py:126-129
+        if H_init is None:
+            H_init = np.random.uniform(0.1, 0.9, (k, n))
+        W_init = np.asarray(W_init, dtype=np.float64)
+        H_init = np.asarray(H_init, dtype=np.float64)
+        if tuple(W_init.shape) != (m, k) or tuple(H_init.shape) != (k, n):
+            raise ValueError(f"W_init / H_init have shapes {W_init.shape} / {H_init.shape}, expected {(m, k)} / {(k, n)}")
+        W_local = W_init[r0:r1]
+        W_up, H_up, result_buffers = W_local, H_init, None
+        if pinned is not None:
+            (W_up, H_up), result_buffers = pinned
+            W_up.numpy()[...] = W_local                        # fp64 -> compute dtype on the host, copies still in flight
+            H_up.numpy()[...] = H_init
+    except BaseException:
+        if prob is not None:                                   # streamed upload in flight: release the context
+            prob.close()
+        raise
 
-    W_local = W_init[r0:r1]
-    W_up, H_up, result_buffers = W_local, H_init, None
-    if pinned is not None:
-        (W_up, H_up), result_buffers = pinned
-        W_up.numpy()[...] = W_local                        # fp64 -> compute dtype on the host, copies still in flight
-        H_up.numpy()[...] = H_init
     def all_ranks_sum(x):
         import torch
         import torch.distributed as dist
