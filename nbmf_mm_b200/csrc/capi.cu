@@ -571,7 +571,15 @@ static void prof_mark(nbmf_ctx* c, std::vector<cudaEvent_t>& v) {
   v.push_back(e);
 }
 
-static int enqueue_h_pass(nbmf_ctx* c, int compute_cd) {
+static FinalizeArgs finalize_args(nbmf_ctx* c) {
+  const Plan& p = c->p;
+  return FinalizeArgs{c->state(), c->at<double>(p.oPrior), p.n_prior, c->cfg.alpha, c->cfg.beta, c->cfg.n_obs, c->tol,
+                      c->max_iter, c->at<double>(p.oHist)};
+}
+
+// with_finalize: the loss / stop rule of the fit loop follows this pass.  On one GPU it rides in the reduction kernel;
+// with row shards the log-likelihood is all-reduced first and finalize is its own launch.
+static int enqueue_h_pass(nbmf_ctx* c, int compute_cd, bool with_finalize = false) {
   const Plan& p = c->p;
   HPassArgs a;
   a.W = c->W(); a.H = c->H(); a.P = c->P; a.M = c->M; a.Vm = c->Vm; a.ldv = p.ldh;
@@ -587,10 +595,17 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd) {
     p.pl.h_launch(a, p.h_nsplit, c->st);
   prof_mark(c, c->prof_h);
   const int64_t count = compute_cd ? (int64_t)2 * p.pl.kp * p.ldh : 0;
+  const bool fused = with_finalize && c->world == 1;
+  FinalizeArgs fin = finalize_args(c);
+  if (!fused) fin.state = nullptr;
   launch_h_reduce(c->cfg.dtype, c->ws + p.oCDpart, p.h_nsplit, count, c->ws + p.oCDsum, c->at<double>(p.oLLpart),
-                  (int64_t)p.h_nsplit * p.h_ncb, c->at<double>(p.oLLsum), c->state(), c->st);
+                  (int64_t)p.h_nsplit * p.h_ncb, c->at<double>(p.oLLsum), c->state(), fin, c->st);
   CHECK_LAUNCH(2);
-  return allreduce(c, compute_cd != 0);
+  int rc = allreduce(c, compute_cd != 0);
+  if (rc || !with_finalize || fused) return rc;
+  launch_finalize(finalize_args(c), c->at<double>(p.oLLsum), c->st);
+  CHECK_LAUNCH(1);
+  return NBMF_OK;
 }
 
 static int enqueue_h_epilogue(nbmf_ctx* c) {
@@ -685,19 +700,11 @@ extern "C" int nbmf_fit_begin(nbmf_ctx* c, int32_t max_iter, double tol) {
   return NBMF_OK;
 }
 
-static int enqueue_finalize(nbmf_ctx* c) {
-  const Plan& p = c->p;
-  launch_finalize(c->state(), c->at<double>(p.oLLsum), c->at<double>(p.oPrior), p.n_prior, c->cfg.alpha, c->cfg.beta,
-                  c->cfg.n_obs, c->tol, c->max_iter, c->at<double>(p.oHist), c->st);
-  CHECK_LAUNCH(1);
-  return NBMF_OK;
-}
 
 static int enqueue_iteration(nbmf_ctx* c) {
   int rc;
   // H pass on (W_t, H_t): partial C, D and the log-likelihood of iteration t-1's factors
-  if ((rc = enqueue_h_pass(c, 1))) return rc;
-  if ((rc = enqueue_finalize(c))) return rc;        // loss_{t-1}, stop rule; may set done
+  if ((rc = enqueue_h_pass(c, 1, true))) return rc;  // + loss_{t-1}, stop rule; may set done
   if ((rc = enqueue_h_epilogue(c))) return rc;      // H_{t+1}
   return enqueue_w_step(c);                         // W_{t+1} from H_{t+1}
 }
@@ -754,8 +761,7 @@ extern "C" int nbmf_fit_enqueue(nbmf_ctx* c, int32_t n_iters) {
   }
   if (c->enqueued >= c->max_iter && !c->tail_enqueued) {
     // loss of the last iteration: one loss-only pass
-    if ((rc = enqueue_h_pass(c, 0))) return rc;
-    if ((rc = enqueue_finalize(c))) return rc;
+    if ((rc = enqueue_h_pass(c, 0, true))) return rc;
     c->tail_enqueued = true;
   }
   return NBMF_OK;

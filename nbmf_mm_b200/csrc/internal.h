@@ -19,6 +19,16 @@ struct FitState {
   double prior_b;      // sum log((1 - H) + eps) of the current H
 };
 
+// ---- loss + stop rule of one iteration (finalize_body in misc_kernels.cu); state == nullptr: not requested
+struct FinalizeArgs {
+  FitState* state;
+  const double* prior_part;
+  int n_prior_part;
+  double alpha, beta, n_obs, tol;
+  int max_iter;
+  double* history;
+};
+
 // ---- variant lookup: dtype 0 = f32, 1 = f64; returns false if K is unsupported
 bool lookup_pass(int dtype, int dense, int strict, int k, PassLaunch* out);
 
@@ -28,10 +38,9 @@ void launch_init_factors(int dtype, const void* W_in, const void* H_in, int64_t 
 void launch_export_factors(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, int kp,
                            int64_t ldh, void* W_out, void* H_out, cudaStream_t st);
 void launch_h_reduce(int dtype, const void* CDpart, int nsplit, int64_t count, void* CDsum,
-                     const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, cudaStream_t st);
-void launch_finalize(FitState* state, const double* LLsum, const double* prior_part, int n_prior_part,
-                     double alpha, double beta, double n_obs, double tol, int max_iter, double* history,
+                     const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, const FinalizeArgs& fin,
                      cudaStream_t st);
+void launch_finalize(const FinalizeArgs& f, const double* LLsum, cudaStream_t st);
 int  h_epilogue_blocks(int64_t n, int kp);
 void launch_h_epilogue(int dtype, const void* CDsum, int64_t n, int k, int kp, int64_t ldh, double alpha,
                        double beta, double eps, void* H, void* Ht, double* prior_part, const FitState* state,

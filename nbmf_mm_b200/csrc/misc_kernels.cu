@@ -77,10 +77,46 @@ void launch_export_factors(int dtype, const void* W, const void* H, int64_t m, i
 // ------------------------------------------------------------------------------------
 // deterministic reduction of the row-split partials of the H pass (fixed split order)
 // ------------------------------------------------------------------------------------
+// loss of the previous iteration + stop rule, on the device (_solver.py:158-175), executed by one full warp.
+// The H pass of iteration `it` sees (W_it, H_it), i.e. the factors PRODUCED by iteration
+// it-1, so its log-likelihood is the loss of iteration it-1.
+__device__ __forceinline__ void finalize_body(const FinalizeArgs& f, double ll) {
+  FitState* state = f.state;
+  double pa = 0.0, pb = 0.0;
+  for (int i = threadIdx.x; i < f.n_prior_part; i += 32) {
+    pa += f.prior_part[2 * i];
+    pb += f.prior_part[2 * i + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pa += __shfl_xor_sync(0xffffffffu, pa, o);
+    pb += __shfl_xor_sync(0xffffffffu, pb, o);
+  }
+  if (threadIdx.x != 0) return;
+  const int it = state->it;
+  int done = 0;
+  if (it >= 1) {
+    const double loss = -(ll + (f.alpha - 1.0) * pa + (f.beta - 1.0) * pb) / f.n_obs;
+    f.history[it - 1] = loss;
+    state->n_hist = it;
+    if (it >= 2) {
+      const double prev = state->prev_loss;
+      const double rel = fabs(prev - loss) / fabs(prev);
+      if (rel < f.tol) { done = 1; state->converged = 1; }
+    }
+    state->prev_loss = loss;
+    if (it >= f.max_iter) done = 1;
+  }
+  state->prior_a = pa;
+  state->prior_b = pb;
+  if (done) state->done = 1;
+  else state->it = it + 1;
+}
+
 template <typename Real>
 __global__ void h_reduce_kernel(const Real* __restrict__ part, int nsplit, int64_t count, Real* __restrict__ sum,
                                 const double* __restrict__ LLpart, int64_t n_ll, double* __restrict__ LLsum,
-                                const FitState* __restrict__ state) {
+                                const FitState* __restrict__ state, const FinalizeArgs fin) {
   if (state->done) return;
   if (blockIdx.x == gridDim.x - 1) {            // last block: the log-likelihood partials
     if (threadIdx.x < 32) {
@@ -89,6 +125,9 @@ __global__ void h_reduce_kernel(const Real* __restrict__ part, int nsplit, int64
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (threadIdx.x == 0) LLsum[0] = v;
+      // single GPU: the loss and the stop rule ride along (one launch less per iteration).  A `done` set here may be
+      // seen by blocks of this launch that have not started yet; they then skip a reduction nobody reads.
+      if (fin.state) finalize_body(fin, v);
     }
     return;
   }
@@ -101,61 +140,28 @@ __global__ void h_reduce_kernel(const Real* __restrict__ part, int nsplit, int64
 }
 
 void launch_h_reduce(int dtype, const void* CDpart, int nsplit, int64_t count, void* CDsum,
-                     const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, cudaStream_t st) {
+                     const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, const FinalizeArgs& fin,
+                     cudaStream_t st) {
   int64_t nb = (count + 1023) / 1024;
   if (nb > 148 * 8) nb = 148 * 8;
   if (nb < 1) nb = 1;
   const unsigned grid = (unsigned)nb + 1;
   if (dtype == 0)
-    h_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)CDpart, nsplit, count, (float*)CDsum, LLpart, n_ll, LLsum, state);
+    h_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)CDpart, nsplit, count, (float*)CDsum, LLpart, n_ll, LLsum, state, fin);
   else
-    h_reduce_kernel<double><<<grid, 256, 0, st>>>((const double*)CDpart, nsplit, count, (double*)CDsum, LLpart, n_ll, LLsum, state);
+    h_reduce_kernel<double><<<grid, 256, 0, st>>>((const double*)CDpart, nsplit, count, (double*)CDsum, LLpart, n_ll, LLsum, state, fin);
 }
 
 // ------------------------------------------------------------------------------------
-// loss of the previous iteration + stop rule, on the device (_solver.py:158-175).
-// The H pass of iteration `it` sees (W_it, H_it), i.e. the factors PRODUCED by iteration
-// it-1, so its log-likelihood is the loss of iteration it-1.
+// stand-alone finalize (multi-GPU: the log-likelihood is all-reduced between h_reduce and this launch)
 // ------------------------------------------------------------------------------------
-__global__ void finalize_kernel(FitState* state, const double* __restrict__ LLsum,
-                                const double* __restrict__ prior_part, int n_prior_part, double alpha, double beta,
-                                double n_obs, double tol, int max_iter, double* __restrict__ history) {
-  if (state->done) return;
-  double pa = 0.0, pb = 0.0;
-  for (int i = threadIdx.x; i < n_prior_part; i += 32) {
-    pa += prior_part[2 * i];
-    pb += prior_part[2 * i + 1];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    pa += __shfl_xor_sync(0xffffffffu, pa, o);
-    pb += __shfl_xor_sync(0xffffffffu, pb, o);
-  }
-  if (threadIdx.x != 0) return;
-  const int it = state->it;
-  int done = 0;
-  if (it >= 1) {
-    const double loss = -(LLsum[0] + (alpha - 1.0) * pa + (beta - 1.0) * pb) / n_obs;
-    history[it - 1] = loss;
-    state->n_hist = it;
-    if (it >= 2) {
-      const double prev = state->prev_loss;
-      const double rel = fabs(prev - loss) / fabs(prev);
-      if (rel < tol) { done = 1; state->converged = 1; }
-    }
-    state->prev_loss = loss;
-    if (it >= max_iter) done = 1;
-  }
-  state->prior_a = pa;
-  state->prior_b = pb;
-  if (done) state->done = 1;
-  else state->it = it + 1;
+__global__ void finalize_kernel(const FinalizeArgs f, const double* __restrict__ LLsum) {
+  if (f.state->done) return;
+  finalize_body(f, LLsum[0]);
 }
 
-void launch_finalize(FitState* state, const double* LLsum, const double* prior_part, int n_prior_part,
-                     double alpha, double beta, double n_obs, double tol, int max_iter, double* history,
-                     cudaStream_t st) {
-  finalize_kernel<<<1, 32, 0, st>>>(state, LLsum, prior_part, n_prior_part, alpha, beta, n_obs, tol, max_iter, history);
+void launch_finalize(const FinalizeArgs& f, const double* LLsum, cudaStream_t st) {
+  finalize_kernel<<<1, 32, 0, st>>>(f, LLsum);
 }
 
 // ------------------------------------------------------------------------------------
