@@ -112,3 +112,43 @@ def test_import_shim_exposes_reference_names():
     from nbmf_mm import NBMF as A, NBMFMM as B, nbmf_mm_solver  # noqa: F401
     from nbmf_mm._utils import generate_synthetic_binary_data as g  # noqa: F401
     assert A is B and set(nbmf_mm.__all__) == {"NBMFMM", "NBMF", "nbmf_mm_solver"}
+
+
+def test_dense_inputs_are_uploaded_in_a_dtype_the_packing_kernels_read():
+    """Host side of the device front end (nbmf_pack_bits_checked): f32 / f64 / u8 go up as they are, bool is a u8 view
+    (no copy), everything else becomes f64."""
+    from nbmf_mm_b200.device import _packable
+    a = np.arange(6).reshape(2, 3)
+    for dt in (np.float32, np.float64, np.uint8):
+        x = a.astype(dt)
+        assert _packable(x) is x
+    b = a.astype(bool)
+    v = _packable(b)
+    assert v.dtype == np.uint8 and np.shares_memory(v, b)
+    for dt in (np.int64, np.int32, np.float16):
+        assert _packable(a.astype(dt)).dtype == np.float64
+    assert _packable([[0, 1], [1, 0]]).dtype == np.float64
+
+
+def test_package_import_asks_for_more_hardware_queues_without_overriding_the_user():
+    """nbmf_mm_multifit runs one fit per stream; the package only sets a DEFAULT for CUDA_DEVICE_MAX_CONNECTIONS."""
+    import os, subprocess, sys as _sys
+    code = "import os, nbmf_mm_b200; print(os.environ['CUDA_DEVICE_MAX_CONNECTIONS'])"
+    root = str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}
+    env["PYTHONPATH"] = root
+    assert subprocess.run([_sys.executable, "-c", code], env=env, capture_output=True, text=True).stdout.strip() == "32"
+    env["CUDA_DEVICE_MAX_CONNECTIONS"] = "4"
+    assert subprocess.run([_sys.executable, "-c", code], env=env, capture_output=True, text=True).stdout.strip() == "4"
+
+
+def test_solver_rejects_bad_shapes_before_touching_the_device():
+    from nbmf_mm_b200 import nbmf_mm_solver
+    with pytest.raises(ValueError, match="2-D"):
+        nbmf_mm_solver(np.zeros(5), 2)
+    with pytest.raises(ValueError, match="Unknown orientation"):
+        nbmf_mm_solver(np.zeros((4, 4)), 2, orientation="Dir Beta")     # the solver takes canonical names only
+    with pytest.raises(UnboundLocalError):
+        nbmf_mm_solver(np.zeros((4, 4)), 2, max_iter=0)
+    with pytest.raises(ValueError, match="shard"):
+        nbmf_mm_solver(np.zeros((4, 4)), 2, shard=(0, 8))
