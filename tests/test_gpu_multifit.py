@@ -44,3 +44,22 @@ def test_n_init_uses_one_upload_and_keeps_the_best_restart():
     assert est.transfer_stats_["n_streams"] >= 1
     # restart 0 of an n_init run is the n_init=1 run with the same random_state
     assert np.array_equal(singles[0].W_, NBMF(**kw).fit(X, mask=mask).W_)
+
+
+def test_graph_replay_on_the_tensor_engine_equals_per_kernel_launches():
+    """Mid-size float32 problems take the tcgen05 engine AND (on the fits' own streams) the CUDA-graph replay of four
+    iterations per launch; the sequential solver calls run on the default stream, kernel by kernel.  Same bits,
+    same n_iter -- including fits that the device-side stop rule ends in the middle of a replayed graph."""
+    X, mask = _data(700, 640, seed=5)
+    jobs = [dict(n_components=k, random_state=s, tol=t, max_iter=mi)
+            for k, s, t, mi in [(8, 0, 0.0, 23), (8, 1, 3e-4, 60), (16, 2, 1e-3, 60), (32, 3, 0.0, 9), (5, 4, 5e-4, 41)]]
+    stats = {}
+    got = nbmf_mm_multifit(X, jobs, mask=mask, dtype="float32", n_streams=3, stats=stats)
+    assert stats["engine"] == "tensor"
+    stopped_early = 0
+    for j, out in zip(jobs, got):
+        W, H, losses, _, n_iter = nbmf_mm_solver(X, mask=mask, dtype="float32", **j)
+        assert n_iter == out[4] and np.array_equal(losses, out[2])
+        assert np.array_equal(W, out[0]) and np.array_equal(H, out[1])
+        stopped_early += n_iter < j["max_iter"]
+    assert stopped_early >= 1
