@@ -158,6 +158,16 @@ int nbmf_fit_begin(nbmf_ctx* ctx, int32_t max_iter, double tol);
 int nbmf_fit_enqueue(nbmf_ctx* ctx, int32_t n_iters);
 /* non-blocking unless wait != 0: fetch (done, n_iter) of the work enqueued so far */
 int nbmf_fit_poll(nbmf_ctx* ctx, int wait, int32_t* done_host, int32_t* n_iter_host);
+/* Batched small fits (n_init restarts, repeated fits of one data set with equal hyper-parameters): n contexts of
+ * identical configuration and data planes, workspaces at a uniform byte stride inside one allocation (the leader's
+ * first), each with its own factors (nbmf_set_factors) and nbmf_fit_begin.  After nbmf_batch_bind(leader, n, stride)
+ * the leader's nbmf_fit_enqueue advances all n fits with one launch per kernel (the Python loop of solver calls in
+ * examples/reproduce_magron2022.py:87-117 / README.md:133,144 becomes 5 launches per iteration for the whole batch);
+ * every fit keeps its own loss history, stop rule and n_iter on the device.  nbmf_batch_poll synchronises the stream
+ * and reports whether every fit has stopped and how many losses each has recorded; results are then read from each
+ * context as usual.  SIMT engine, single GPU. */
+int nbmf_batch_bind(nbmf_ctx* leader, int32_t n, int64_t stride_bytes);
+int nbmf_batch_poll(nbmf_ctx* leader, int32_t* all_done_host, int32_t* n_iter_host);
 int nbmf_fit_history(nbmf_ctx* ctx, double* history_host, int32_t count, int32_t* converged_host);
 
 /* ---- transform (replaces the 50 fixed-H W steps of NBMFMM.transform, _base.py:178-198) ----

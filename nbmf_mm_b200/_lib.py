@@ -64,6 +64,8 @@ SIGNATURES = {
     "nbmf_objective": (_INT, [_P, C.POINTER(_DBL)]),
     "nbmf_fit": (_INT, [_P, _I32, _DBL, C.POINTER(_DBL), C.POINTER(_I32), C.POINTER(_I32)]),
     "nbmf_fit_begin": (_INT, [_P, _I32, _DBL]),
+    "nbmf_batch_bind": (_INT, [_P, _I32, _I64]),
+    "nbmf_batch_poll": (_INT, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
     "nbmf_fit_enqueue": (_INT, [_P, _I32]),
     "nbmf_fit_poll": (_INT, [_P, _INT, C.POINTER(_I32), C.POINTER(_I32)]),
     "nbmf_fit_history": (_INT, [_P, C.POINTER(_DBL), _I32, C.POINTER(_I32)]),

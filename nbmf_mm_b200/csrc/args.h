@@ -26,6 +26,11 @@ struct HPassArgs {
   double eps;
   const int* done;   // device flag: 1 = converged, every kernel becomes a no-op
   int compute_cd;    // 0 = loss-only pass
+  // batched small fits (SIMT engine): gridDim.z fits whose workspaces lie batch_stride bytes apart advance with one
+  // launch; every workspace pointer above (W, H, CD, LL, done) is shifted by blockIdx.z * batch_stride, the data
+  // planes are shared
+  int batch_n = 1;
+  int64_t batch_stride = 0;
 };
 
 struct WPassArgs {
@@ -41,6 +46,8 @@ struct WPassArgs {
   void* Q;           // [nsplit][m]     partial sum_j q
   double eps;
   const int* done;
+  int batch_n = 1;           // see HPassArgs: W, Ht, G, Q, done are shifted per fit
+  int64_t batch_stride = 0;
 };
 
 struct PassLaunch {

@@ -128,6 +128,10 @@ struct nbmf_ctx {
   int graph_state = 0;
   cudaGraphExec_t graph_exec = nullptr;
   long long graph_launches = 0;     // kernel launches per replay (for nbmf_launch_count)
+  // batched small fits: this context leads batch_n contexts of identical configuration whose workspaces lie
+  // batch_stride bytes apart; every launch of its fit loop covers all of them (gridDim.z), nbmf_batch_bind
+  int batch_n = 1;
+  int64_t batch_stride = 0;
   // loop
   int max_iter = 0;
   double tol = 0.0;
@@ -587,6 +591,7 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd, bool with_finalize = fals
   a.rows_per_split = p.h_rows_per_split;
   a.CD = c->ws + p.oCDpart; a.LL = c->at<double>(p.oLLpart);
   a.eps = c->cfg.eps; a.done = &c->state()->done; a.compute_cd = compute_cd;
+  a.batch_n = c->batch_n; a.batch_stride = c->batch_stride;
   prof_mark(c, c->prof_h);
   if (p.tensor)
     launch_h_pass_tensor(a, c->ws + p.oWf, c->at<uint32_t>(p.oPc), p.strict ? c->at<uint32_t>(p.oMc) : nullptr, p.mpad / 32,
@@ -599,7 +604,7 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd, bool with_finalize = fals
   FinalizeArgs fin = finalize_args(c);
   if (!fused) fin.state = nullptr;
   launch_h_reduce(c->cfg.dtype, c->ws + p.oCDpart, p.h_nsplit, count, c->ws + p.oCDsum, c->at<double>(p.oLLpart),
-                  (int64_t)p.h_nsplit * p.h_ncb, c->at<double>(p.oLLsum), c->state(), fin, c->st);
+                  (int64_t)p.h_nsplit * p.h_ncb, c->at<double>(p.oLLsum), c->state(), fin, c->st, c->batch_n, c->batch_stride);
   CHECK_LAUNCH(2);
   int rc = allreduce(c, compute_cd != 0);
   if (rc || !with_finalize || fused) return rc;
@@ -611,7 +616,7 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd, bool with_finalize = fals
 static int enqueue_h_epilogue(nbmf_ctx* c) {
   const Plan& p = c->p;
   launch_h_epilogue(c->cfg.dtype, c->ws + p.oCDsum, c->cfg.n, c->cfg.k, p.pl.kp, p.ldh, c->cfg.alpha, c->cfg.beta,
-                    c->cfg.eps, c->H(), c->Ht(), c->at<double>(p.oPrior), c->state(), c->st);
+                    c->cfg.eps, c->H(), c->Ht(), c->at<double>(p.oPrior), c->state(), c->st, c->batch_n, c->batch_stride);
   CHECK_LAUNCH(1);
   return format_h(c, true);
 }
@@ -628,6 +633,7 @@ static int enqueue_w_step(nbmf_ctx* c) {
   a.m = c->cfg.m; a.n = c->cfg.n; a.ldh = p.ldh; a.wpr = p.wpr;
   a.cols_per_split = p.w_cols_per_split;
   a.G = c->ws + p.oG; a.Q = c->ws + p.oQ; a.eps = c->cfg.eps; a.done = &c->state()->done;
+  a.batch_n = c->batch_n; a.batch_stride = c->batch_stride;
   prof_mark(c, c->prof_w);
   if (p.tensor)
     launch_w_pass_tensor(a, c->ws + p.oHf, c->ws + p.oPM, p.w_nsplit, c->st);
@@ -636,7 +642,7 @@ static int enqueue_w_step(nbmf_ctx* c) {
   prof_mark(c, c->prof_w);
   const void* rowcount = (c->cfg.projection == NBMF_PROJ_DUCHI && c->M) ? (const void*)(c->ws + p.oRowcount) : nullptr;
   launch_w_epilogue(c->cfg.dtype, c->ws + p.oG, c->ws + p.oQ, p.w_nsplit, c->cfg.m, c->cfg.n, c->cfg.k, p.pl.kp,
-                    c->cfg.projection, rowcount, c->W(), c->state(), c->st);
+                    c->cfg.projection, rowcount, c->W(), c->state(), c->st, c->batch_n, c->batch_stride);
   CHECK_LAUNCH(2);
   return format_w(c, true);
 }
@@ -787,6 +793,40 @@ extern "C" int nbmf_fit_poll(nbmf_ctx* c, int wait, int32_t* done_host, int32_t*
   c->poll_pending = false;
   if (done_host) *done_host = c->host_state->done;
   if (n_iter_host) *n_iter_host = c->host_state->n_hist;
+  return NBMF_OK;
+}
+
+// ---- batched small fits (restarts, n_init): one launch per phase advances all fits of a group.
+// The caller creates n contexts of IDENTICAL configuration (same m, n, k, dtype, alpha, beta, eps, flags, data planes)
+// on the same stream, with workspaces at a uniform byte stride inside one allocation (leader first), gives each its
+// factors (nbmf_set_factors) and calls nbmf_fit_begin on each with the same max_iter / tol.  After nbmf_batch_bind
+// the leader's nbmf_fit_enqueue drives all of them: every kernel of the loop runs with gridDim.z = n and shifts its
+// workspace pointers by blockIdx.z * stride; each fit keeps its own device-side state (loss history, stop rule,
+// done flag), so fits that converge early simply turn into no-ops.  SIMT engine, single GPU.
+extern "C" int nbmf_batch_bind(nbmf_ctx* c, int32_t n, int64_t stride_bytes) {
+  if (!c || n < 1 || (n > 1 && stride_bytes < (int64_t)c->p.total) || (stride_bytes % 16) != 0 || n > 65535)
+    return fail(NBMF_ERR_ARG, "nbmf_batch_bind: bad arguments");
+  if (n > 1 && (c->p.tensor || c->world != 1))
+    return fail(NBMF_ERR_ARG, "nbmf_batch_bind: batches run on the SIMT engine of a single GPU");
+  c->batch_n = n;
+  c->batch_stride = n > 1 ? stride_bytes : 0;
+  graph_drop(c);
+  return NBMF_OK;
+}
+// states of all fits of the leader's batch: *all_done = every fit has stopped, n_iter_host[i] = losses recorded by fit i
+extern "C" int nbmf_batch_poll(nbmf_ctx* c, int32_t* all_done, int32_t* n_iter_host) {
+  if (!c || !all_done) return fail(NBMF_ERR_ARG, "nbmf_batch_poll: null argument");
+  std::vector<FitState> h((size_t)c->batch_n);
+  const size_t pitch = c->batch_n > 1 ? (size_t)c->batch_stride : sizeof(FitState);
+  CUDA_TRY(cudaMemcpy2DAsync(h.data(), sizeof(FitState), c->state(), pitch, sizeof(FitState), (size_t)c->batch_n,
+                             cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  int done = 1;
+  for (int i = 0; i < c->batch_n; ++i) {
+    done &= h[(size_t)i].done != 0;
+    if (n_iter_host) n_iter_host[i] = h[(size_t)i].n_hist;
+  }
+  *all_done = done;
   return NBMF_OK;
 }
 

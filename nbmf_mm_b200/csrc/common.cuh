@@ -5,6 +5,13 @@
 
 namespace nbmf {
 
+// workspace pointer of fit `blockIdx.z` of a batch (workspaces lie a fixed number of bytes apart)
+template <typename T>
+__device__ __forceinline__ T* batch_shift(T* p, size_t bytes) {
+  return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + bytes);
+}
+
+
 // ---------------------------------------------------------------- vector-of-2 arithmetic
 // fp32 uses Blackwell's packed FFMA2 (PTX fma.rn.f32x2, sm_100+): one issue slot, two
 // FMAs.  ptxas folds make2(s, s) operands into the scalar-broadcast form (Rn.F32), so

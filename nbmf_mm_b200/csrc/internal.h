@@ -39,17 +39,17 @@ void launch_export_factors(int dtype, const void* W, const void* H, int64_t m, i
                            int64_t ldh, void* W_out, void* H_out, cudaStream_t st);
 void launch_h_reduce(int dtype, const void* CDpart, int nsplit, int64_t count, void* CDsum,
                      const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, const FinalizeArgs& fin,
-                     cudaStream_t st);
+                     cudaStream_t st, int batch_n = 1, int64_t batch_stride = 0);
 void launch_finalize(const FinalizeArgs& f, const double* LLsum, cudaStream_t st);
 int  h_epilogue_blocks(int64_t n, int kp);
 void launch_h_epilogue(int dtype, const void* CDsum, int64_t n, int k, int kp, int64_t ldh, double alpha,
                        double beta, double eps, void* H, void* Ht, double* prior_part, const FitState* state,
-                       cudaStream_t st);
+                       cudaStream_t st, int batch_n = 1, int64_t batch_stride = 0);
 void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64_t ldh, double eps,
                        double* prior_part, cudaStream_t st);
 void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nsplit, int64_t m, int64_t n,
                        int k, int kp, int projection, const void* rowcount, void* W, const FitState* state,
-                       cudaStream_t st);
+                       cudaStream_t st, int batch_n = 1, int64_t batch_stride = 0);
 void launch_simplex_deviation(int dtype, const void* W, int64_t m, int k, int kp, unsigned long long* out, cudaStream_t st);
 void launch_export_f64(int dtype, const void* W, const void* H, int64_t m, int64_t n, int k, int kp, int64_t ldh,
                        int normalize_w, double* W_out, double* H_out, cudaStream_t st);

@@ -116,7 +116,16 @@ __device__ __forceinline__ void finalize_body(const FinalizeArgs& f, double ll) 
 template <typename Real>
 __global__ void h_reduce_kernel(const Real* __restrict__ part, int nsplit, int64_t count, Real* __restrict__ sum,
                                 const double* __restrict__ LLpart, int64_t n_ll, double* __restrict__ LLsum,
-                                const FitState* __restrict__ state, const FinalizeArgs fin) {
+                                const FitState* __restrict__ state, FinalizeArgs fin, int64_t bstride) {
+  if (bstride) {                                  // fit blockIdx.z of a batch: its own workspace
+    const size_t sh = (size_t)blockIdx.z * (size_t)bstride;
+    part = batch_shift(part, sh); sum = batch_shift(sum, sh); LLpart = batch_shift(LLpart, sh);
+    LLsum = batch_shift(LLsum, sh); state = batch_shift(state, sh);
+    if (fin.state) {
+      fin.state = batch_shift(fin.state, sh); fin.prior_part = batch_shift(fin.prior_part, sh);
+      fin.history = batch_shift(fin.history, sh);
+    }
+  }
   if (state->done) return;
   if (blockIdx.x == gridDim.x - 1) {            // last block: the log-likelihood partials
     if (threadIdx.x < 32) {
@@ -141,15 +150,15 @@ __global__ void h_reduce_kernel(const Real* __restrict__ part, int nsplit, int64
 
 void launch_h_reduce(int dtype, const void* CDpart, int nsplit, int64_t count, void* CDsum,
                      const double* LLpart, int64_t n_ll, double* LLsum, const FitState* state, const FinalizeArgs& fin,
-                     cudaStream_t st) {
+                     cudaStream_t st, int batch_n, int64_t bstride) {
   int64_t nb = (count + 1023) / 1024;
   if (nb > 148 * 8) nb = 148 * 8;
   if (nb < 1) nb = 1;
-  const unsigned grid = (unsigned)nb + 1;
+  const dim3 grid((unsigned)nb + 1, 1, (unsigned)batch_n);
   if (dtype == 0)
-    h_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)CDpart, nsplit, count, (float*)CDsum, LLpart, n_ll, LLsum, state, fin);
+    h_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)CDpart, nsplit, count, (float*)CDsum, LLpart, n_ll, LLsum, state, fin, bstride);
   else
-    h_reduce_kernel<double><<<grid, 256, 0, st>>>((const double*)CDpart, nsplit, count, (double*)CDsum, LLpart, n_ll, LLsum, state, fin);
+    h_reduce_kernel<double><<<grid, 256, 0, st>>>((const double*)CDpart, nsplit, count, (double*)CDsum, LLpart, n_ll, LLsum, state, fin, bstride);
 }
 
 // ------------------------------------------------------------------------------------
@@ -174,8 +183,13 @@ int h_epilogue_blocks(int64_t n, int kp) { return (int)((n + HEPI_NT - 1) / HEPI
 template <typename Real, bool UPDATE>
 __global__ void h_epilogue_kernel(const Real* __restrict__ CD, int64_t n, int k, int kp, int64_t ldh, double alpha,
                                   double beta, double eps_d, Real* __restrict__ H, Real* __restrict__ Ht,
-                                  double* __restrict__ prior_part, const FitState* __restrict__ state) {
+                                  double* __restrict__ prior_part, const FitState* __restrict__ state, int64_t bstride) {
   __shared__ double scratch[HEPI_NT / 32];
+  if (bstride) {                                  // fit blockIdx.z of a batch: its own workspace
+    const size_t sh = (size_t)blockIdx.z * (size_t)bstride;
+    CD = batch_shift(CD, sh); H = batch_shift(H, sh); Ht = batch_shift(Ht, sh);
+    prior_part = batch_shift(prior_part, sh); state = batch_shift(state, sh);
+  }
   if (UPDATE && state->done) return;
   const int64_t j = (int64_t)blockIdx.x * HEPI_NT + threadIdx.x;
   const int kk = blockIdx.y;
@@ -207,21 +221,21 @@ __global__ void h_epilogue_kernel(const Real* __restrict__ CD, int64_t n, int k,
 
 void launch_h_epilogue(int dtype, const void* CDsum, int64_t n, int k, int kp, int64_t ldh, double alpha,
                        double beta, double eps, void* H, void* Ht, double* prior_part, const FitState* state,
-                       cudaStream_t st) {
-  dim3 grid((unsigned)((n + HEPI_NT - 1) / HEPI_NT), (unsigned)kp);
+                       cudaStream_t st, int batch_n, int64_t bstride) {
+  dim3 grid((unsigned)((n + HEPI_NT - 1) / HEPI_NT), (unsigned)kp, (unsigned)batch_n);
   if (dtype == 0)
-    h_epilogue_kernel<float, true><<<grid, HEPI_NT, 0, st>>>((const float*)CDsum, n, k, kp, ldh, alpha, beta, eps, (float*)H, (float*)Ht, prior_part, state);
+    h_epilogue_kernel<float, true><<<grid, HEPI_NT, 0, st>>>((const float*)CDsum, n, k, kp, ldh, alpha, beta, eps, (float*)H, (float*)Ht, prior_part, state, bstride);
   else
-    h_epilogue_kernel<double, true><<<grid, HEPI_NT, 0, st>>>((const double*)CDsum, n, k, kp, ldh, alpha, beta, eps, (double*)H, (double*)Ht, prior_part, state);
+    h_epilogue_kernel<double, true><<<grid, HEPI_NT, 0, st>>>((const double*)CDsum, n, k, kp, ldh, alpha, beta, eps, (double*)H, (double*)Ht, prior_part, state, bstride);
 }
 
 void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64_t ldh, double eps,
                        double* prior_part, cudaStream_t st) {
   dim3 grid((unsigned)((n + HEPI_NT - 1) / HEPI_NT), (unsigned)kp);
   if (dtype == 0)
-    h_epilogue_kernel<float, false><<<grid, HEPI_NT, 0, st>>>(nullptr, n, k, kp, ldh, 1.0, 1.0, eps, (float*)H, nullptr, prior_part, nullptr);
+    h_epilogue_kernel<float, false><<<grid, HEPI_NT, 0, st>>>(nullptr, n, k, kp, ldh, 1.0, 1.0, eps, (float*)H, nullptr, prior_part, nullptr, 0);
   else
-    h_epilogue_kernel<double, false><<<grid, HEPI_NT, 0, st>>>(nullptr, n, k, kp, ldh, 1.0, 1.0, eps, (double*)H, nullptr, prior_part, nullptr);
+    h_epilogue_kernel<double, false><<<grid, HEPI_NT, 0, st>>>(nullptr, n, k, kp, ldh, 1.0, 1.0, eps, (double*)H, nullptr, prior_part, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -235,7 +249,11 @@ template <typename Real>
 __global__ void w_epilogue_kernel(const Real* __restrict__ Gpart, const Real* __restrict__ Qpart, int nsplit,
                                   int64_t m, int64_t n, int k, int kp, int projection,
                                   const Real* __restrict__ rowcount, Real* __restrict__ W,
-                                  const FitState* __restrict__ state) {
+                                  const FitState* __restrict__ state, int64_t bstride) {
+  if (bstride) {                                  // fit blockIdx.z of a batch: its own workspace (rowcount is shared)
+    const size_t sh = (size_t)blockIdx.z * (size_t)bstride;
+    Gpart = batch_shift(Gpart, sh); Qpart = batch_shift(Qpart, sh); W = batch_shift(W, sh); state = batch_shift(state, sh);
+  }
   if (state->done) return;
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= m) return;
@@ -274,12 +292,12 @@ __global__ void w_epilogue_kernel(const Real* __restrict__ Gpart, const Real* __
 
 void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nsplit, int64_t m, int64_t n,
                        int k, int kp, int projection, const void* rowcount, void* W, const FitState* state,
-                       cudaStream_t st) {
-  const unsigned grid = (unsigned)((m + 127) / 128);
+                       cudaStream_t st, int batch_n, int64_t bstride) {
+  const dim3 grid((unsigned)((m + 127) / 128), 1, (unsigned)batch_n);
   if (dtype == 0)
-    w_epilogue_kernel<float><<<grid, 128, 0, st>>>((const float*)Gpart, (const float*)Qpart, nsplit, m, n, k, kp, projection, (const float*)rowcount, (float*)W, state);
+    w_epilogue_kernel<float><<<grid, 128, 0, st>>>((const float*)Gpart, (const float*)Qpart, nsplit, m, n, k, kp, projection, (const float*)rowcount, (float*)W, state, bstride);
   else
-    w_epilogue_kernel<double><<<grid, 128, 0, st>>>((const double*)Gpart, (const double*)Qpart, nsplit, m, n, k, kp, projection, (const double*)rowcount, (double*)W, state);
+    w_epilogue_kernel<double><<<grid, 128, 0, st>>>((const double*)Gpart, (const double*)Qpart, nsplit, m, n, k, kp, projection, (const double*)rowcount, (double*)W, state, bstride);
 }
 
 // ------------------------------------------------------------------------------------

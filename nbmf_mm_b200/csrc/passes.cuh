@@ -95,7 +95,10 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
   constexpr int KP = Cfg::KP, S = Cfg::S, C = Cfg::C, KH = Cfg::KH, NT = Cfg::NT;
   constexpr int BM = Cfg::BM, WPT = Cfg::WPT, NSTAGE = Cfg::NSTAGE;
   constexpr bool DENSE = Cfg::DENSE, STRICT = Cfg::STRICT;
-  if (*a.done) return;
+  // fit blockIdx.z of a batch works in its own workspace: W, H, CD, LL and done are shifted where they are used (the
+  // offset is recomputed there: it must not occupy registers across the main loop); 0 for a single fit
+#define NBMF_BSH ((size_t)blockIdx.z * (size_t)a.batch_stride)
+  if (*batch_shift(a.done, NBMF_BSH)) return;
 
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double red_scratch[NT / 32];
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
   // ---- H slice -> registers (padded columns hold 0.5, always in bounds)
   V2 hp[C][KH / 2];
   {
-    const Real* __restrict__ Hg = reinterpret_cast<const Real*>(a.H);
+    const Real* __restrict__ Hg = batch_shift(reinterpret_cast<const Real*>(a.H), NBMF_BSH);
 #pragma unroll
     for (int q = 0; q < KH / 2; ++q)
 #pragma unroll
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
 #pragma unroll
   for (int cc = 0; cc < C; ++cc) lld[cc] = 0.0;
 
-  const unsigned char* __restrict__ Wg = reinterpret_cast<const unsigned char*>(a.W);
+  const unsigned char* __restrict__ Wg = batch_shift(reinterpret_cast<const unsigned char*>(a.W), NBMF_BSH);
   using VT = typename Cfg::VT;
   const VT* __restrict__ Vg = reinterpret_cast<const VT*>(a.Vm);
   const int64_t ntiles = (r1 > r0) ? (r1 - r0 + BM - 1) / BM : 0;
@@ -309,8 +312,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
 
   // ---- partial C, D for this row split
   if (a.compute_cd) {
-    Real* __restrict__ Cg = reinterpret_cast<Real*>(a.CD) + (size_t)(split * 2 + 0) * KP * a.ldh;
-    Real* __restrict__ Dg = reinterpret_cast<Real*>(a.CD) + (size_t)(split * 2 + 1) * KP * a.ldh;
+    Real* __restrict__ Cg = batch_shift(reinterpret_cast<Real*>(a.CD), NBMF_BSH) + (size_t)(split * 2 + 0) * KP * a.ldh;
+    Real* __restrict__ Dg = batch_shift(reinterpret_cast<Real*>(a.CD), NBMF_BSH) + (size_t)(split * 2 + 1) * KP * a.ldh;
 #pragma unroll
     for (int q = 0; q < KH / 2; ++q) {
       const size_t o0 = (size_t)(kp * KH + 2 * q) * a.ldh + j0;
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
       if (j0 + cc < a.n) mine += lld[cc];
   }
   const double tot = block_sum<NT>(mine, red_scratch);
-  if (tid == 0) a.LL[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<Real>();
+  if (tid == 0) batch_shift(a.LL, NBMF_BSH)[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<Real>();
 }
 
 template <typename Cfg>
@@ -342,7 +345,7 @@ void launch_h_pass(const HPassArgs& a, int nsplit, cudaStream_t st) {
     cudaFuncSetAttribute(h_pass_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     attr_set = true;
   }
-  dim3 grid((unsigned)((a.n + Cfg::BN - 1) / Cfg::BN), (unsigned)nsplit);
+  dim3 grid((unsigned)((a.n + Cfg::BN - 1) / Cfg::BN), (unsigned)nsplit, (unsigned)a.batch_n);
   h_pass_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(a);
 }
 
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
   constexpr int KP = Cfg::KP, S = Cfg::S, C = Cfg::C, KH = Cfg::KH, NT = Cfg::NT;
   constexpr int BNT = Cfg::BNT, NWORD = Cfg::NWORD, NSTAGE = Cfg::NSTAGE, BMR = Cfg::BMR;
   constexpr bool DENSE = Cfg::DENSE;
-  if (*a.done) return;
+  if (*batch_shift(a.done, NBMF_BSH)) return;                    // batch: W, Ht, G, Q, done shifted at their uses
 
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
   // ---- W slice -> registers (rows past m are clamped; their results are not stored)
   V2 wp[C][KH / 2];
   {
-    const Real* __restrict__ Wg = reinterpret_cast<const Real*>(a.W);
+    const Real* __restrict__ Wg = batch_shift(reinterpret_cast<const Real*>(a.W), NBMF_BSH);
 #pragma unroll
     for (int rr = 0; rr < C; ++rr) {
       const int64_t row = min(ib + il + rr, a.m - 1);
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
     for (int q = 0; q < KH / 2; ++q) gacc[rr][q] = make2(Real(0), Real(0));
   }
 
-  const unsigned char* __restrict__ Htg = reinterpret_cast<const unsigned char*>(a.Ht);
+  const unsigned char* __restrict__ Htg = batch_shift(reinterpret_cast<const unsigned char*>(a.Ht), NBMF_BSH);
   using VT = typename Cfg::VT;
   const VT* __restrict__ Vg = reinterpret_cast<const VT*>(a.Vm);
   const int64_t ntiles = (c1 > c0) ? (c1 - c0 + BNT - 1) / BNT : 0;
@@ -532,8 +535,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
   }
   cp_async_wait<0>();
 
-  Real* __restrict__ Gg = reinterpret_cast<Real*>(a.G) + (size_t)split * a.m * KP;
-  Real* __restrict__ Qg = reinterpret_cast<Real*>(a.Q) + (size_t)split * a.m;
+  Real* __restrict__ Gg = batch_shift(reinterpret_cast<Real*>(a.G), NBMF_BSH) + (size_t)split * a.m * KP;
+  Real* __restrict__ Qg = batch_shift(reinterpret_cast<Real*>(a.Q), NBMF_BSH) + (size_t)split * a.m;
 #pragma unroll
   for (int rr = 0; rr < C; ++rr) {
     const int64_t row = ib + il + rr;
@@ -553,7 +556,7 @@ void launch_w_pass(const WPassArgs& a, int nsplit, cudaStream_t st) {
     cudaFuncSetAttribute(w_pass_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     attr_set = true;
   }
-  dim3 grid((unsigned)((a.m + Cfg::BMR - 1) / Cfg::BMR), (unsigned)nsplit);
+  dim3 grid((unsigned)((a.m + Cfg::BMR - 1) / Cfg::BMR), (unsigned)nsplit, (unsigned)a.batch_n);
   w_pass_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(a);
 }
 

@@ -227,7 +227,7 @@ class DeviceProblem:
 
     def __init__(self, m, n, k, *, dtype="float64", vkind="bits", has_mask=False, alpha=1.2, beta=1.2,
                  eps=1e-8, n_obs=None, mask_semantics="reference", projection="normalize",
-                 max_iter_cap=2000, device=None, engine="auto"):
+                 max_iter_cap=2000, device=None, engine="auto", workspace=None):
         torch = _torch()
         self.lib = _lib.load()
         self.dev = require_cuda(device)
@@ -257,7 +257,9 @@ class DeviceProblem:
         nbytes = self.lib.nbmf_workspace_bytes(C.byref(cfg))
         if nbytes < 0:
             _lib.check(-1, "nbmf_workspace_bytes")
-        self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+        # workspace: one allocation per problem, or (batched small fits) a slice handed out by `workspace(nbytes)`
+        self.workspace = (torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev) if workspace is None
+                          else workspace(int(nbytes)))
         self._ctx = C.c_void_p(0)
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.nbmf_create(C.byref(cfg), _ptr(self.workspace), nbytes, _stream(self.dev),
@@ -441,6 +443,20 @@ class DeviceProblem:
         conv = C.c_int32(0)
         self._call("nbmf_fit_history", hist.ctypes.data_as(C.POINTER(C.c_double)), int(count), C.byref(conv))
         return hist[: int(count)].copy(), bool(conv.value)
+
+    def batch_bind(self, n, stride_bytes):
+        """Make this context the leader of ``n`` contexts of identical configuration whose workspaces lie
+        ``stride_bytes`` apart (``nbmf_batch_bind``): its ``fit_enqueue`` then advances all of them per launch."""
+        self._call("nbmf_batch_bind", int(n), int(stride_bytes))
+        self._batch_n = int(n)
+
+    def batch_poll(self):
+        """(every fit of the batch has stopped, [losses recorded by fit i]); synchronises the stream."""
+        n = getattr(self, "_batch_n", 1)
+        done = C.c_int32(0)
+        iters = (C.c_int32 * n)()
+        self._call("nbmf_batch_poll", C.byref(done), iters)
+        return bool(done.value), [int(v) for v in iters]
 
     def transform(self, n_steps=50):
         self._call("nbmf_transform", int(n_steps))

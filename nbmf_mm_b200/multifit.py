@@ -32,13 +32,15 @@ def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
 
 def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500, tol=1e-5, eps=1e-8,
                      projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
-                     engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False):
+                     engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False, batch=True):
     """Fit ``len(jobs)`` models to the same ``Y`` / ``mask``.
 
     ``jobs``: sequence of dicts with ``n_components`` and optionally ``alpha``, ``beta`` (default 1.2),
     ``random_state``, ``W_init``, ``H_init``, ``max_iter``, ``tol`` (defaults: the keyword arguments).  Returns a
     list of ``(W, H, losses, 0.0, n_iter)`` in job order, each identical to
-    ``nbmf_mm_solver(Y, mask=mask, orientation=orientation, **job)``.  ``n_streams``: concurrent fits
+    ``nbmf_mm_solver(Y, mask=mask, orientation=orientation, **job)``.  ``batch``: jobs that differ only in their
+    inits (same K, alpha, beta, max_iter, tol: restarts) advance together on small problems, one launch per kernel
+    for the whole group (``nbmf_batch_bind``).  ``n_streams``: concurrent fits for the remaining jobs
     (default: one per hardware queue, 8..32, for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own)."""
     import torch
     if orientation not in _CANON:
@@ -95,12 +97,89 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
             W, H = np.ascontiguousarray(H.T), np.ascontiguousarray(W.T)
         return W, H, [np.float64(v) for v in losses_arr], 0.0, n_iter, converged, eng
 
-    if n_streams == 1:
-        results = [run(i) for i in range(len(jobs))]
+    def run_batch(idxs):
+        """Fits with the same K and hyper-parameters advance TOGETHER: contexts with workspaces at a uniform stride in one
+        allocation, one launch per kernel for the whole group (``nbmf_batch_bind``).  Returns None when the group is not
+        eligible (tensor engine), else the results in the order of ``idxs``."""
+        k, alpha, beta, mi, tl = prepared[idxs[0]][:5]
+        B = len(idxs)
+        big = {}
+
+        def slice_of(b):
+            def provide(nbytes):
+                if "t" not in big:
+                    big["S"] = (nbytes + 255) // 256 * 256
+                    big["t"] = torch.empty(big["S"] * B, dtype=torch.uint8, device=dev)
+                return big["t"][b * big["S"]: b * big["S"] + nbytes]
+            return provide
+
+        stream = torch.cuda.Stream(device=dev)               # not the default stream: the loop is replayed from a graph
+        probs, out = [], []
+        with torch.cuda.stream(stream):
+            stream.wait_event(ready)
+            try:
+                for b, idx in enumerate(idxs):
+                    prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps,
+                                        mask_semantics=mask_semantics, projection=projection_method, max_iter_cap=mi,
+                                        device=device, engine=engine, workspace=slice_of(b))
+                    probs.append(prob)
+                    if prob.engine != "simt":
+                        return None
+                    prob.set_factors(prepared[idx][5], prepared[idx][6], normalize_w=True)
+                    prob.fit_begin(mi, tl)
+                leader = probs[0]
+                leader.batch_bind(B, big["S"])
+                chunk, n_iters = 16, [0] * B
+                for _ in range(mi + 8):                      # every pass enqueues >= 1 iteration until the tail is in
+                    leader.fit_enqueue(chunk)
+                    done, n_iters = leader.batch_poll()
+                    if done:
+                        break
+                    chunk = min(chunk * 2, 256)
+                else:
+                    raise RuntimeError("batched fit loop did not terminate")
+                leader.batch_bind(1, 0)
+                for prob, n_iter in zip(probs, n_iters):
+                    losses_arr, converged = prob.fit_history(n_iter)
+                    dv = prob.simplex_deviation()            # solver tail, _solver.py:192-213
+                    W, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dv) and dv > 1e-9))
+                    if transpose:                            # _solver.py:182-184
+                        W, H = np.ascontiguousarray(H.T), np.ascontiguousarray(W.T)
+                    out.append((W, H, [np.float64(v) for v in losses_arr], 0.0, n_iter, converged, prob.engine))
+            finally:
+                for prob in probs:
+                    prob.close()
+        return out
+
+    # groups of fits that can advance together (restarts: same K, alpha, beta, max_iter, tol) on small problems
+    results = [None] * len(jobs)
+    batched = 0
+    if batch and m * n <= (1 << 24) and data.vkind == "bits":
+        groups = {}
+        for i, pj in enumerate(prepared):
+            groups.setdefault(pj[:5], []).append(i)
+        for idxs in groups.values():
+            if len(idxs) < 2:
+                continue
+            for c0 in range(0, len(idxs), 256):               # bounded batches: workspace memory, gridDim.z
+                part = idxs[c0:c0 + 256]
+                if len(part) < 2:
+                    continue
+                got = run_batch(part)
+                if got is None:
+                    break
+                for i, r in zip(part, got):
+                    results[i] = r
+                batched += len(part)
+    rest = [i for i, r in enumerate(results) if r is None]
+    if n_streams == 1 or len(rest) <= 1:
+        for i in rest:
+            results[i] = run(i)
     else:
-        with ThreadPoolExecutor(max_workers=n_streams) as pool:
-            results = list(pool.map(run, range(len(jobs))))
+        with ThreadPoolExecutor(max_workers=min(n_streams, len(rest))) as pool:
+            for i, r in zip(rest, pool.map(run, rest)):
+                results[i] = r
     if stats is not None:
-        stats.update(h2d_bytes=data.h2d_bytes, n_streams=n_streams, engine=results[0][6],
+        stats.update(h2d_bytes=data.h2d_bytes, n_streams=n_streams, engine=results[0][6], batched=batched,
                      converged=[r[5] for r in results])
     return [r[:5] for r in results]

@@ -63,3 +63,32 @@ def test_graph_replay_on_the_tensor_engine_equals_per_kernel_launches():
         assert np.array_equal(W, out[0]) and np.array_equal(H, out[1])
         stopped_early += n_iter < j["max_iter"]
     assert stopped_early >= 1
+
+
+@pytest.mark.parametrize("orientation,dtype,projection,tol", [("beta-dir", "float32", "normalize", 0.0),
+                                                              ("dir-beta", "float64", "duchi", 2e-4),
+                                                              ("beta-dir", "float64", "normalize", 7.5e-4)])
+def test_batched_restarts_equal_sequential_solver_calls(orientation, dtype, projection, tol):
+    """Restarts (same K, alpha, beta, max_iter, tol) advance together: one launch per kernel for the whole group
+    (nbmf_batch_bind), every fit with its own device-side loss history and stop rule.  Bit-identical to the loop of
+    solver calls, including restarts that stop at different iterations; odd jobs take the per-stream path."""
+    X, mask = _data(seed=9)
+    jobs = [dict(n_components=7, alpha=1.3, beta=1.1, random_state=r) for r in range(7)]
+    jobs.insert(3, dict(n_components=5, random_state=99))        # a job of another group (singleton)
+    stats = {}
+    got = nbmf_mm_multifit(X, jobs, mask=mask, orientation=orientation, max_iter=45, tol=tol, dtype=dtype,
+                           projection_method=projection, stats=stats)
+    assert stats["batched"] == 7
+    n_iters = set()
+    for j, out in zip(jobs, got):
+        W, H, losses, _, n_iter = nbmf_mm_solver(X, mask=mask, orientation=orientation, max_iter=45, tol=tol, dtype=dtype,
+                                                 projection_method=projection, **j)
+        assert n_iter == out[4] and np.array_equal(losses, out[2]), (j, n_iter, out[4])
+        assert np.array_equal(W, out[0]) and np.array_equal(H, out[1]), (j, float(np.abs(W - out[0]).max()))
+        n_iters.add(n_iter)
+    if tol == 7.5e-4:                                              # (CPU oracle: 12, 45, 11, 10, 10, 10, 11 iterations)
+        assert len(n_iters) > 1, n_iters                           # the restarts did stop at different iterations
+    plain = nbmf_mm_multifit(X, jobs, mask=mask, orientation=orientation, max_iter=45, tol=tol, dtype=dtype,
+                             projection_method=projection, batch=False)
+    for a, b in zip(got, plain):
+        assert a[4] == b[4] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
