@@ -145,6 +145,11 @@ int nbmf_h_half_step(nbmf_ctx* ctx);            /* H <- H' (_solver.py:39-47) */
 int nbmf_w_half_step(nbmf_ctx* ctx);            /* W <- W' with the current H (_solver.py:50-57) */
 /* MAP objective of the current factors (_solver.py:148-162); synchronises the stream */
 int nbmf_objective(nbmf_ctx* ctx, double* loss_host);
+/* Per-CTA partial sums of the log-likelihood (the `np.sum(log_lik)` of _solver.py:150-161 before the sum) left by the
+ * most recent H pass: entry [s * col_blocks + b] covers the rows of row split s and the columns of column block b
+ * (nbmf_plan_info / nbmf_variant_info give the block width).  Lets a caller check the fused NLL of one column block
+ * against a host computation on a problem too large to check whole.  Synchronises the stream. */
+int nbmf_loglik_partials(nbmf_ctx* ctx, double* out_host, int64_t capacity, int32_t* col_blocks_host, int32_t* row_splits_host);
 
 /* ---- the fit loop (replaces the loop of nbmf_mm_solver, _solver.py:143-175) ----
  * Runs up to max_iter MM iterations entirely on the stream; the loss of every iteration, the

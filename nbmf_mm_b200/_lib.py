@@ -62,6 +62,7 @@ SIGNATURES = {
     "nbmf_h_half_step": (_INT, [_P]),
     "nbmf_w_half_step": (_INT, [_P]),
     "nbmf_objective": (_INT, [_P, C.POINTER(_DBL)]),
+    "nbmf_loglik_partials": (_INT, [_P, C.POINTER(_DBL), _I64, C.POINTER(_I32), C.POINTER(_I32)]),
     "nbmf_fit": (_INT, [_P, _I32, _DBL, C.POINTER(_DBL), C.POINTER(_I32), C.POINTER(_I32)]),
     "nbmf_fit_begin": (_INT, [_P, _I32, _DBL]),
     "nbmf_batch_bind": (_INT, [_P, _I32, _I64]),

@@ -686,6 +686,21 @@ extern "C" int nbmf_objective(nbmf_ctx* c, double* loss_host) {
   return NBMF_OK;
 }
 
+// Per-CTA log-likelihood partials of the most recent H pass (row split s, column block b at [s * col_blocks + b]):
+// lets a caller check the fused NLL of one column block against a host computation when the whole matrix is far too
+// large for one (bench.py parity_check at config 4).
+extern "C" int nbmf_loglik_partials(nbmf_ctx* c, double* out_host, int64_t capacity, int32_t* col_blocks, int32_t* row_splits) {
+  if (!c || !out_host) return fail(NBMF_ERR_ARG, "nbmf_loglik_partials: null argument");
+  if (c->batch_n > 1) return fail(NBMF_ERR_ARG, "nbmf_loglik_partials: not available on a batch leader");
+  const int64_t count = (int64_t)c->p.h_nsplit * c->p.h_ncb;
+  if (capacity < count) return fail(NBMF_ERR_ARG, "nbmf_loglik_partials: buffer too small");
+  CUDA_TRY(cudaMemcpyAsync(out_host, c->at<double>(c->p.oLLpart), (size_t)count * 8, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  if (col_blocks) *col_blocks = c->p.h_ncb;
+  if (row_splits) *row_splits = c->p.h_nsplit;
+  return NBMF_OK;
+}
+
 // ------------------------------------------------------------------------------------ fit loop
 extern "C" int nbmf_fit_begin(nbmf_ctx* c, int32_t max_iter, double tol) {
   int rc = require_data(c);

@@ -3,7 +3,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace nbmf {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: a launcher keeps one bit per
+// device and opts in again on every device it meets (a process-wide flag would leave cuda:1 without the opt-in after
+// cuda:0 set it).  Safe to race: setting the attribute twice is harmless.
+template <typename Kernel>
+inline void ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>& done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask.load(std::memory_order_relaxed) & bit) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done_mask.fetch_or(bit, std::memory_order_relaxed);
+}
 
 // workspace pointer of fit `blockIdx.z` of a batch (workspaces lie a fixed number of bytes apart)
 template <typename T>

@@ -340,11 +340,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
 
 template <typename Cfg>
 void launch_h_pass(const HPassArgs& a, int nsplit, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(h_pass_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_set{0};
+  ensure_dynamic_smem(h_pass_kernel<Cfg>, Cfg::SMEM, attr_set);
   dim3 grid((unsigned)((a.n + Cfg::BN - 1) / Cfg::BN), (unsigned)nsplit, (unsigned)a.batch_n);
   h_pass_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(a);
 }
@@ -551,11 +548,8 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
 
 template <typename Cfg>
 void launch_w_pass(const WPassArgs& a, int nsplit, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(w_pass_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_set{0};
+  ensure_dynamic_smem(w_pass_kernel<Cfg>, Cfg::SMEM, attr_set);
   dim3 grid((unsigned)((a.m + Cfg::BMR - 1) / Cfg::BMR), (unsigned)nsplit, (unsigned)a.batch_n);
   w_pass_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(a);
 }

@@ -686,23 +686,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
 }
 
 inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(w_pass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTC_SMEM);
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_set{0};
+  ensure_dynamic_smem(w_pass_tc_kernel, WTC_SMEM, attr_set);
   dim3 grid((unsigned)((a.m + 127) / 128), (unsigned)nsplit);
   w_pass_tc_kernel<<<grid, TC_THREADS, WTC_SMEM, st>>>(a);
 }
 inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(h_pass_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
-    cudaFuncSetAttribute(h_pass_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
-    cudaFuncSetAttribute(h_pass_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
-    cudaFuncSetAttribute(h_pass_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HTC_SMEM);
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_set[4];
+  ensure_dynamic_smem(h_pass_tc_kernel<false, true>, HTC_SMEM, attr_set[0]);
+  ensure_dynamic_smem(h_pass_tc_kernel<true, true>, HTC_SMEM, attr_set[1]);
+  ensure_dynamic_smem(h_pass_tc_kernel<false, false>, HTC_SMEM, attr_set[2]);
+  ensure_dynamic_smem(h_pass_tc_kernel<true, false>, HTC_SMEM, attr_set[3]);
   dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit);
   if (a.compute_cd) {
     if (a.Mc) h_pass_tc_kernel<true, true><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);

@@ -417,6 +417,15 @@ class DeviceProblem:
         self._call("nbmf_objective", C.byref(out))
         return float(out.value)
 
+    def loglik_partials(self):
+        """(row splits x column blocks) array of the per-CTA log-likelihood sums of the most recent H pass."""
+        info = self.plan_info()
+        n = info["h_col_blocks"] * info["h_row_splits"]
+        out = np.zeros(n, dtype=np.float64)
+        cb, rs = C.c_int32(0), C.c_int32(0)
+        self._call("nbmf_loglik_partials", out.ctypes.data_as(C.POINTER(C.c_double)), n, C.byref(cb), C.byref(rs))
+        return out.reshape(rs.value, cb.value)
+
     # -- loop
     def fit(self, max_iter, tol):
         """Run the device-resident loop; returns (losses ndarray, n_iter, converged)."""
@@ -499,6 +508,15 @@ class DeviceProblem:
             handle = C.c_void_p()
             _lib.check(self.lib.nbmf_comm_create(raw, rank, world, C.byref(handle)), "nbmf_comm_create")
             comm = _COMM_CACHE[key] = handle
+        # every rank must reduce the same [C | D] layout: same engine, same padded K (fail loudly instead of hanging)
+        torch = _torch()
+        mine = [1 if self.engine == "tensor" else 0, int(self.k), self.np_dtype.itemsize, int(self.n)]
+        t = torch.tensor(mine + [-v for v in mine], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)         # max(x) and -min(x) in one small collective
+        t = t.tolist()
+        if any(t[i] != -t[i + 4] for i in range(4)):
+            raise RuntimeError(f"row shards disagree on (tensor engine, k, itemsize, n): max {t[:4]}, min {[-v for v in t[4:]]}; "
+                               "pass an explicit engine= or let nbmf_mm_solver decide it from the global problem size")
         self._call("nbmf_comm_attach", comm, rank, world)
         self.world = world
 

@@ -168,7 +168,8 @@ class NBMFMM(BaseEstimator, TransformerMixin):
             outs = nbmf_mm_multifit(X, jobs, mask=mask, orientation=orientation, max_iter=self.max_iter, tol=self.tol,
                                     projection_method=self.projection_method, mask_semantics=self.mask_semantics,
                                     dtype=self.dtype, device=self.device, engine=self.engine,
-                                    dense_storage=self.dense_storage, stats=stats, check_range=True)
+                                    dense_storage=self.dense_storage, stats=stats, check_range=True,
+                                    verbose=self.verbose)
             for r, out in zip(mine, outs):
                 if best is None or out[2][-1] < best[0][2][-1]:
                     best = (out, stats, r)

@@ -32,7 +32,8 @@ def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
 
 def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500, tol=1e-5, eps=1e-8,
                      projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
-                     engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False, batch=True):
+                     engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False, batch=True,
+                     verbose=0):
     """Fit ``len(jobs)`` models to the same ``Y`` / ``mask``.
 
     ``jobs``: sequence of dicts with ``n_components`` and optionally ``alpha``, ``beta`` (default 1.2),
@@ -179,6 +180,12 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
         with ThreadPoolExecutor(max_workers=min(n_streams, len(rest))) as pool:
             for i, r in zip(rest, pool.map(run, rest)):
                 results[i] = r
+    if verbose > 0:                                          # the lines of _solver.py:165-166,172-173, per job
+        for i, r in enumerate(results):
+            for it in range(0, r[4], 10):
+                print(f"[fit {i}] Iter {it:4d}: Loss = {r[2][it]:.6f}")
+            if r[5]:
+                print(f"[fit {i}] Converged at iteration {r[4] - 1}")
     if stats is not None:
         stats.update(h2d_bytes=data.h2d_bytes, n_streams=n_streams, engine=results[0][6], batched=batched,
                      converged=[r[5] for r in results])

@@ -173,27 +173,17 @@ def make_problem(data: PreparedData, k, *, dtype, alpha, beta, eps, mask_semanti
     return prob
 
 
-def final_simplex_cleanup(W, H, orientation):
-    """Tail of the reference solver (``_solver.py:192-213``): renormalise the simplex factor
-    only when its worst deviation exceeds 1e-9; vectors with sum <= 1e-12 are left alone."""
-    tiny, dev_tol = 1e-12, 1e-9
-    if orientation == "beta-dir":
-        if W.size:
-            rs = W.sum(axis=1, keepdims=True)
-            dev = np.max(np.abs(rs - 1.0))
-            if np.isfinite(dev) and dev > dev_tol:
-                ok = (rs > tiny).ravel()
-                if ok.any():
-                    W[ok, :] = W[ok, :] / rs[ok]
-    else:
-        if H.size:
-            cs = H.sum(axis=0, keepdims=True)
-            dev = np.max(np.abs(cs - 1.0))
-            if np.isfinite(dev) and dev > dev_tol:
-                ok = (cs > tiny).ravel()
-                if ok.any():
-                    H[:, ok] = H[:, ok] / cs[:, ok]
-    return W, H
+TENSOR_MAX_K = 32            # largest n_components the tcgen05 engine covers (capi.cu make_plan)
+
+
+def resolve_engine(engine, *, dtype, vkind, k, eps, m_total, n):
+    """The engine every rank of a row-sharded fit must use, decided from GLOBAL quantities (``m_total``, not the
+    local shard): ranks that disagreed would all-reduce differently shaped [C | D] buffers (the tensor engine pads K to
+    its own tile).  Same rule as ``make_plan`` in capi.cu applies to a single GPU."""
+    if engine != "auto":
+        return engine
+    eligible = np.dtype(dtype) == np.float32 and vkind == "bits" and k <= TENSOR_MAX_K and eps >= 1e-9
+    return "tensor" if eligible and m_total >= 512 and n >= 512 else "simt"
 
 
 def _row_shard(m, rank, world):
@@ -249,8 +239,10 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         r0, r1 = shard_row0, shard_row0 + shape[0]
     elif world > 1:
         r0, r1 = _row_shard(m, rank, world)
-        if r1 <= r0:
-            raise ValueError(f"rank {rank} of {world} has no rows (m={m}); use fewer ranks")
+        empty = [r for r in range(world) if _row_shard(m, r, world)[1] <= _row_shard(m, r, world)[0]]
+        if empty:                                             # the same table on every rank: all of them raise
+            raise ValueError(f"ranks {empty} of {world} would have no rows (m={m}, shards start on multiples of 32 rows); "
+                             "use fewer ranks")
     else:
         r0, r1 = 0, m
     # large problems: the inits go up from, and the results come back into, pinned host memory (plain DMA instead of
@@ -269,6 +261,8 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
                 and (world == 1 or shard is not None))
     data = prob = None
     if streamed:
+        if world > 1:
+            engine = resolve_engine(engine, dtype=dtype, vkind="bits", k=k, eps=eps, m_total=m, n=n)
         prob = DeviceProblem(shape[0], n, k, dtype=dtype, vkind="bits", has_mask=mask is not None, alpha=alpha, beta=beta,
                              eps=eps, n_obs=None, mask_semantics=mask_semantics, projection=projection_method,
                              max_iter_cap=max_iter, device=device, engine=engine)
@@ -284,10 +278,19 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     try:
         if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
             W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
+        rng = np.random
+        if world > 1 and random_state is None and (W_init is None or H_init is None):
+            # every rank is its own process with its own global stream: without a seed the ranks would start from
+            # different "global" H (and stop at different iterations -> mismatched collectives).  Rank 0 draws a seed
+            # from its global stream and every rank draws the inits from that seed.
+            import torch.distributed as dist
+            box = [int(np.random.randint(0, 2**31 - 1)) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            rng = np.random.RandomState(box[0])
         if W_init is None:
-            W_init = np.random.uniform(0.1, 0.9, (m, k))      # W first, then H: _solver.py:126-129
+            W_init = rng.uniform(0.1, 0.9, (m, k))            # W first, then H: _solver.py:126-129
         if H_init is None:
-            H_init = np.random.uniform(0.1, 0.9, (k, n))
+            H_init = rng.uniform(0.1, 0.9, (k, n))
         W_init = np.asarray(W_init, dtype=np.float64)
         H_init = np.asarray(H_init, dtype=np.float64)
         if tuple(W_init.shape) != (m, k) or tuple(H_init.shape) != (k, n):
@@ -322,6 +325,8 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
                                 None if data.P is None else data.P.rows(r0, r1),
                                 None if data.M is None else data.M.rows(r0, r1),
                                 None if data.Vm is None else data.Vm[r0:r1], n_obs_global, data.h2d_bytes)
+        if world > 1:
+            engine = resolve_engine(engine, dtype=dtype, vkind=data.vkind, k=k, eps=eps, m_total=m, n=n)
         prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
                             projection=projection_method, max_iter_cap=max_iter, device=device, n_obs=n_obs_global,
                             engine=engine)

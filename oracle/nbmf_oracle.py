@@ -83,9 +83,11 @@ def project_columns_duchi(U):
 # ---------------------------------------------------------------------------
 # one MM iteration (H half-step, then W half-step with the NEW H)
 # ---------------------------------------------------------------------------
-def h_half_step(Y, W, H, mask, alpha, beta, eps=EPS_DEFAULT, mask_semantics="reference"):
-    """H half-step, ``_solver.py:34-47``.  Returns H_new (k x n)."""
-    pos, negH, _, _ = _weights(Y, mask, mask_semantics)
+def h_half_step(Y, W, H, mask, alpha, beta, eps=EPS_DEFAULT, mask_semantics="reference", weights=None):
+    """H half-step, ``_solver.py:34-47``.  Returns H_new (k x n).  ``weights`` = the tuple ``_weights`` returns,
+    built once per iteration by ``mm_step`` exactly as the reference builds its masked copies once
+    (``_solver.py:21-32``)."""
+    pos, negH, _, _ = _weights(Y, mask, mask_semantics) if weights is None else weights
     prior_a = np.ones_like(H) * (alpha - 1)
     prior_b = np.ones_like(H) * (beta - 1)
     theta = W.T @ H                                             # :39
@@ -95,7 +97,7 @@ def h_half_step(Y, W, H, mask, alpha, beta, eps=EPS_DEFAULT, mask_semantics="ref
     return np.clip(H_new, eps, 1 - eps)                         # :47
 
 
-def w_half_step(Y, W, H_new, mask, eps=EPS_DEFAULT, projection="normalize"):
+def w_half_step(Y, W, H_new, mask, eps=EPS_DEFAULT, projection="normalize", weights=None):
     """W half-step, ``_solver.py:50-57`` (same formulas as ``_base.py:180-193``).
 
     Always properly masked.  ``projection="normalize"``: multiplicative step,
@@ -104,7 +106,7 @@ def w_half_step(Y, W, H_new, mask, eps=EPS_DEFAULT, projection="normalize"):
     per-row observed count, then Euclidean projection onto the simplex.
     """
     n = Y.shape[1]
-    _, _, posT, negT = _weights(Y, mask, "reference")
+    _, _, posT, negT = _weights(Y, mask, "reference") if weights is None else weights
     thetaT = H_new.T @ W                                        # :50  (n x m)
     G = H_new @ (posT / (thetaT + eps)) + (1 - H_new) @ (negT / (1 - thetaT + eps))  # :53
     step = W * G
@@ -124,8 +126,9 @@ def w_half_step(Y, W, H_new, mask, eps=EPS_DEFAULT, projection="normalize"):
 def mm_step(Y, W, H, mask, alpha, beta, eps=EPS_DEFAULT,
             mask_semantics="reference", projection="normalize"):
     """One full MM iteration == ``nbmf_mm_update_beta_dir`` (``_solver.py:5-59``)."""
-    H_new = h_half_step(Y, W, H, mask, alpha, beta, eps, mask_semantics)
-    W_new = w_half_step(Y, W, H_new, mask, eps, projection)
+    weights = _weights(Y, mask, mask_semantics)          # once per iteration, as _solver.py:21-32
+    H_new = h_half_step(Y, W, H, mask, alpha, beta, eps, mask_semantics, weights)
+    W_new = w_half_step(Y, W, H_new, mask, eps, projection, weights)
     return W_new, H_new
 
 

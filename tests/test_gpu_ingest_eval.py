@@ -115,10 +115,11 @@ def test_fp16_layout_of_probabilistic_v(orientation):
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
-def test_solver_tail_on_device_equals_the_host_rule(dtype):
-    """fp64 export + final simplex clean-up (_solver.py:192-213) run on the device; same result as the host
-    statement of the rule applied to the plain export."""
-    from nbmf_mm_b200.solver import final_simplex_cleanup, make_problem, prepare_data
+def test_solver_tail_on_device_equals_the_oracle_rule(dtype):
+    """fp64 export + final simplex clean-up (_solver.py:192-213) run on the device; same result as the oracle's
+    restatement of the rule (pinned to the reference by the golden trajectories) applied to the plain export."""
+    from nbmf_oracle import final_simplex_cleanup
+    from nbmf_mm_b200.solver import make_problem, prepare_data
     X, mask = _xy(257, 130, seed=8)
     data = prepare_data(X, mask, transpose=False, dtype=dtype, device=None)
     rs = np.random.RandomState(1)

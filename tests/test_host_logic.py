@@ -5,7 +5,8 @@ import pytest
 
 from nbmf_mm_b200 import NBMF, NBMFMM, BitMatrix
 from nbmf_mm_b200.bits import words_per_row
-from nbmf_mm_b200.solver import _row_shard, final_simplex_cleanup
+from nbmf_mm_b200.solver import _row_shard
+from nbmf_oracle import final_simplex_cleanup       # the rule itself lives in the oracle; the product applies it on the device
 from nbmf_mm_b200._utils import check_is_fitted, generate_synthetic_binary_data
 
 

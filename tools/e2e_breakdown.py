@@ -27,7 +27,6 @@ def wrap(mod, name):
     setattr(mod, name, g)
 for cls, names in ((D.DeviceProblem, ["__init__", "set_bits", "set_factors", "fit", "simplex_deviation", "get_factors_f64", "close"]),):
     for nm in names: wrap(cls, nm)
-wrap(S, "final_simplex_cleanup")
 wrap(S.PreparedData, "finish")
 for rep in range(2):
     marks.clear()
