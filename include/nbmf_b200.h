@@ -192,6 +192,16 @@ int nbmf_comm_destroy(void* comm);
 /* engine actually selected for this context: NBMF_ENGINE_SIMT or NBMF_ENGINE_TENSOR */
 int nbmf_engine(nbmf_ctx* ctx);
 
+/* ---- the init stream of the reference for one row shard (host function, no GPU) ----
+ * out[i] = lo + (hi - lo) * u_i for the `count` doubles that follow `skip` doubles in the stream of
+ * numpy.random.RandomState(seed) -- the legacy MT19937 stream nbmf_mm_solver draws W_init (m x k) and then H_init (k x n)
+ * from (_solver.py:102-103,126-129), bit for bit.  `skip` is reached by polynomial jump-ahead, not by drawing: a rank of
+ * a row-sharded fit produces rows [r0, r1) of W_init (skip = r0 * k) and H_init (skip = m * k) without generating the
+ * rows of the other ranks.  state_out (nullable, 625 x uint32): the generator state afterwards (key[624], pos), in the
+ * layout numpy.random.set_state takes, so that a caller can leave the global stream where the reference leaves it. */
+int nbmf_mt19937_uniform(uint32_t seed, uint64_t skip, uint64_t count, double lo, double hi, double* out_host,
+                         uint32_t* state_out_host);
+
 /* ---- measurement helpers ---- */
 /* sustained FMA-pipe throughput (TFLOP/s) of packed FFMA2 (dtype F32) or DFMA (F64); synchronises */
 int nbmf_fma_peak(int dtype, int32_t iters, void* scratch_dev, void* stream, double* tflops_host);

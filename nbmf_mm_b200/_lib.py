@@ -78,6 +78,7 @@ SIGNATURES = {
     "nbmf_comm_attach": (_INT, [_P, _P, _I32, _I32]),
     "nbmf_comm_destroy": (_INT, [_P]),
     "nbmf_engine": (_INT, [_P]),
+    "nbmf_mt19937_uniform": (_INT, [C.c_uint32, C.c_uint64, C.c_uint64, _DBL, _DBL, _P, _P]),
     "nbmf_fma_peak": (_INT, [_INT, _I32, _P, _P, C.POINTER(_DBL)]),
     "nbmf_profile_enable": (_INT, [_P, _INT]),
     "nbmf_profile_read": (_INT, [_P, C.POINTER(_DBL), C.POINTER(_I32), C.POINTER(_DBL), C.POINTER(_I32)]),

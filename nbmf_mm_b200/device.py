@@ -387,7 +387,7 @@ class DeviceProblem:
         self._call("nbmf_simplex_deviation", C.byref(dev))
         return float(dev.value)
 
-    def get_factors_f64(self, normalize_w=False, out=None):
+    def get_factors_f64(self, normalize_w=False, out=None, gather=None):
         """Host fp64 copies of W (m x k) and H (k x n); conversion to fp64 and the optional row renormalisation
         of the solver tail (``_solver.py:200-204``) run on the device.  ``out`` = (W, H) pinned host fp64 tensors
         (``pinned_result_buffers``) makes the D2H copy a plain DMA and the returned arrays views of them: at
@@ -396,6 +396,18 @@ class DeviceProblem:
         W = torch.empty((self.m, self.k), dtype=torch.float64, device=self.dev)
         H = torch.empty((self.k, self.n), dtype=torch.float64, device=self.dev)
         self._call("nbmf_get_factors_f64", _ptr(W), _ptr(H), 1 if normalize_w else 0)
+        if gather is not None:
+            # row shards: all-gather the W blocks on the devices.  ``gather = (m_total, rows_per_rank, world)``: every
+            # rank contributes rows_per_rank rows (its block, zero padded), rank r's block starts at r * rows_per_rank
+            import torch.distributed as dist
+            m_total, per, world = gather
+            mine = W
+            if self.m != per:
+                mine = torch.zeros((per, self.k), dtype=torch.float64, device=self.dev)
+                mine[: self.m] = W
+            full = torch.empty((per * world, self.k), dtype=torch.float64, device=self.dev)
+            dist.all_gather_into_tensor(full, mine)
+            W = full[:m_total]
         if out is None:
             return W.cpu().numpy(), H.cpu().numpy()
         Wh, Hh = out
@@ -527,14 +539,15 @@ _COMM_CACHE = {}
 PIN_THRESHOLD = 1 << 22        # factor elements from which pinned host staging pays (torch caches pinned blocks)
 
 
-def pinned_factor_buffers(m, k, n, dtype):
+def pinned_factor_buffers(m, k, n, dtype, result_rows=None):
     """Pinned host tensors for a large problem's factors: (W0, H0) in the compute dtype for the upload of the
     inits and (W, H) in fp64 for the results.  Page-locking ~0.4 GB costs ~0.15 s the first time; the solver calls
     this while the H2D copies of the bit planes are in flight, when the host has nothing else to do."""
     torch = _torch()
     tdt = getattr(torch, np.dtype(dtype).name)
     mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
-    return (mk((m, k), tdt), mk((k, n), tdt)), (mk((m, k), torch.float64), mk((k, n), torch.float64))
+    return (mk((m, k), tdt), mk((k, n), tdt)), (mk((m if result_rows is None else result_rows, k), torch.float64),
+                                                mk((k, n), torch.float64))
 
 
 def destroy_cached_comms():

@@ -186,6 +186,59 @@ def resolve_engine(engine, *, dtype, vkind, k, eps, m_total, n):
     return "tensor" if eligible and m_total >= 512 and n >= 512 else "simt"
 
 
+def draw_shard_inits(seed, m, n, k, r0, r1, *, h_part=(0, 1), set_global_state=True):
+    """Rows [r0, r1) of ``W_init`` and part ``h_part = (i, parts)`` of the flattened ``H_init`` exactly as
+    ``np.random.seed(seed); uniform(0.1, 0.9, (m, k)); uniform(0.1, 0.9, (k, n))`` would produce them
+    (``_solver.py:102-103,126-129``), without drawing what lies before them: ``nbmf_mt19937_uniform`` jumps ahead in the
+    MT19937 stream.  Returns ``(W_rows, H_flat_part, (c0, c1))`` with ``H_init.ravel()[c0:c1] == H_flat_part``.
+    ``set_global_state``: leave NumPy's global stream where the reference's two draws leave it."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    seed = int(seed) & 0xFFFFFFFF
+
+    def draw(skip, count, state=None):
+        out = np.empty(int(count), dtype=np.float64)
+        _lib.check(lib.nbmf_mt19937_uniform(seed, int(skip), int(count), 0.1, 0.9, out.ctypes.data,
+                                            None if state is None else state.ctypes.data), "nbmf_mt19937_uniform")
+        return out
+
+    W_rows = draw(r0 * k, (r1 - r0) * k).reshape(r1 - r0, k)
+    i, parts = h_part
+    per = (k * n + parts - 1) // parts
+    c0, c1 = min(k * n, i * per), min(k * n, (i + 1) * per)
+    H_part = draw(m * k + c0, c1 - c0)
+    if set_global_state:
+        st = np.zeros(625, dtype=np.uint32)
+        draw(m * k + k * n, 0, st)
+        np.random.set_state(("MT19937", st[:624], int(st[624])))
+    return W_rows, H_part, (c0, c1)
+
+
+def _gather_h_parts(H_part, k, n, world, dtype, dev):
+    """Every rank drew 1/world of the flattened H_init: all-gather the parts on the devices (fp64 over NVLink) and
+    convert to the compute dtype there.  Returns the (k x n) device tensor ``set_factors`` takes."""
+    import torch
+    import torch.distributed as dist
+    per = (k * n + world - 1) // world
+    mine = torch.zeros(per, dtype=torch.float64, device=dev)
+    mine[: H_part.size].copy_(torch.from_numpy(H_part), non_blocking=False)
+    full = torch.empty(per * world, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(full, mine)
+    return full[: k * n].view(k, n).to(getattr(torch, np.dtype(dtype).name))
+
+
+def _rank_block(A, r0, r1, transpose):
+    """Rows [r0, r1) of the INTERNAL orientation of a host input (dense, scipy sparse or BitMatrix)."""
+    if isinstance(A, BitMatrix):
+        return A.rows(r0, r1)
+    if hasattr(A, "tocsr"):
+        A = A.tocsr()
+        return A[:, r0:r1] if transpose else A[r0:r1]
+    A = np.asarray(A)
+    return A[:, r0:r1] if transpose else A[r0:r1]
+
+
 def _row_shard(m, rank, world):
     """Contiguous row block of this rank (boundaries on multiples of 32 rows)."""
     per = (m + world - 1) // world
@@ -245,20 +298,29 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
                              "use fewer ranks")
     else:
         r0, r1 = 0, m
+    # distributed=True: every rank was handed the FULL matrix; only this rank's row block (internal orientation) is
+    # uploaded and packed.  (Bit-packed input with dir-beta cannot be sliced by columns on the host: that one case still
+    # packs the whole plane and slices after the device-side transpose.)
+    local_input = shard is not None
+    if world > 1 and shard is None and not (transpose and isinstance(Y, BitMatrix)):
+        Y, mask = _rank_block(Y, r0, r1, transpose), (None if mask is None else _rank_block(mask, r0, r1, transpose))
+        shape = tuple(Y.shape)
+        local_input = True
     # large problems: the inits go up from, and the results come back into, pinned host memory (plain DMA instead of
     # staged pageable copies and page faults of a fresh array).  Page-lock BEFORE the big copies start: cudaHostAlloc
     # stalls DMA submission while it runs (measured: 0.4 s lost when it overlapped the bit-plane upload).
     pinned = None
+    full_w = world > 1 and shard is None                   # every rank returns the whole W (all-gathered on the devices)
     if (r1 - r0) * k + k * n >= PIN_THRESHOLD:
         require_cuda(device)
-        pinned = pinned_factor_buffers(r1 - r0, k, n, dtype)
+        pinned = pinned_factor_buffers(r1 - r0, k, n, dtype, result_rows=m if full_w else None)
     # Host bit planes in the internal orientation are STREAMED: row chunks go up on a copy stream and each chunk is
     # prepared on the compute stream as it lands (P &= M, mask count, re-tiling for the tensor engine) while the next
     # ones are still crossing PCIe.  Other inputs: asynchronous H2D copies now, device-side preparation in
     # data.finish().  Either way the inits are drawn on the host while the copies are in flight.
     streamed = (isinstance(Y, BitMatrix) and not Y.is_device and not transpose
                 and (mask is None or (isinstance(mask, BitMatrix) and not mask.is_device))
-                and (world == 1 or shard is not None))
+                and (world == 1 or local_input))
     data = prob = None
     if streamed:
         if world > 1:
@@ -274,33 +336,52 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     else:
         data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, defer=True, dense_storage=dense_storage,
                             check_range=check_range)
-        assert (data.m, data.n) == ((r1 - r0) if shard is not None else m, n)
+        assert (data.m, data.n) == ((r1 - r0) if local_input else m, n)
     try:
         if transpose and W_init is not None and H_init is not None:      # _solver.py:122-123
             W_init, H_init = np.asarray(H_init).T, np.asarray(W_init).T
-        rng = np.random
-        if world > 1 and random_state is None and (W_init is None or H_init is None):
-            # every rank is its own process with its own global stream: without a seed the ranks would start from
-            # different "global" H (and stop at different iterations -> mismatched collectives).  Rank 0 draws a seed
-            # from its global stream and every rank draws the inits from that seed.
+        rng, shard_seed = np.random, None
+        if world > 1 and W_init is None and H_init is None:
+            # Row shards: a rank needs rows [r0, r1) of W_init and its share of H_init.  Drawing the whole (m x k) W_init
+            # on every rank to reach them costs 0.25 s at 10^6 x 32 and does not shrink with the number of GPUs, so the
+            # reference's stream is entered by MT19937 jump-ahead (draw_shard_inits: same numbers, same global-stream
+            # position afterwards).  Without a seed every rank (its own process, its own global stream) would start from
+            # a different "global" H and stop at different iterations: rank 0 draws the seed and broadcasts it.
+            shard_seed = random_state
+            if shard_seed is None:
+                import torch.distributed as dist
+                box = [int(np.random.randint(0, 2**31 - 1)) if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                shard_seed = box[0]
+        elif world > 1 and random_state is None and (W_init is None or H_init is None):
             import torch.distributed as dist
             box = [int(np.random.randint(0, 2**31 - 1)) if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             rng = np.random.RandomState(box[0])
-        if W_init is None:
-            W_init = rng.uniform(0.1, 0.9, (m, k))            # W first, then H: _solver.py:126-129
-        if H_init is None:
-            H_init = rng.uniform(0.1, 0.9, (k, n))
-        W_init = np.asarray(W_init, dtype=np.float64)
-        H_init = np.asarray(H_init, dtype=np.float64)
-        if tuple(W_init.shape) != (m, k) or tuple(H_init.shape) != (k, n):
-            raise ValueError(f"W_init / H_init have shapes {W_init.shape} / {H_init.shape}, expected {(m, k)} / {(k, n)}")
-        W_local = W_init[r0:r1]
+        H_part = None
+        if shard_seed is not None:
+            W_local, H_part, _ = draw_shard_inits(shard_seed, m, n, k, r0, r1, h_part=(rank, world),
+                                                  set_global_state=random_state is not None)
+            n_w_init, n_h_init = W_local.size, H_part.size
+        else:
+            if W_init is None:
+                W_init = rng.uniform(0.1, 0.9, (m, k))        # W first, then H: _solver.py:126-129
+            if H_init is None:
+                H_init = rng.uniform(0.1, 0.9, (k, n))
+            W_init = np.asarray(W_init, dtype=np.float64)
+            H_init = np.asarray(H_init, dtype=np.float64)
+            if tuple(W_init.shape) != (m, k) or tuple(H_init.shape) != (k, n):
+                raise ValueError(f"W_init / H_init have shapes {W_init.shape} / {H_init.shape}, expected {(m, k)} / {(k, n)}")
+            W_local = W_init[r0:r1]
+            n_w_init, n_h_init = W_local.size, H_init.size
         W_up, H_up, result_buffers = W_local, H_init, None
         if pinned is not None:
             (W_up, H_up), result_buffers = pinned
             W_up.numpy()[...] = W_local                        # fp64 -> compute dtype on the host, copies still in flight
-            H_up.numpy()[...] = H_init
+            if H_part is None:
+                H_up.numpy()[...] = H_init
+        if H_part is not None:
+            H_up = _gather_h_parts(H_part, k, n, world, dtype, require_cuda(device))
     except BaseException:
         if prob is not None:                                   # streamed upload in flight: release the context
             prob.close()
@@ -317,7 +398,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         data.finish()
         data_h2d = data.h2d_bytes
         n_obs_global = data.n_obs
-        if shard is not None:
+        if local_input:
             if world > 1:
                 n_obs_global = all_ranks_sum(data.n_obs)
         elif world > 1:
@@ -348,21 +429,18 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
             t = torch.tensor([dev if np.isfinite(dev) else np.inf], dtype=torch.float64, device=require_cuda(device))
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dev = float(t.item())
-        W_loc, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dev) and dev > 1e-9), out=result_buffers)
+        norm = bool(np.isfinite(dev) and dev > 1e-9)
+        if full_w:
+            # every rank returns the whole W: the fp64 row blocks are all-gathered on the devices (equal-sized,
+            # zero-padded blocks of _row_shard's stride) and cross PCIe once, into pinned memory
+            W, H = prob.get_factors_f64(normalize_w=norm, out=result_buffers,
+                                        gather=(m, _row_shard(m, 0, world)[1], world))
+            n_w_out = (r1 - r0) * k
+        else:
+            W, H = prob.get_factors_f64(normalize_w=norm, out=result_buffers)
+            n_w_out = W.size
     finally:
         prob.close()
-
-    if shard is not None:
-        W = W_loc
-    elif world > 1:
-        import torch.distributed as dist
-        parts = [None] * world
-        dist.all_gather_object(parts, (r0, W_loc))
-        W = np.zeros((m, k), dtype=np.float64)
-        for pr0, pw in parts:
-            W[pr0:pr0 + pw.shape[0]] = pw
-    else:
-        W = W_loc
 
     losses = [np.float64(v) for v in losses_arr]
     if verbose > 0:                                        # same lines as _solver.py:165-166,172-173
@@ -372,8 +450,9 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
             print(f"Converged at iteration {n_iter - 1}")
     if stats is not None:
         isz = np.dtype(dtype).itemsize                     # factors cross PCIe in the compute dtype
-        stats.update(h2d_bytes=data_h2d + isz * (W_local.size + H_init.size), converged=converged, streamed=streamed,
-                     d2h_bytes=isz * (W_loc.size + H.size) + losses_arr.nbytes, world=world, engine=prob.engine)
+        stats.update(h2d_bytes=data_h2d + isz * n_w_init + (8 if H_part is not None else isz) * n_h_init, converged=converged, streamed=streamed,
+                     d2h_bytes=8 * (W.size + H.size) + losses_arr.nbytes, w_rows_local=n_w_out // max(k, 1), world=world,
+                     engine=prob.engine)
 
     W_final, H_final = W, H                                # (m x k), (k x n) internal
     if transpose:                                          # _solver.py:182-184

@@ -122,3 +122,33 @@ def test_restart_partition_keeps_what_a_sequential_loop_keeps(tmp_path, n_init):
     losses = np.random.default_rng(7).permutation(n_init).astype(np.float64) // 2
     want = int(np.argmin(losses))                                # first index among ties
     assert int(np.load(out)["idx"]) == want
+
+
+def _init_worker(rank, world, port, m, n, k, seed, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nbmf_mm_b200.solver import _gather_h_parts, draw_shard_inits
+        r0, r1 = _row_shard(m, rank, world)
+        W_local, H_part, _ = draw_shard_inits(seed, m, n, k, r0, r1, h_part=(rank, world), set_global_state=True)
+        H = _gather_h_parts(H_part, k, n, world, "float64", torch.device("cpu")).numpy()
+        after = np.random.uniform(0.1, 0.9, 4)                  # the global stream sits where the reference leaves it
+        np.savez(f"{out}.{rank}.npz", W=W_local, H=H, r0=r0, after=after)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_inits_equal_the_reference_stream(tmp_path):
+    """Row shards enter the reference's init stream (seed; W_init m x k; H_init k x n: _solver.py:102-103,126-129) by
+    MT19937 jump-ahead: each rank draws only its W rows and its 1/world of H_init, the H parts are all-gathered."""
+    m, n, k, seed = 5000, 333, 9, 5
+    out = str(tmp_path / "init")
+    mp.spawn(_init_worker, args=(2, _free_port(), m, n, k, seed, out), nprocs=2, join=True)
+    rs = np.random.RandomState(seed)
+    W = rs.uniform(0.1, 0.9, (m, k)); H = rs.uniform(0.1, 0.9, (k, n)); after = rs.uniform(0.1, 0.9, 4)
+    for rank in range(2):
+        z = np.load(f"{out}.{rank}.npz")
+        r0 = int(z["r0"])
+        assert np.array_equal(z["W"], W[r0:r0 + z["W"].shape[0]]) and np.array_equal(z["H"], H)
+        assert np.array_equal(z["after"], after)

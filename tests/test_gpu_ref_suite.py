@@ -40,10 +40,10 @@ def test_reference_suite_passes_unmodified_through_the_shim(tmp_path):
     probe = subprocess.run([sys.executable, "-c", "import nbmf_mm, nbmf_mm_b200; print(nbmf_mm.__file__); "
                             "assert nbmf_mm.NBMF is nbmf_mm_b200.NBMF"], cwd=tmp_path, env=env, capture_output=True, text=True)
     assert probe.returncode == 0 and str(ROOT / "nbmf_mm") in probe.stdout, probe.stdout + probe.stderr
-    m = re.search(r"(\d+) passed", out)
-    passed = int(m.group(1)) if m else 0
-    failed = int(re.search(r"(\d+) failed", out).group(1)) if re.search(r"(\d+) failed", out) else 0
-    errors = int(re.search(r"(\d+) error", out).group(1)) if re.search(r"(\d+) error", out) else 0
+    # the reference's pytest.ini adds -q on top of ours: no summary line, so count the -rA report lines
+    passed = len(re.findall(r"^PASSED ", out, flags=re.M))
+    failed = len(re.findall(r"^FAILED ", out, flags=re.M))
+    errors = len(re.findall(r"^ERROR ", out, flags=re.M))
     print(tail)
     assert proc.returncode == 0 and failed == 0 and errors == 0, tail
-    assert passed >= 45, tail          # 53 collected upstream; a handful skip on their own
+    assert passed >= 50, tail          # 53 collected upstream: 51 pass, 2 skip on their own (pyreadr absent, upstream skip mark)

@@ -100,7 +100,7 @@ int main() {
   const int count = 4096;
   printf("%-4s %-5s %-7s %16s %24s\n", "form", "N", "issuers", "issue cyc/mma", "aggregate cyc/mma (all)");
   for (int mode = 0; mode < 2; ++mode)
-    for (int N : {32, 64})
+    for (int N : {16, 32, 64})
       for (int issuers : {1, 2, 3, 4}) {
         for (int rep = 0; rep < 2; ++rep) {
           bench_kernel<<<1, 128, 49152 + 1024>>>(mode, N, 1, count, d_out, issuers);
@@ -114,7 +114,7 @@ int main() {
   // latency of a dependent accumulate chain
   printf("%-4s %-5s %-7s %16s %24s\n", "form", "N", "nacc", "issue cyc/mma", "total cyc/mma");
   for (int mode = 0; mode < 2; ++mode)
-    for (int N : {32, 64, 128, 256})
+    for (int N : {16, 32, 64, 128, 256})
       for (int nacc : {1, 2, 4, 8}) {
         if (nacc * N > 256) continue;
         for (int rep = 0; rep < 2; ++rep) {
