@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--configs", action="store_true", help="time BASELINE configs 1, 2, 3, 5 end to end instead (text lines)")
+    ap.add_argument("--restarts-only", action="store_true", help="with --configs: only configs[4] (64 restarts, K sweep), as the multi-GPU mode runs it")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-warmup", type=int, default=1, help="untimed end-to-end calls before the timed one")
     ap.add_argument("--no-cpu", action="store_true")
@@ -378,7 +379,7 @@ def run_ours(a):
         tr = None
     if tr:
         common["traffic"] = tr["h_pass"]
-        common["traffic_detail"] = dict(tr, unit="bytes per launch", source="profiles/r01_ncu_dram_traffic_full_size.csv")
+        common["traffic_detail"] = dict(tr, unit="bytes per launch (regenerated per build by tools/ncu_regen.py)")
     if engine == "tensor":
         # kind::tf32 runs at half the bf16 rate; the kernels are timed inside a long step -> sustained figure
         bf16 = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")
@@ -402,14 +403,15 @@ def run_ours(a):
         # (ratio arithmetic, tf32 / bf16 splits, masking, TMEM traffic, barrier code).  Executed warp instructions per
         # entry from the committed ncu capture x entries / launch time, against 4 issue slots per SM and clock.
         clk = (sampler.summary().get("sm_mhz") or sampler.max_mhz or 1965) * 1e6
-        wi = {"h_pass": 1038796792 / (65536.0 * 32768.0), "w_pass": 955308628 / (65536.0 * 32768.0)}
-        roofline["issue_slots"] = {
-            "warp_instructions_per_entry": wi,
-            "source": "smsp__inst_executed.sum in profiles/r01_ncu_full_tensor_pass_kernels_final_65536x32768_k32.txt",
-            "peak": "4 warp instructions per clock and SM x 148 SMs at the median SM clock of the timed region",
-            "h_pass_frac": (wi["h_pass"] * entries_local / (h_avg_ms * 1e-3) / (4 * 148 * clk)) if h_cnt else None,
-            "w_pass_frac": (wi["w_pass"] * entries_local / (w_avg_ms * 1e-3) / (4 * 148 * clk)) if w_cnt else None,
-        }
+        if tr and tr.get("h_pass_warp_instructions") and tr.get("w_pass_warp_instructions"):
+            wi = {"h_pass": tr["h_pass_warp_instructions"] / entries_local, "w_pass": tr["w_pass_warp_instructions"] / entries_local}
+            roofline["issue_slots"] = {
+                "warp_instructions_per_entry": wi,
+                "source": f"smsp__inst_executed.sum of this shape in {tr.get('source')} (tools/ncu_regen.py, this build)",
+                "peak": "4 warp instructions per clock and SM x 148 SMs at the median SM clock of the timed region",
+                "h_pass_frac": (wi["h_pass"] * entries_local / (h_avg_ms * 1e-3) / (4 * 148 * clk)) if h_cnt else None,
+                "w_pass_frac": (wi["w_pass"] * entries_local / (w_avg_ms * 1e-3) / (4 * 148 * clk)) if w_cnt else None,
+            }
     else:
         roofline = dict(common, **{
             "bound": "fp32" if a.dtype == "float32" else "fp64", "kernel": "h_pass_kernel (H half-step + fused NLL)",
@@ -433,8 +435,14 @@ def run_ours(a):
             return nbmf_mm_solver(BitMatrix(Ph, (m_local, N)), K, max_iter=steps, tol=0.0, alpha=1.2, beta=1.2,
                                   mask=BitMatrix(Mh, (m_local, N)), random_state=0, dtype=a.dtype, device=dev,
                                   distributed=True, shard=(r0, M_rows), stats=st, engine=a.engine)
-        for _ in range(max(0, a.e2e_warmup)):              # untimed, like the W warm-up steps of the device-timed figure:
-            e2e_call({})                                   # page-locked factor staging and allocator pools exist afterwards
+        cold = None
+        for i in range(max(0, a.e2e_warmup)):              # like the W warm-up steps of the device-timed figure: page-locked
+            barrier()                                      # factor staging, allocator pools, the NCCL communicator and the
+            t0 = time.perf_counter()                       # jump polynomials of the init stream exist afterwards.  The
+            e2e_call({})                                   # first call is timed too and reported as `cold_seconds`.
+            barrier()
+            if i == 0:
+                cold = max_over_ranks(time.perf_counter() - t0)
         stats = {}
         barrier()
         t0 = time.perf_counter()
@@ -444,7 +452,8 @@ def run_ours(a):
         assert out[4] == steps
         e2e = {"value": M_rows * N * steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": stats["h2d_bytes"] / steps, "d2h_bytes_per_step": stats["d2h_bytes"] / steps,
-               "seconds": dt, "warmup_calls": max(0, a.e2e_warmup), "api": "nbmf_mm_b200.nbmf_mm_solver(BitMatrix(pinned host), mask=BitMatrix(pinned host), "
+               "seconds": dt, "warmup_calls": max(0, a.e2e_warmup), "cold_seconds": cold,
+               "cold_value": (M_rows * N * steps / cold) if cold else None, "api": "nbmf_mm_b200.nbmf_mm_solver(BitMatrix(pinned host), mask=BitMatrix(pinned host), "
                                     "max_iter=steps, tol=0, dtype=float32): H2D of both bit planes and the inits, "
                                     "the fit loop, D2H of W, H and the loss history",
                "final_loss": float(out[2][-1])}
@@ -544,6 +553,53 @@ def run_configs():
         line(f"cfg5 64 restarts 1226x285 K={k} float32", gs, 200 * 64, cs * 64, 200 * 64, L.size, "(CPU: one restart timed, x 64)")
 
 
+def run_config5_restarts(a):
+    """`python bench.py --configs --gpus N` (under torchrun for N > 1): BASELINE.json configs[4] -- n_init = 64 restarts on
+    lastfm-shaped data, K sweep, FP32 -- with the restarts partitioned across the N GPUs (`distributed="restarts"`: restart r
+    on rank r % N, no data-path collective, the best restart's factors broadcast at the end).  One JSON line per K on rank
+    0: 64 restarts x 200 iterations, wall time of the whole `NBMF(n_init=64).fit` call, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from nbmf_mm_b200 import NBMF
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = (np.random.default_rng(0).random((1226, 285)) < 0.0435).astype(np.float64)
+    n_init, iters = 64, 200
+    for k in (6, 8, 12, 16, 24, 32, 48, 64):
+        best = None
+        for rep in range(3):                                   # first repetition warms up (module load, pinned pools, graphs)
+            est = NBMF(n_components=k, n_init=n_init, random_state=0, max_iter=iters, tol=0.0, dtype="float32",
+                       distributed="restarts" if world > 1 else False, device=dev)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            est.fit(L)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            if rep > 0:
+                best = dt if best is None else min(best, dt)
+        if rank == 0:
+            print(json.dumps({"config": "configs[4]: 64 restarts on 1226x285 (4.35% ones), 200 iterations each, float32",
+                              "k": k, "n_gpus": world, "seconds": best, "unit": UNIT,
+                              "value": L.size * iters * n_init / best, "best_restart": int(est.best_init_),
+                              "final_loss": float(est.loss_curve_[-1]), "engine": est.transfer_stats_.get("engine"),
+                              "restarts_per_gpu": -(-n_init // world)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 class C_double:
     def __init__(self):
         import ctypes
@@ -567,7 +623,9 @@ def measured_peaks():
 
 if __name__ == "__main__":
     args = parse()
-    if args.configs:
+    if args.configs and (args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.restarts_only):
+        run_config5_restarts(args)
+    elif args.configs:
         run_configs()
     elif args.impl == "reference":
         run_reference_arm(args)

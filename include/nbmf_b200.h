@@ -54,7 +54,7 @@ extern "C" {
 
 #define NBMF_ENGINE_AUTO 0   /* tensor engine when eligible and m, n >= 512, else SIMT */
 #define NBMF_ENGINE_SIMT 1   /* packed-FFMA2 CUDA-core kernels: every dtype / K <= 64 / layout */
-#define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, TF32 + bf16 split precision: float32, bit-packed V, K <= 32, eps >= 1e-9 */
+#define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, TF32 + bf16 split precision: float32, bit-packed V, K <= 64, eps >= 1e-9 */
 
 typedef struct nbmf_ctx nbmf_ctx;
 
@@ -125,11 +125,22 @@ int nbmf_set_data_bits(nbmf_ctx* ctx, const uint32_t* p_bits_dev, const uint32_t
  * are consecutive, start on multiples of 128 rows and the last one ends at m.  nbmf_ingest_bits_end synchronises the
  * stream and returns the mask count (m * n without a mask); nbmf_set_n_obs installs the normaliser of the objective
  * (the count itself, or its sum over the row shards of a multi-GPU fit). */
+/* 1 while the context still reads the caller's row-major planes, 0 once it does not: the tensor engine works on its own
+ * re-tiled copies (and takes the per-row observed counts of the Duchi projection when the planes are handed over), so the
+ * caller may free or reuse the planes after nbmf_set_data_bits / nbmf_ingest_bits_end -- stream order makes a free or an
+ * overwrite enqueued on the same stream afterwards safe.  At config 4 that is 25 GB of the 62.5 GB a fit would hold. */
+int nbmf_planes_in_use(nbmf_ctx* ctx);
 int nbmf_ingest_bits_begin(nbmf_ctx* ctx, uint32_t* p_bits_dev, const uint32_t* m_bits_dev);
 int nbmf_ingest_bits_rows(nbmf_ctx* ctx, int64_t row0, int64_t row1);
 int nbmf_ingest_bits_end(nbmf_ctx* ctx, double* mask_count_host);
 int nbmf_set_n_obs(nbmf_ctx* ctx, double n_obs);
 int nbmf_set_data_dense(nbmf_ctx* ctx, const void* vm_dev, const uint32_t* m_bits_dev);
+/* Weighted observation mask (values other than 0 / 1): the reference multiplies by the mask VALUES (Y * mask for the H
+ * half-step and the loss, (1 - Y).T * mask.T for the W half-step: _solver.py:30-32; count_nonzero(mask) normalises the
+ * loss, :155).  V * mask is what nbmf_set_data_dense takes (NBMF_V_DENSE layout in cfg.dtype, also for a binary V), its bit
+ * plane is then (mask != 0); wm_dev holds the mask values in the same dense layout and dtype ((1 - V) * mask = mask -
+ * V * mask).  Call after nbmf_set_data_dense; NULL goes back to a 0/1 mask.  Reference mask semantics only. */
+int nbmf_set_mask_weights(nbmf_ctx* ctx, const void* wm_dev);
 /* W_init (m x k) / H_init (k x n) in cfg.dtype; normalize_w != 0 divides every W row by its sum
  * (_solver.py:132-136).  Either pointer may be NULL to keep the current factor.  Resets the loop state. */
 int nbmf_set_factors(nbmf_ctx* ctx, const void* w_dev, const void* h_dev, int normalize_w);
@@ -163,8 +174,8 @@ int nbmf_fit_begin(nbmf_ctx* ctx, int32_t max_iter, double tol);
 int nbmf_fit_enqueue(nbmf_ctx* ctx, int32_t n_iters);
 /* non-blocking unless wait != 0: fetch (done, n_iter) of the work enqueued so far */
 int nbmf_fit_poll(nbmf_ctx* ctx, int wait, int32_t* done_host, int32_t* n_iter_host);
-/* Batched small fits (n_init restarts, repeated fits of one data set with equal hyper-parameters): n contexts of
- * identical configuration and data planes, workspaces at a uniform byte stride inside one allocation (the leader's
+/* Batched small fits (n_init restarts, alpha / beta grids over one data set): n contexts of identical configuration
+ * (alpha and beta may differ from context to context) and data planes, workspaces at a uniform byte stride inside one allocation (the leader's
  * first), each with its own factors (nbmf_set_factors) and nbmf_fit_begin.  After nbmf_batch_bind(leader, n, stride)
  * the leader's nbmf_fit_enqueue advances all n fits with one launch per kernel (the Python loop of solver calls in
  * examples/reproduce_magron2022.py:87-117 / README.md:133,144 becomes 5 launches per iteration for the whole batch);

@@ -50,11 +50,13 @@ SIGNATURES = {
     "nbmf_create": (_INT, [C.POINTER(NbmfConfig), _P, _I64, _P, C.POINTER(_P)]),
     "nbmf_destroy": (_INT, [_P]),
     "nbmf_set_data_bits": (_INT, [_P, _P, _P]),
+    "nbmf_planes_in_use": (_INT, [_P]),
     "nbmf_ingest_bits_begin": (_INT, [_P, _P, _P]),
     "nbmf_ingest_bits_rows": (_INT, [_P, _I64, _I64]),
     "nbmf_ingest_bits_end": (_INT, [_P, C.POINTER(_DBL)]),
     "nbmf_set_n_obs": (_INT, [_P, _DBL]),
     "nbmf_set_data_dense": (_INT, [_P, _P, _P]),
+    "nbmf_set_mask_weights": (_INT, [_P, _P]),
     "nbmf_set_factors": (_INT, [_P, _P, _P, _INT]),
     "nbmf_get_factors": (_INT, [_P, _P, _P]),
     "nbmf_simplex_deviation": (_INT, [_P, C.POINTER(_DBL)]),

@@ -39,6 +39,7 @@ struct WPassArgs {
   const uint32_t* P;
   const uint32_t* M;
   const void* Vm;
+  const void* Wm = nullptr;  // dense mode, weighted mask: the mask VALUES [m][ldv] Real (pad 0); NULL = 0/1 mask (bit plane M)
   int64_t ldv;
   int64_t m, n, ldh, wpr;
   int64_t cols_per_split;   // multiple of 128

@@ -106,10 +106,11 @@ struct Plan {
   int64_t h_rows_per_split, w_cols_per_split;
   size_t sz;   // sizeof(Real)
   bool tensor;           // tcgen05 engine (tc_passes.cuh) instead of the SIMT pass kernels
+  int kb;                // tensor engine: K extent the MMAs cover (16 | 32 | 64); padded K (pl.kp) is 32 or 64
   int64_t mpad;          // tensor engine: rows padded to 128
   // workspace offsets
   size_t oW, oH, oHt, oCDpart, oCDsum, oLLpart, oLLsum, oPrior, oG, oQ, oRowcount, oHist, oState, oLoss, total;
-  size_t oWf, oHf, oPc, oMc, oPM;   // tensor engine: formatted factor blocks and re-tiled bit planes
+  size_t oWf, oHf, oPc, oMc, oPM, oColcnt, oFlipcol, oFlipAny;   // tensor engine: formatted factor blocks, re-tiled bit planes, ones per column
   bool strict;
 };
 
@@ -121,6 +122,7 @@ struct nbmf_ctx {
   const uint32_t* P = nullptr;
   const uint32_t* M = nullptr;
   const void* Vm = nullptr;
+  const void* Wm = nullptr;         // dense layout: values of a weighted (non-0/1) mask, or NULL
   bool rowcount_ready = false;
   int64_t ingest_rows = 0;          // rows handed over by nbmf_ingest_bits_rows so far
   // small problems: kGraphIters MM iterations captured once per fit into a CUDA graph (their ~7 launches per iteration
@@ -195,12 +197,13 @@ static int make_plan(const nbmf_config& c, Plan* p) {
     else if (!strcmp(e, "auto")) engine = NBMF_ENGINE_AUTO;
   }
   // eps >= 1e-9: the tensor H pass takes one log per product of four x >= eps (no underflow)
-  const bool eligible = c.dtype == NBMF_F32 && c.vkind == NBMF_V_BITS && c.k <= 32 && c.eps >= 1e-9;
+  const bool eligible = c.dtype == NBMF_F32 && c.vkind == NBMF_V_BITS && c.k <= 64 && c.eps >= 1e-9;
   if (engine == NBMF_ENGINE_TENSOR && !eligible)
-    return fail(NBMF_ERR_UNSUPPORTED, "tensor engine needs float32, bit-packed V, k <= 32 and eps >= 1e-9");
+    return fail(NBMF_ERR_UNSUPPORTED, "tensor engine needs float32, bit-packed V, k <= 64 and eps >= 1e-9");
   p->strict = strict != 0;
   p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR || (engine == NBMF_ENGINE_AUTO && c.m >= 512 && c.n >= 512));
-  if (p->tensor) { p->pl.kp = 32; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
+  p->kb = c.k <= 16 ? 16 : (c.k <= 32 ? 32 : 64);
+  if (p->tensor) { p->pl.kp = c.k <= 32 ? 32 : 64; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
   const int occ = 1;
   p->sz = c.dtype == NBMF_F32 ? 4 : 8;
   p->wpr = nbmf_words_per_row(c.n);
@@ -240,10 +243,13 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   p->oState = take(sizeof(FitState));
   p->oLoss = take(64);
   p->mpad = (c.m + 127) / 128 * 128;
-  p->oWf = p->oHf = p->oPc = p->oMc = p->oPM = 0;
+  p->oWf = p->oHf = p->oPc = p->oMc = p->oPM = p->oColcnt = p->oFlipcol = p->oFlipAny = 0;
   if (p->tensor) {
-    p->oWf = take((size_t)p->mpad * 128 * 4);
-    p->oHf = take((size_t)p->ldh * 128 * 4);
+    p->oWf = take((size_t)p->mpad * kp * 16);           // per row: hi + corr + transposed hi + corr = 4 x KT x 4 bytes
+    p->oHf = take((size_t)p->ldh * kp * 16);
+    p->oColcnt = take((size_t)p->ldh * 4);
+    p->oFlipcol = take((size_t)p->ldh * 4);
+    p->oFlipAny = take(64);
     p->oPc = take((size_t)p->ldh * p->mpad / 8);
     if (p->strict) p->oMc = take((size_t)p->ldh * p->mpad / 8);
     p->oPM = take((size_t)p->mpad * p->wpr * 8);
@@ -365,9 +371,10 @@ extern "C" int64_t nbmf_workspace_bytes(const nbmf_config* cfg) {
   return (int64_t)p.total;
 }
 
-__global__ void reset_state_kernel(FitState* s) {
+__global__ void reset_state_kernel(FitState* s, double alpha, double beta) {
   s->done = 0; s->it = 0; s->n_hist = 0; s->converged = 0;
   s->prev_loss = INFINITY; s->prior_a = 0.0; s->prior_b = 0.0;
+  s->alpha = alpha; s->beta = beta;
 }
 
 extern "C" int nbmf_create(const nbmf_config* cfg, void* ws, int64_t ws_bytes, void* stream, nbmf_ctx** out) {
@@ -387,8 +394,12 @@ extern "C" int nbmf_create(const nbmf_config* cfg, void* ws, int64_t ws_bytes, v
   if (!c->host_state) { delete c; return cuda_fail(cudaGetLastError(), "cudaMallocHost"); }
   cudaError_t e = cudaEventCreateWithFlags(&c->poll_ev, cudaEventDisableTiming);
   if (e != cudaSuccess) { pinned_state_put(c->host_state); delete c; return cuda_fail(e, "cudaEventCreate"); }
-  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state());
+  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state(), c->cfg.alpha, c->cfg.beta);
   g_launches += 1;
+  if (c->p.tensor) {                                   // "no column flips" until flip_cols_kernel says otherwise
+    cudaMemsetAsync(c->at<uint32_t>(c->p.oFlipcol), 0, (size_t)c->p.ldh * 4, c->st);
+    cudaMemsetAsync(c->at<int>(c->p.oFlipAny), 0, 64, c->st);
+  }
   *out = c;
   return NBMF_OK;
 }
@@ -412,6 +423,27 @@ extern "C" int nbmf_destroy(nbmf_ctx* c) {
   return NBMF_OK;
 }
 
+// Tensor engine: the pass kernels read the re-tiled copies only; the one remaining reader of the caller's row-major
+// mask plane is the per-row observed count of the Duchi projection, taken here, so that the caller may free or reuse
+// its planes right after handing them over (nbmf_planes_in_use): 25 GB of 62.5 GB at config 4.
+static int eager_rowcount(nbmf_ctx* c) {
+  if (c->cfg.projection == NBMF_PROJ_DUCHI && c->M && !c->rowcount_ready) {
+    launch_rowcount(c->cfg.dtype, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->ws + c->p.oRowcount, c->st);
+    CHECK_LAUNCH(1);
+    c->rowcount_ready = true;
+  }
+  return NBMF_OK;
+}
+// 1 while the context still reads the planes given to nbmf_set_data_bits / nbmf_ingest_bits_begin (SIMT engine: always;
+// tensor engine: only until the work enqueued by nbmf_set_data_bits / nbmf_ingest_bits_end has run -- stream order makes
+// a free or overwrite enqueued on the same stream afterwards safe).
+extern "C" int nbmf_planes_in_use(nbmf_ctx* c) {
+  if (!c) return 0;
+  if (c->cfg.vkind != NBMF_V_BITS) return 1;
+  if (!c->p.tensor) return 1;
+  return (c->ingest_rows != 0 && c->ingest_rows != c->cfg.m) ? 1 : 0;     // a streamed ingestion is still in progress
+}
+
 extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t* M) {
   if (!c || !P) return fail(NBMF_ERR_ARG, "nbmf_set_data_bits: null argument");
   if (c->cfg.vkind != NBMF_V_BITS) return fail(NBMF_ERR_ARG, "context was created for dense V");
@@ -423,7 +455,11 @@ extern "C" int nbmf_set_data_bits(nbmf_ctx* c, const uint32_t* P, const uint32_t
   if (c->p.tensor) {   // the tensor kernels read planes re-tiled per TMEM lane (format_factors.cu)
     launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, 0, c->cfg.m, c->at<uint32_t>(c->p.oPc),
                        c->p.strict ? c->at<uint32_t>(c->p.oMc) : nullptr, c->ws + c->p.oPM, c->st);
-    CHECK_LAUNCH(c->p.strict ? 3 : 2);
+    CUDA_TRY(cudaMemsetAsync(c->at<uint32_t>(c->p.oColcnt), 0, (size_t)c->p.ldh * 4, c->st));
+    launch_colcount(c->at<uint32_t>(c->p.oPc), c->p.mpad / 32, 0, c->p.mpad / 32, c->p.ldh, c->at<uint32_t>(c->p.oColcnt), c->st);
+    CHECK_LAUNCH(c->p.strict ? 4 : 3);
+    int rc = eager_rowcount(c);
+    if (rc) return rc;
   }
   return NBMF_OK;
 }
@@ -442,6 +478,7 @@ extern "C" int nbmf_ingest_bits_begin(nbmf_ctx* c, uint32_t* P, const uint32_t* 
   graph_drop(c);
   c->ingest_rows = 0;
   CUDA_TRY(cudaMemsetAsync(ingest_counter(c), 0, sizeof(unsigned long long), c->st));
+  if (c->p.tensor) CUDA_TRY(cudaMemsetAsync(c->at<uint32_t>(c->p.oColcnt), 0, (size_t)c->p.ldh * 4, c->st));
   return NBMF_OK;
 }
 extern "C" int nbmf_ingest_bits_rows(nbmf_ctx* c, int64_t row0, int64_t row1) {
@@ -457,7 +494,10 @@ extern "C" int nbmf_ingest_bits_rows(nbmf_ctx* c, int64_t row0, int64_t row1) {
   if (c->p.tensor) {
     launch_tile_planes(P, c->M, c->cfg.m, c->cfg.n, c->p.wpr, c->p.mpad, row0, row1, c->at<uint32_t>(c->p.oPc),
                        c->p.strict ? c->at<uint32_t>(c->p.oMc) : nullptr, c->ws + c->p.oPM, c->st);
-    launches += c->p.strict ? 3 : 2;
+    const int64_t end = row1 >= c->cfg.m ? c->p.mpad : row1;         // the re-tiled words of this chunk exist now
+    launch_colcount(c->at<uint32_t>(c->p.oPc), c->p.mpad / 32, row0 / 32, (end + 31) / 32, c->p.ldh,
+                    c->at<uint32_t>(c->p.oColcnt), c->st);
+    launches += c->p.strict ? 4 : 3;
   }
   CHECK_LAUNCH(launches);
   c->ingest_rows = row1;
@@ -466,6 +506,10 @@ extern "C" int nbmf_ingest_bits_rows(nbmf_ctx* c, int64_t row0, int64_t row1) {
 extern "C" int nbmf_ingest_bits_end(nbmf_ctx* c, double* mask_count_host) {
   if (!c || !c->P) return fail(NBMF_ERR_ARG, "nbmf_ingest_bits_begin was not called");
   if (c->ingest_rows != c->cfg.m) return fail(NBMF_ERR_ARG, "nbmf_ingest_bits_end: not all rows were ingested");
+  if (c->p.tensor) {
+    int rc = eager_rowcount(c);
+    if (rc) return rc;
+  }
   unsigned long long h = 0;
   CUDA_TRY(cudaMemcpyAsync(&h, ingest_counter(c), 8, cudaMemcpyDeviceToHost, c->st));
   CUDA_TRY(cudaStreamSynchronize(c->st));
@@ -483,8 +527,22 @@ extern "C" int nbmf_set_data_dense(nbmf_ctx* c, const void* Vm, const uint32_t* 
   if (c->cfg.vkind != NBMF_V_DENSE && c->cfg.vkind != NBMF_V_DENSE_F16) return fail(NBMF_ERR_ARG, "context was created for bit-packed V");
   if (c->cfg.has_mask && !M) return fail(NBMF_ERR_ARG, "has_mask is set but no mask plane given");
   c->Vm = Vm;
+  c->Wm = nullptr;
   c->M = c->cfg.has_mask ? M : nullptr;
   c->rowcount_ready = false;
+  graph_drop(c);
+  return NBMF_OK;
+}
+
+// Weighted observation mask (values other than 0 / 1): the reference multiplies by the mask values (Y * mask,
+// (1 - Y).T * mask.T: _solver.py:30-32).  V * mask is what nbmf_set_data_dense takes anyway; the W half-step additionally
+// needs the mask values themselves ((1 - V) * mask = mask - V * mask), in the same dense layout and dtype.  The bit plane
+// given to nbmf_set_data_dense is then (mask != 0).  Reference mask semantics only.
+extern "C" int nbmf_set_mask_weights(nbmf_ctx* c, const void* wm) {
+  if (!c) return fail(NBMF_ERR_ARG, "null context");
+  if (c->cfg.vkind != NBMF_V_DENSE) return fail(NBMF_ERR_UNSUPPORTED, "weighted masks need the dense V layout in the compute dtype");
+  if (wm && c->p.strict) return fail(NBMF_ERR_UNSUPPORTED, "weighted masks are defined for the reference mask semantics only");
+  c->Wm = wm;
   graph_drop(c);
   return NBMF_OK;
 }
@@ -499,7 +557,7 @@ extern "C" int nbmf_set_factors(nbmf_ctx* c, const void* w, const void* h, int n
   if (!c) return fail(NBMF_ERR_ARG, "null context");
   launch_init_factors(c->cfg.dtype, w, h, c->cfg.m, c->cfg.n, c->cfg.k, c->p.pl.kp, c->p.ldh, c->W(), c->H(), c->Ht(),
                       normalize_w, c->st);
-  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state());
+  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state(), c->cfg.alpha, c->cfg.beta);
   CHECK_LAUNCH((w ? 1 : 0) + (h ? 1 : 0) + 1);
   c->enqueued = 0;
   c->tail_enqueued = false;
@@ -538,13 +596,13 @@ extern "C" int nbmf_get_factors_f64(nbmf_ctx* c, double* w, double* h, int norma
 // ------------------------------------------------------------------------------------ steps
 static int format_w(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;
-  launch_format_w(c->W(), c->cfg.m, c->p.mpad, c->ws + c->p.oWf, guarded ? c->state() : nullptr, c->st);
+  launch_format_w(c->W(), c->cfg.m, c->p.mpad, c->p.pl.kp, c->ws + c->p.oWf, guarded ? c->state() : nullptr, c->st);
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }
 static int format_h(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;
-  launch_format_h(c->H(), c->p.ldh, c->ws + c->p.oHf, guarded ? c->state() : nullptr, c->st);
+  launch_format_h(c->H(), c->p.ldh, c->p.pl.kp, c->ws + c->p.oHf, guarded ? c->state() : nullptr, c->st);
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }
@@ -595,7 +653,8 @@ static int enqueue_h_pass(nbmf_ctx* c, int compute_cd, bool with_finalize = fals
   prof_mark(c, c->prof_h);
   if (p.tensor)
     launch_h_pass_tensor(a, c->ws + p.oWf, c->at<uint32_t>(p.oPc), p.strict ? c->at<uint32_t>(p.oMc) : nullptr, p.mpad / 32,
-                         p.h_nsplit, c->st);
+                         p.kb, c->cfg.k, getenv("NBMF_TC_NOFLIP") ? nullptr : c->at<uint32_t>(p.oColcnt),
+                         c->at<uint32_t>(p.oFlipcol), c->at<int>(p.oFlipAny), p.h_nsplit, c->st);
   else
     p.pl.h_launch(a, p.h_nsplit, c->st);
   prof_mark(c, c->prof_h);
@@ -629,14 +688,14 @@ static int enqueue_w_step(nbmf_ctx* c) {
     c->rowcount_ready = true;
   }
   WPassArgs a;
-  a.W = c->W(); a.Ht = c->Ht(); a.P = c->P; a.M = c->M; a.Vm = c->Vm; a.ldv = p.ldh;
+  a.W = c->W(); a.Ht = c->Ht(); a.P = c->P; a.M = c->M; a.Vm = c->Vm; a.Wm = c->Wm; a.ldv = p.ldh;
   a.m = c->cfg.m; a.n = c->cfg.n; a.ldh = p.ldh; a.wpr = p.wpr;
   a.cols_per_split = p.w_cols_per_split;
   a.G = c->ws + p.oG; a.Q = c->ws + p.oQ; a.eps = c->cfg.eps; a.done = &c->state()->done;
   a.batch_n = c->batch_n; a.batch_stride = c->batch_stride;
   prof_mark(c, c->prof_w);
   if (p.tensor)
-    launch_w_pass_tensor(a, c->ws + p.oHf, c->ws + p.oPM, p.w_nsplit, c->st);
+    launch_w_pass_tensor(a, c->ws + p.oHf, c->ws + p.oPM, p.kb, p.w_nsplit, c->st);
   else
     p.pl.w_launch(a, p.w_nsplit, c->st);
   prof_mark(c, c->prof_w);
@@ -713,7 +772,7 @@ extern "C" int nbmf_fit_begin(nbmf_ctx* c, int32_t max_iter, double tol) {
   c->enqueued = 0;
   c->tail_enqueued = false;
   c->poll_pending = false;
-  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state());
+  reset_state_kernel<<<1, 1, 0, c->st>>>(c->state(), c->cfg.alpha, c->cfg.beta);
   // prior sums of the initial H are not needed for any recorded loss, but keep the buffer defined
   launch_prior_sums(c->cfg.dtype, c->H(), c->cfg.n, c->cfg.k, c->p.pl.kp, c->p.ldh, c->cfg.eps,
                     c->at<double>(c->p.oPrior), c->st);
@@ -812,7 +871,8 @@ extern "C" int nbmf_fit_poll(nbmf_ctx* c, int wait, int32_t* done_host, int32_t*
 }
 
 // ---- batched small fits (restarts, n_init): one launch per phase advances all fits of a group.
-// The caller creates n contexts of IDENTICAL configuration (same m, n, k, dtype, alpha, beta, eps, flags, data planes)
+// The caller creates n contexts of identical configuration (same m, n, k, dtype, eps, flags, data planes; alpha and beta
+// may differ from fit to fit: they live in each fit's FitState, so hyper-parameter grids batch like restarts)
 // on the same stream, with workspaces at a uniform byte stride inside one allocation (leader first), gives each its
 // factors (nbmf_set_factors) and calls nbmf_fit_begin on each with the same max_iter / tol.  After nbmf_batch_bind
 // the leader's nbmf_fit_enqueue drives all of them: every kernel of the loop runs with gridDim.z = n and shifts its

@@ -3,10 +3,11 @@
 // Factors: every streamed factor block is split into tf32 hi + lo parts and written in the K-major,
 // 128-byte-swizzled layout the tcgen05 shared-memory descriptors expect, all operand forms of one
 // block contiguous, so a pipeline stage of the hot kernels is ONE 1-D bulk copy.
-//   Wf [mpad/32][4][4 KB]   per 32-row block of W:   rows i x k  tf32 hi | bf16 correction  (B of the H pass MMA1)
-//                                                    rows k x i  tf32 hi | bf16 correction  (B of the H pass MMA2)
-//   Hf [ldh/64][4][8 KB]    per 64-column block of H: rows j x k tf32 hi | bf16 correction  (B of the W pass MMA1)
-//                                                    2 K-blocks of rows k x 32 j, tf32 hi | bf16 correction (MMA2)
+//   Wf [mpad/32][4][KT/32 x 4 KB]  per 32-row block of W:    rows i x k  tf32 hi | bf16 correction  (B of the H pass MMA1)
+//                                                           rows k x i  tf32 hi | bf16 correction  (B of the H pass MMA2)
+//   Hf [ldh/64][4][KT/32 x 8 KB]   per 64-column block of H: rows j x k tf32 hi | bf16 correction  (B of the W pass MMA1)
+//                                                           2 K-blocks of rows k x 32 j, tf32 hi | bf16 correction (MMA2)
+//   (KT = 32 for K <= 32, 64 for K <= 64)
 // Every product a.b = hi.hi + (hi.lo + lo.hi): the first term is a TF32 MMA chain, the two correction terms come
 // from ONE bf16 MMA chain with twice the K extent.  MMA1: the A tile holds [hi | lo] as bf16, the streamed
 // correction plane [lo | hi] per row.  MMA2: the SIMT stage packs (hi, lo) of a ratio into one 32-bit column
@@ -17,63 +18,95 @@
 // warp's 32 lanes read 32 consecutive words:
 //   Pc [ldh/128][mpad/32][128]        word = rows 32 rb .. 32 rb + 31 of column 128 jt + jj of P
 //   PM [mpad/128][wpr][128] (uint2)   {P word, observed word} of row 128 it + ii, columns 32 cw .. 32 cw + 31
+#include <algorithm>
+
 #include "internal.h"
 #include "tc_common.cuh"
 
 namespace nbmf {
 
+// KT = 32 (K <= 32) or 64 (K <= 64): K extent of the formatted operands.  A K-major operand wider than 128 bytes per row is
+// stored as KT/32 slabs (one SWIZZLE_128B tile per 32 k / per 64 bf16), slab after slab.
+template <int KT>
 __global__ void format_w_kernel(const float* __restrict__ W, int64_t m, int64_t mpad, float* __restrict__ Wf,
                                 const FitState* __restrict__ state) {
   if (state && state->done) return;
+  constexpr int REGF = (KT / 32) * 1024;                           // floats per operand region of a 32-row block
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= mpad * 32) return;
-  const int64_t i = e >> 5;
-  const int k = (int)(e & 31);
+  if (e >= mpad * KT) return;
+  const int64_t i = e / KT;
+  const int k = (int)(e % KT);
   const float x = i < m ? W[e] : 0.0f;
   const float hi = tc::tf32_trunc(x), lo = x - hi;
   const int r = (int)(i & 31);
-  float* blk = Wf + (size_t)(i >> 5) * 4096;
-  const uint32_t oa = tc::sw128_offset(r, k) / 4, ob = tc::sw128_offset(k, r) / 4;
-  blk[oa] = hi;
-  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + 1024);
-  corr[tc::sw128_offset_b16(r, k) / 2] = (unsigned short)tc::bf16_bits(lo);
-  corr[tc::sw128_offset_b16(r, 32 + k) / 2] = (unsigned short)tc::bf16_bits(hi);
-  blk[2048 + ob] = hi;
-  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 3072);     // row k: (lo, hi) pairs per i
+  float* blk = Wf + (size_t)(i >> 5) * (4 * REGF);
+  blk[(k >> 5) * 1024 + tc::sw128_offset(r, k & 31) / 4] = hi;                       // rows i x k, tf32 hi
+  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + REGF);             // rows i: [lo (KT) | hi (KT)] bf16
+  const int il = k, ih = KT + k;
+  corr[(il >> 6) * 2048 + tc::sw128_offset_b16(r, il & 63) / 2] = (unsigned short)tc::bf16_bits(lo);
+  corr[(ih >> 6) * 2048 + tc::sw128_offset_b16(r, ih & 63) / 2] = (unsigned short)tc::bf16_bits(hi);
+  blk[2 * REGF + tc::sw128_offset(k, r) / 4] = hi;                                   // rows k x i, tf32 hi
+  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 3 * REGF);        // row k: (lo, hi) pairs per i
   corr2[tc::sw128_offset_b16(k, 2 * r) / 2] = (unsigned short)tc::bf16_bits(lo);
   corr2[tc::sw128_offset_b16(k, 2 * r + 1) / 2] = (unsigned short)tc::bf16_bits(hi);
 }
 
+template <int KT>
 __global__ void format_h_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Hf,
                                 const FitState* __restrict__ state) {
   if (state && state->done) return;
+  constexpr int RWF = (KT / 32) * 2048;                            // floats per operand region of a 64-column block
+  constexpr int RBF = KT * 32;                                     // floats per K-block (32 columns) of the H operand
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
   if (j >= ldh) return;
   const float x = H[(size_t)k * ldh + j];
   const float hi = tc::tf32_trunc(x), lo = x - hi;
   const int r = (int)(j & 63);
-  float* blk = Hf + (size_t)(j >> 6) * 8192;
-  const uint32_t oa = tc::sw128_offset(r, k) / 4;
-  const uint32_t ob = (uint32_t)(r >> 5) * 1024 + tc::sw128_offset(k, r & 31) / 4;
-  blk[oa] = hi;
-  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + 2048);
-  corr[tc::sw128_offset_b16(r, k) / 2] = (unsigned short)tc::bf16_bits(lo);
-  corr[tc::sw128_offset_b16(r, 32 + k) / 2] = (unsigned short)tc::bf16_bits(hi);
-  blk[4096 + ob] = hi;
-  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 6144);     // 2 K-blocks; row k: (lo, hi) pairs per j
-  const int rr = r & 31;
-  corr2[((r >> 5) * 4096 + tc::sw128_offset_b16(k, 2 * rr)) / 2] = (unsigned short)tc::bf16_bits(lo);
-  corr2[((r >> 5) * 4096 + tc::sw128_offset_b16(k, 2 * rr + 1)) / 2] = (unsigned short)tc::bf16_bits(hi);
+  float* blk = Hf + (size_t)(j >> 6) * (4 * RWF);
+  blk[(k >> 5) * 2048 + tc::sw128_offset(r, k & 31) / 4] = hi;                       // rows j x k, tf32 hi
+  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + RWF);              // rows j: [lo (KT) | hi (KT)] bf16
+  const int il = k, ih = KT + k;
+  corr[(il >> 6) * 4096 + tc::sw128_offset_b16(r, il & 63) / 2] = (unsigned short)tc::bf16_bits(lo);
+  corr[(ih >> 6) * 4096 + tc::sw128_offset_b16(r, ih & 63) / 2] = (unsigned short)tc::bf16_bits(hi);
+  const int rr = r & 31, hb = r >> 5;
+  blk[2 * RWF + hb * RBF + tc::sw128_offset(k, rr) / 4] = hi;                         // 2 K-blocks of rows k x 32 j
+  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 3 * RWF + hb * RBF);   // row k: (lo, hi) pairs per j
+  corr2[tc::sw128_offset_b16(k, 2 * rr) / 2] = (unsigned short)tc::bf16_bits(lo);
+  corr2[tc::sw128_offset_b16(k, 2 * rr + 1) / 2] = (unsigned short)tc::bf16_bits(hi);
 }
 
-void launch_format_w(const void* W, int64_t m, int64_t mpad, void* Wf, const FitState* state, cudaStream_t st) {
-  const unsigned grid = (unsigned)((mpad * 32 + 255) / 256);
-  format_w_kernel<<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state);
+void launch_format_w(const void* W, int64_t m, int64_t mpad, int kt, void* Wf, const FitState* state, cudaStream_t st) {
+  const unsigned grid = (unsigned)((mpad * kt + 255) / 256);
+  if (kt == 64) format_w_kernel<64><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state);
+  else format_w_kernel<32><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state);
 }
-void launch_format_h(const void* H, int64_t ldh, void* Hf, const FitState* state, cudaStream_t st) {
-  dim3 grid((unsigned)((ldh + 255) / 256), 32);
-  format_h_kernel<<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state);
+void launch_format_h(const void* H, int64_t ldh, int kt, void* Hf, const FitState* state, cudaStream_t st) {
+  dim3 grid((unsigned)((ldh + 255) / 256), (unsigned)kt);
+  if (kt == 64) format_h_kernel<64><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state);
+  else format_h_kernel<32><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state);
+}
+
+// Ones per column of a re-tiled plane (Pc layout), accumulated over the row blocks [rb0, rb1): the H pass uses the
+// density of ones of a column to pick the plane it accumulates directly.  Integer atomics: deterministic.
+__global__ void colcount_kernel(const uint32_t* __restrict__ Pc, int64_t nrb, int64_t rb0, int64_t rb1, int64_t ldh,
+                                uint32_t* __restrict__ colcnt) {
+  const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;       // one column block of 128 per CTA.x
+  if (j >= ldh) return;
+  const int64_t per = (rb1 - rb0 + gridDim.y - 1) / gridDim.y;
+  const int64_t a0 = rb0 + (int64_t)blockIdx.y * per, a1 = min(rb1, a0 + per);
+  const uint32_t* __restrict__ p = Pc + ((size_t)blockIdx.x * nrb) * 128 + threadIdx.x;
+  uint32_t c = 0;
+  for (int64_t rb = a0; rb < a1; ++rb) c += __popc(p[(size_t)rb * 128]);
+  if (c) atomicAdd(&colcnt[j], c);
+}
+void launch_colcount(const uint32_t* Pc, int64_t nrb, int64_t rb0, int64_t rb1, int64_t ldh, uint32_t* colcnt, cudaStream_t st) {
+  if (rb1 <= rb0) return;
+  const int64_t ncb = ldh / 128;
+  int ysplit = (int)std::min<int64_t>(64, std::max<int64_t>(1, (148 * 8 + ncb - 1) / ncb));
+  ysplit = (int)std::min<int64_t>(ysplit, rb1 - rb0);
+  dim3 grid((unsigned)ncb, (unsigned)ysplit);
+  colcount_kernel<<<grid, 128, 0, st>>>(Pc, nrb, rb0, rb1, ldh, colcnt);
 }
 
 // One warp per 32 x 32 bit tile: lane r holds the word of row 32 rb + r, 32 ballots transpose it, lane c

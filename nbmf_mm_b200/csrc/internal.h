@@ -17,6 +17,7 @@ struct FitState {
   double prev_loss;    // loss of the previous iteration (inf before the first)
   double prior_a;      // sum log(H + eps) of the current H
   double prior_b;      // sum log((1 - H) + eps) of the current H
+  double alpha, beta;  // Beta prior of this fit (_solver.py:35-36): per fit, so that the fits of a batch (gridDim.z) may differ
 };
 
 // ---- loss + stop rule of one iteration (finalize_body in misc_kernels.cu); state == nullptr: not requested
@@ -55,14 +56,16 @@ void launch_export_f64(int dtype, const void* W, const void* H, int64_t m, int64
                        int normalize_w, double* W_out, double* H_out, cudaStream_t st);
 void launch_clip_rows(int dtype, void* W, int64_t m, int k, int kp, double lo, double hi, cudaStream_t st);
 
-// ---- tensor-core engine (K <= 32, fp32, bit-packed V): operand formatting + pass launchers
-void launch_format_w(const void* W, int64_t m, int64_t mpad, void* Wf, const FitState* state, cudaStream_t st);
-void launch_format_h(const void* H, int64_t ldh, void* Hf, const FitState* state, cudaStream_t st);
+// ---- tensor-core engine (K <= 64, fp32, bit-packed V): operand formatting + pass launchers
+void launch_format_w(const void* W, int64_t m, int64_t mpad, int kt, void* Wf, const FitState* state, cudaStream_t st);
+void launch_format_h(const void* H, int64_t ldh, int kt, void* Hf, const FitState* state, cudaStream_t st);
+void launch_colcount(const uint32_t* Pc, int64_t nrb, int64_t rb0, int64_t rb1, int64_t ldh, uint32_t* colcnt, cudaStream_t st);
 void launch_tile_planes(const uint32_t* P, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, int64_t mpad,
                         int64_t row0, int64_t row1, uint32_t* Pc, uint32_t* Mc, void* PM, cudaStream_t st);
-void launch_w_pass_tensor(const WPassArgs& a, const void* Hf, const void* PM, int nsplit, cudaStream_t st);
+// kb = 16 | 32 | 64: K extent the MMAs cover (TcCfg<KB> in tc_passes.cuh); k = n_components
+void launch_w_pass_tensor(const WPassArgs& a, const void* Hf, const void* PM, int kb, int nsplit, cudaStream_t st);
 void launch_h_pass_tensor(const HPassArgs& a, const void* Wf, const uint32_t* Pc, const uint32_t* Mc, int64_t nrb,
-                          int nsplit, cudaStream_t st);
+                          int kb, int k, const uint32_t* colcnt, uint32_t* flipcol, int* flip_any, int nsplit, cudaStream_t st);
 
 // ---- data layer
 void launch_pack_bits(int in_dtype, const void* X, int64_t ldx, const void* mask, int mask_dtype, int64_t ldm,

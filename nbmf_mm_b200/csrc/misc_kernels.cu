@@ -96,7 +96,8 @@ __device__ __forceinline__ void finalize_body(const FinalizeArgs& f, double ll) 
   const int it = state->it;
   int done = 0;
   if (it >= 1) {
-    const double loss = -(ll + (f.alpha - 1.0) * pa + (f.beta - 1.0) * pb) / f.n_obs;
+    // alpha, beta from the fit's own state (== f.alpha, f.beta for a single fit; per fit in a batch)
+    const double loss = -(ll + (state->alpha - 1.0) * pa + (state->beta - 1.0) * pb) / f.n_obs;
     f.history[it - 1] = loss;
     state->n_hist = it;
     if (it >= 2) {
@@ -191,6 +192,7 @@ __global__ void h_epilogue_kernel(const Real* __restrict__ CD, int64_t n, int k,
     prior_part = batch_shift(prior_part, sh); state = batch_shift(state, sh);
   }
   if (UPDATE && state->done) return;
+  if (UPDATE) { alpha = state->alpha; beta = state->beta; }       // per fit: the fits of a batch may differ
   const int64_t j = (int64_t)blockIdx.x * HEPI_NT + threadIdx.x;
   const int kk = blockIdx.y;
   double la = 0.0, lb = 0.0;
@@ -243,61 +245,134 @@ void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64
 // projection 0 = "normalize": (W*G)/n then L1 renormalisation;  1 = "duchi": (W*G)/n_obs(row)
 // then Euclidean projection onto the simplex (Duchi et al. 2008 sort/threshold; unpinned).
 // ------------------------------------------------------------------------------------
-constexpr int MAX_K = 64;
-
+// One WARP per row, lane = component k (two components per lane for 32 < K <= 64): row reads and writes are single
+// coalesced lines and every reduction is a fixed shuffle tree (deterministic).  Round 1 ran one thread per row with
+// two 64-element local arrays and stride-K global access: on small problems (config 5) it cost as much as the H pass.
+// Duchi: descending bitonic sort of the row across the warp's registers, inclusive prefix sums in sorted order, rho =
+// last index whose value exceeds the running threshold (Duchi et al. 2008), then w = max(v - theta, 0).
 template <typename Real>
-__global__ void w_epilogue_kernel(const Real* __restrict__ Gpart, const Real* __restrict__ Qpart, int nsplit,
-                                  int64_t m, int64_t n, int k, int kp, int projection,
-                                  const Real* __restrict__ rowcount, Real* __restrict__ W,
-                                  const FitState* __restrict__ state, int64_t bstride) {
+__device__ __forceinline__ Real warp_sum(Real v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename Real>
+__device__ __forceinline__ Real warp_scan_incl(Real v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const Real t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+template <typename Real, int EPL>
+__global__ void __launch_bounds__(256) w_epilogue_kernel(const Real* __restrict__ Gpart, const Real* __restrict__ Qpart, int nsplit,
+                                                         int64_t m, int64_t n, int k, int kp, int projection,
+                                                         const Real* __restrict__ rowcount, Real* __restrict__ W,
+                                                         const FitState* __restrict__ state, int64_t bstride) {
   if (bstride) {                                  // fit blockIdx.z of a batch: its own workspace (rowcount is shared)
     const size_t sh = (size_t)blockIdx.z * (size_t)bstride;
     Gpart = batch_shift(Gpart, sh); Qpart = batch_shift(Qpart, sh); W = batch_shift(W, sh); state = batch_shift(state, sh);
   }
   if (state->done) return;
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= m) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= m) return;                            // warp-uniform
   Real q = Qpart[row];
   for (int s = 1; s < nsplit; ++s) q += Qpart[(int64_t)s * m + row];
-  Real v[MAX_K];
   const Real denom = (projection == 0) ? (Real)n : (rowcount ? rowcount[row] : (Real)n);
-  Real sum = Real(0);
-  for (int kk = 0; kk < k; ++kk) {
-    Real gs = Gpart[row * kp + kk];
-    for (int s = 1; s < nsplit; ++s) gs += Gpart[((int64_t)s * m + row) * kp + kk];
-    const Real x = (W[row * kp + kk] * (gs + q)) / denom;
-    v[kk] = x;
-    sum += x;
+  Real v[EPL];
+  Real part = Real(0);
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int kk = lane + 32 * e;
+    v[e] = Real(0);
+    if (kk < k) {
+      Real gs = Gpart[row * kp + kk];
+      for (int s = 1; s < nsplit; ++s) gs += Gpart[((int64_t)s * m + row) * kp + kk];
+      v[e] = (W[row * kp + kk] * (gs + q)) / denom;
+    }
+    part += v[e];
   }
   if (projection == 0) {
-    for (int kk = 0; kk < k; ++kk) W[row * kp + kk] = v[kk] / sum;
+    const Real sum = warp_sum(part);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e)
+      if (lane + 32 * e < k) W[row * kp + lane + 32 * e] = v[e] / sum;
     return;
   }
-  // Duchi: sort descending (insertion sort, k <= 64), find rho and the threshold
-  Real u[MAX_K];
-  for (int a = 0; a < k; ++a) {
-    const Real x = v[a];
-    int b = a;
-    while (b > 0 && u[b - 1] < x) { u[b] = u[b - 1]; --b; }
-    u[b] = x;
+  // ---- Duchi: bitonic sort (descending) of the 32 * EPL values held one (two) per lane; padding sorts last
+  const Real NEG = -INFINITY;
+  Real u[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) u[e] = (lane + 32 * e < k) ? v[e] : NEG;
+  constexpr int NEL = 32 * EPL;
+#pragma unroll
+  for (int size = 2; size <= NEL; size <<= 1) {
+#pragma unroll
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {                               // partner is this lane's other register (EPL == 2, j == 32)
+        if constexpr (EPL == 2) {
+          // element indices lane and lane + 32; direction of the merge: descending when (index & size) == 0
+          const bool desc = ((lane & size) == 0);   // size == 64 here: always descending
+          const Real lo = fmin(u[0], u[1]), hi = fmax(u[0], u[1]);
+          u[0] = desc ? hi : lo;
+          u[1] = desc ? lo : hi;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const int idx = lane + 32 * e;
+          const Real other = __shfl_xor_sync(0xffffffffu, u[e], j);
+          const bool desc = ((idx & size) == 0);
+          const bool lower = ((lane & j) == 0);     // this element is the lower index of the pair
+          const Real mx = fmax(u[e], other), mn = fmin(u[e], other);
+          u[e] = (lower == desc) ? mx : mn;
+        }
+      }
+    }
   }
-  Real css = Real(0), theta = Real(0);
-  for (int a = 0; a < k; ++a) {
-    css += u[a];
-    const Real t = (css - Real(1)) / (Real)(a + 1);
-    if (u[a] - t > Real(0)) theta = t;
+  // inclusive prefix sums in sorted order (element index = lane + 32 e), padding contributes nothing
+  Real css[EPL];
+  Real carry = Real(0);
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const Real x = (u[e] == NEG) ? Real(0) : u[e];
+    css[e] = warp_scan_incl(x, lane) + carry;
+    carry = __shfl_sync(0xffffffffu, css[e], 31);
   }
-  for (int kk = 0; kk < k; ++kk) W[row * kp + kk] = fmax(v[kk] - theta, Real(0));
+  // theta = (css_rho - 1) / (rho + 1) for the LAST index rho with u_rho - (css_rho - 1) / (rho + 1) > 0
+  int best = -1;
+  Real theta = Real(0);
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int idx = lane + 32 * e;
+    const Real t = (css[e] - Real(1)) / (Real)(idx + 1);
+    const bool ok = (u[e] != NEG) && (u[e] - t > Real(0));
+    if (ok && idx > best) { best = idx; theta = t; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const Real ot = __shfl_xor_sync(0xffffffffu, theta, o);
+    if (ob > best) { best = ob; theta = ot; }
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e)
+    if (lane + 32 * e < k) W[row * kp + lane + 32 * e] = fmax(v[e] - theta, Real(0));
 }
 
 void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nsplit, int64_t m, int64_t n,
                        int k, int kp, int projection, const void* rowcount, void* W, const FitState* state,
                        cudaStream_t st, int batch_n, int64_t bstride) {
-  const dim3 grid((unsigned)((m + 127) / 128), 1, (unsigned)batch_n);
-  if (dtype == 0)
-    w_epilogue_kernel<float><<<grid, 128, 0, st>>>((const float*)Gpart, (const float*)Qpart, nsplit, m, n, k, kp, projection, (const float*)rowcount, (float*)W, state, bstride);
-  else
-    w_epilogue_kernel<double><<<grid, 128, 0, st>>>((const double*)Gpart, (const double*)Qpart, nsplit, m, n, k, kp, projection, (const double*)rowcount, (double*)W, state, bstride);
+  const dim3 grid((unsigned)((m + 7) / 8), 1, (unsigned)batch_n);
+#define NBMF_WEPI(Real, EPL)                                                                                               \
+  w_epilogue_kernel<Real, EPL><<<grid, 256, 0, st>>>((const Real*)Gpart, (const Real*)Qpart, nsplit, m, n, k, kp, projection, \
+                                                     (const Real*)rowcount, (Real*)W, state, bstride)
+  if (dtype == 0) { if (k <= 32) NBMF_WEPI(float, 1); else NBMF_WEPI(float, 2); }
+  else { if (k <= 32) NBMF_WEPI(double, 1); else NBMF_WEPI(double, 2); }
+#undef NBMF_WEPI
 }
 
 // ------------------------------------------------------------------------------------

@@ -419,6 +419,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
   const unsigned char* __restrict__ Htg = batch_shift(reinterpret_cast<const unsigned char*>(a.Ht), NBMF_BSH);
   using VT = typename Cfg::VT;
   const VT* __restrict__ Vg = reinterpret_cast<const VT*>(a.Vm);
+  // weighted (non-0/1) observation mask: its VALUES, dense, same layout as V*mask (the reference multiplies by them:
+  // (1 - Y).T * mask.T, _solver.py:32); NULL for a 0/1 mask, whose bit plane says it all
+  const Real* __restrict__ Wmg = DENSE ? reinterpret_cast<const Real*>(a.Wm) : nullptr;
   const int64_t ntiles = (c1 > c0) ? (c1 - c0 + BNT - 1) / BNT : 0;
 
   auto issue_tile = [&](int64_t t) {
@@ -516,8 +519,10 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
               qacc[rr] += p ? Real(0) : r_;
             } else {
               const Real v = vv[rr][e];
+              Real wv = ob ? Real(1) : Real(0);
+              if (Wmg) wv = Wmg[(size_t)min(ib + il + rr, a.m - 1) * a.ldv + colw + jj];
               const Real pa = div_(v, theta + eps);
-              const Real qb = div_((ob ? Real(1) : Real(0)) - v, (Real(1) - theta) + eps);
+              const Real qb = div_(wv - v, (Real(1) - theta) + eps);     // (1 - V) * mask = mask - V * mask
               s = pa - qb;
               qacc[rr] += qb;
             }

@@ -1,4 +1,6 @@
-// Tensor-core (tcgen05 / TMEM) versions of the two pass kernels for K <= 32, fp32, bit-packed V.
+// Tensor-core (tcgen05 / TMEM) versions of the two pass kernels for K <= 32, fp32, bit-packed V (32 < K <= 64: tc_passes_k64.cuh).
+// Template KB = 16 | 32: K extent the MMAs cover.  KB = 16 uses the same operand formats and skips the MMA K steps that
+// are all padding and half of MMA2's N.
 //
 // Same math as passes.cuh, restructured like attention on Blackwell (S = QK^T -> P -> O = PV):
 //   MMA1  Theta tile = resident factor tile [TMEM] . streamed factor block [smem]   (tcgen05.mma, TS form)
@@ -30,8 +32,12 @@
 #include "args.h"
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_args.h"
+
+#include <type_traits>
 
 namespace nbmf {
+namespace k32 {
 
 // Optional cycle trace of CTA (0,0) (tools/tc_trace.cu defines TC_TRACE): event e of warp slot w at block b.
 #ifdef TC_TRACE
@@ -69,13 +75,35 @@ __device__ __forceinline__ void h_entry(float theta, uint32_t bits, uint32_t bit
       : "=f"(x), "=r"(hi), "=r"(c), "=r"(phi), "=r"(pc)
       : "f"(theta), "r"(bits), "r"(bit), "f"(eps));
 }
+//   The same with the directly accumulated plane selected by a second bit word (`qbits`): the zeros' plane of a column
+//   whose ones dominate (see h_pass_tc_kernel).  Costs a second predicate per entry; only warps that hold such a column
+//   take this path.
+__device__ __forceinline__ void h_entry_q(float theta, uint32_t bits, uint32_t qbits, uint32_t bit, float eps, float& x,
+                                          uint32_t& hi, uint32_t& c, uint32_t& phi, uint32_t& pc) {
+  asm("{\n\t.reg .pred p, q;\n\t.reg .b32 t;\n\t.reg .f32 y, r, h, l;\n\t"
+      "and.b32 t, %6, %8;\n\tsetp.ne.b32 p, t, 0;\n\t"
+      "and.b32 t, %7, %8;\n\tsetp.ne.b32 q, t, 0;\n\t"
+      "mov.f32 y, %5;\n\t@!p sub.sat.f32 y, 0f3F800000, y;\n\t"
+      "add.f32 y, y, %9;\n\t"
+      "rcp.approx.ftz.f32 r, y;\n\t"
+      "and.b32 h, r, 0xffffe000;\n\t"
+      "sub.f32 l, r, h;\n\t"
+      "cvt.rn.bf16x2.f32 %2, l, h;\n\t"
+      "mov.b32 %1, h;\n\t"
+      "selp.b32 %3, %1, 0, q;\n\t"
+      "selp.b32 %4, %2, 0, q;\n\t"
+      "mov.f32 %0, y;\n\t}\n"
+      : "=f"(x), "=r"(hi), "=r"(c), "=r"(phi), "=r"(pc)
+      : "f"(theta), "r"(bits), "r"(qbits), "r"(bit), "f"(eps));
+}
 //   H pass, strict mask semantics (unobserved entries contribute nothing: _solver.py with the README/paper mask):
 //   additionally the unmasked outputs are zeroed and x is replaced by 1 (log 1 = 0) where the entry is unobserved.
-__device__ __forceinline__ void h_entry_strict(float theta, uint32_t bits, uint32_t obits, uint32_t bit, float eps, float& x,
-                                               uint32_t& hi, uint32_t& c, uint32_t& phi, uint32_t& pc) {
-  asm("{\n\t.reg .pred p, o;\n\t.reg .b32 t, hh, cc;\n\t.reg .f32 y, r, h, l;\n\t"
+__device__ __forceinline__ void h_entry_strict(float theta, uint32_t bits, uint32_t obits, uint32_t qbits, uint32_t bit, float eps,
+                                               float& x, uint32_t& hi, uint32_t& c, uint32_t& phi, uint32_t& pc) {
+  asm("{\n\t.reg .pred p, o, q;\n\t.reg .b32 t, hh, cc;\n\t.reg .f32 y, r, h, l;\n\t"
       "and.b32 t, %6, %8;\n\tsetp.ne.b32 p, t, 0;\n\t"
       "and.b32 t, %7, %8;\n\tsetp.ne.b32 o, t, 0;\n\t"
+      "and.b32 t, %10, %8;\n\tsetp.ne.b32 q, t, 0;\n\t"
       "mov.f32 y, %5;\n\t@!p sub.sat.f32 y, 0f3F800000, y;\n\t"
       "add.f32 y, y, %9;\n\t"
       "rcp.approx.ftz.f32 r, y;\n\t"
@@ -83,13 +111,13 @@ __device__ __forceinline__ void h_entry_strict(float theta, uint32_t bits, uint3
       "sub.f32 l, r, h;\n\t"
       "cvt.rn.bf16x2.f32 cc, l, h;\n\t"
       "mov.b32 hh, h;\n\t"
-      "selp.b32 %3, hh, 0, p;\n\t"
-      "selp.b32 %4, cc, 0, p;\n\t"
+      "selp.b32 %3, hh, 0, q;\n\t"
+      "selp.b32 %4, cc, 0, q;\n\t"
       "selp.b32 %1, hh, 0, o;\n\t"
       "selp.b32 %2, cc, 0, o;\n\t"
       "selp.f32 %0, y, 0f3F800000, o;\n\t}\n"
       : "=f"(x), "=r"(hi), "=r"(c), "=r"(phi), "=r"(pc)
-      : "f"(theta), "r"(bits), "r"(obits), "r"(bit), "f"(eps));
+      : "f"(theta), "r"(bits), "r"(obits), "r"(bit), "f"(eps), "r"(qbits));
 }
 //   Loss-only H pass (the objective of the final factors, score / evaluate): only x is needed.
 __device__ __forceinline__ float h_x(float theta, uint32_t bits, uint32_t bit, float eps) {
@@ -129,32 +157,6 @@ __device__ __forceinline__ void w_entry(float theta, uint32_t pbits, uint32_t ob
       : "f"(theta), "r"(pbits), "r"(obits), "r"(bit), "f"(eps));
 }
 
-struct HTcArgs {
-  const float* H;            // [32][ldh] k-major factor (pad rows/columns 0.5): source of the resident A tile
-  const float* Wf;           // [mpad/32][4][1024]  W rows hi | lo | W^T hi | lo   (format_factors.cu)
-  const uint32_t* Pc;        // [ldh/128][nrb][128] bit r of word (jt, rb, jj) = P[32 rb + r][128 jt + jj]
-  const uint32_t* Mc;        // same tiling of the observation mask (strict mask semantics only)
-  int64_t m, n, ldh, nrb;
-  int64_t rows_per_split;    // multiple of 32
-  float* CD;                 // [nsplit][2][32][ldh]
-  double* LL;                // [nsplit * gridDim.x]
-  float eps;
-  const int* done;
-  int compute_cd;
-};
-
-struct WTcArgs {
-  const float* W;            // [m][32] row-major factor: source of the resident A tile
-  const float* Hf;           // [ldh/64][4][2048]  Ht rows hi | lo | H (2 K-blocks) hi | lo
-  const uint2* PM;           // [mpad/128][wpr][128] {P word, observed word} of row 128 it + ii, columns 32 cw..
-  int64_t m, n, wpr;
-  int64_t cols_per_split;    // multiple of 64
-  float* G;                  // [nsplit][m][32]
-  float* Q;                  // [nsplit][m]
-  float eps;
-  const int* done;
-};
-
 constexpr int TC_SIMT_WARPS = 16;
 constexpr int TC_MMA1_WARP = 16;                        // + group
 constexpr int TC_MMA2_WARP = 18;                        // + group
@@ -176,8 +178,18 @@ constexpr int HTC_STAGE_BYTES = 16384;
 constexpr int HTC_OFF_ACC = HTC_STAGES * HTC_STAGE_BYTES;        // fp32 accumulators [32][512 SIMT threads]
 constexpr int HTC_SMEM = HTC_OFF_ACC + 32 * 512 * 4 + 1024;
 
-template <bool STRICT, bool CD>      // CD = false: loss-only pass (no ratio planes, no MMA2, no C / D output)
+// Which plane a COLUMN accumulates directly: Rq is the ones' plane (C direct, D = S - C) unless the column's density of
+// ones exceeds its mean H -- then the ones' sum C is expected to dominate the zeros' sum D (C / D ~ odds(density) /
+// odds(mean Theta)), Rq becomes the zeros' plane and C = S - D: forming the SMALL one by subtraction would lose
+// log2(large / small) bits.  Every warp that owns the column decides alike (same inputs); the choice is per TMEM lane.
+// The decision is taken per H pass by flip_cols_kernel (below); FLIP = false is the instantiation for the common case
+// that no column flips (one predicate per entry: the round-1 inner loop, untouched), FLIP = true the one with a second
+// predicate per entry.  Both are launched, the one that does not match the device-side flag returns at once.
+template <int KB, bool STRICT, bool CD, bool FLIP>   // CD = false: loss-only pass (no ratio planes, no MMA2, no C / D output)
 __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs a) {
+  static_assert(KB == 16 || KB == 32, "KB");
+  static_assert(CD || !FLIP, "the loss-only pass has no planes to choose");
+  if (CD && a.flip_any != nullptr && (*a.flip_any != 0) != FLIP) return;
   using namespace tc;
   if (*a.done) return;
   extern __shared__ unsigned char smem_raw[];
@@ -212,7 +224,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const uint32_t tA = tb, tTheta = tb + 64, tR = tb + 128, tAcc = tb + 384;
-  constexpr uint32_t id = idesc_tf32(128, 32), idb = idesc_bf16(128, 32);
+  constexpr uint32_t id = idesc_tf32(128, 32), idb = idesc_bf16(128, 32);       // MMA1: N = 32 rows of the block
+  constexpr uint32_t id2 = idesc_tf32(128, KB), id2b = idesc_bf16(128, KB);     // MMA2: N = KB components
+  constexpr int KS = KB / 8;                                                    // K steps of MMA1 per chain
 
   double ll_total = 0.0;
   if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
@@ -248,9 +262,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
         const uint32_t st = smem_u32(smem + s * HTC_STAGE_BYTES);
         const uint64_t dWh = desc_kmajor_sw128(st), dWc = desc_kmajor_sw128(st + 4096);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dWh + 2 * ks, id, ks > 0);            // hi . hi, tf32
+        for (int ks = 0; ks < KS; ++ks) mma_ts(tT, tA + 8 * ks, dWh + 2 * ks, id, ks > 0);           // hi . hi, tf32
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts_bf16(tT, tA + 32 + 8 * ks, dWc + 2 * ks, idb, 1);     // hi.lo + lo.hi, bf16
+        for (int i = 0; i < KS; ++i) {                                 // hi.lo + lo.hi, bf16: A [hi | lo], B [lo | hi];
+          const int ks = KB == 16 ? 2 * i : i;                         // KB = 16: hi[0..15] is K step 0, lo[0..15] K step 2
+          mma_ts_bf16(tT, tA + 32 + 8 * ks, dWc + 2 * ks, idb, 1);
+        }
         commit(&bar_theta[g]);
         if (!cd) commit(&bar_empty[s]);                                // loss-only pass: MMA1 is the last reader
       }
@@ -278,12 +295,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t acc = (ks > 0 || !chain_start) ? 1u : 0u;
             const uint32_t tr = tRb + 32 * ks;                         // Rp_hi +0, R_hi +8, Rp_c +16, R_c +24
-            mma_ts(tC, tr, dTh + 2 * ks, id, acc);                     // hi . hi, tf32
-            mma_ts(tS, tr + 8, dTh + 2 * ks, id, acc);
-#if !defined(TC_EXP) || TC_EXP < 1     // TC_EXP: timing experiments only (results are wrong)
-            mma_ts_bf16(tC, tr + 16, dTc + 2 * ks, idb, 1);            // hi.lo + lo.hi, bf16, K = 16 = 8 rows x (hi, lo)
-            mma_ts_bf16(tS, tr + 24, dTc + 2 * ks, idb, 1);
-#endif
+            mma_ts(tC, tr, dTh + 2 * ks, id2, acc);                    // hi . hi, tf32
+            mma_ts(tS, tr + 8, dTh + 2 * ks, id2, acc);
+            mma_ts_bf16(tC, tr + 16, dTc + 2 * ks, id2b, 1);           // hi.lo + lo.hi, bf16, K = 16 = 8 rows x (hi, lo)
+            mma_ts_bf16(tS, tr + 24, dTc + 2 * ks, id2b, 1);
           }
           commit(&bar_rfree[g]);
           commit(&bar_empty[s]);
@@ -320,24 +335,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);
     }
-    // fp32 sums of this thread's accumulator slice (k = 16 h .. 16 h + 15 of the group's C and S) live in
+    uint32_t fmask = 0u;                                               // all ones: this column accumulates the zeros' plane
+    if constexpr (FLIP) fmask = a.flipcol[col];
+    // fp32 sums of this thread's accumulator slice (k = HALF h .. of the group's Q and S, HALF = KB / 2) live in
     // shared memory: they are touched once per chain, registers are what the hot loop is short of
+    constexpr int HALF = KB / 2;
     float* __restrict__ myacc = sAcc + tid;
     if constexpr (CD) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) myacc[e * 512] = 0.f;
+      for (int e = 0; e < 2 * HALF; ++e) myacc[e * 512] = 0.f;
     }
     int flushed = 0;                                                   // chains of this group already flushed
     auto flush = [&]() {                                               // TMEM chain -> fp32 accumulators
       mbar_wait(&bar_cd[g], flushed & 1);
       fence_after_sync();
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {                           // C, then S
-        uint32_t c[16];
-        tmem_ld16(tAcc + 64 * g + 32 * part + lane_off + 16 * h, c);
-        wait_ld();
+      for (int part = 0; part < 2; ++part) {                           // Q, then S
+        if constexpr (KB == 32) {
+          uint32_t c[16];
+          tmem_ld16(tAcc + 64 * g + 32 * part + lane_off + 16 * h, c);
+          wait_ld();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) myacc[(16 * part + e) * 512] += __uint_as_float(c[e]);
+          for (int e = 0; e < 16; ++e) myacc[(16 * part + e) * 512] += __uint_as_float(c[e]);
+        } else {
+          uint32_t c[8];
+          tmem_ld8(tAcc + 64 * g + 32 * part + lane_off + 8 * h, c);
+          wait_ld();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) myacc[(8 * part + e) * 512] += __uint_as_float(c[e]);
+        }
       }
       ++flushed;
     };
@@ -359,6 +385,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       if (b + 2 < nb) {                                                // prefetch the next block's bits
         word = pc[(size_t)(b + 2) * 128];
         if constexpr (STRICT) mword = mc[(size_t)(b + 2) * 128];
+      }
+      uint32_t qbits = bits;                                           // the plane that is accumulated directly
+      if constexpr (FLIP) {
+        if constexpr (STRICT) { if (fmask) qbits = obits & ~bits; } else { qbits = bits ^ fmask; }
       }
       TC_EV(1 + g, b, 0);
       if (!ok_theta) mbar_wait(&bar_theta[g], ob & 1);
@@ -384,13 +414,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
         uint32_t out[32];
         float prod = 1.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {                                  // out: Rp_hi | R_hi | Rp_c | R_c, 8 columns each
+        for (int e = 0; e < 8; ++e) {                                  // out: Rq_hi | R_hi | Rq_c | R_c, 8 columns each
           float x;
           if constexpr (!CD)
             x = STRICT ? h_x_strict(__uint_as_float(v[8 * u + e]), bits, obits, 1u << (8 * u + e), eps)
                        : h_x(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps);
           else if constexpr (STRICT)
-            h_entry_strict(__uint_as_float(v[8 * u + e]), bits, obits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
+            h_entry_strict(__uint_as_float(v[8 * u + e]), bits, obits, qbits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
+          else if constexpr (FLIP)
+            h_entry_q(__uint_as_float(v[8 * u + e]), bits, qbits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
           else
             h_entry(__uint_as_float(v[8 * u + e]), bits, 1u << (8 * u + e), eps, x, out[8 + e], out[24 + e], out[e], out[16 + e]);
           prod = (e & 3) ? prod * x : x;
@@ -432,11 +464,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       if (g == 0) {                                                    // group 0 + group 1 (thread tid + 128), fixed order
         float* __restrict__ base = a.CD + (size_t)(split * 2) * 32 * a.ldh;   // C rows 0..31 then D rows 0..31
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {                                 // column j of row k: coalesced across the warp
-          const float c = myacc[e * 512] + myacc[e * 512 + 128];
-          const float sm = myacc[(16 + e) * 512] + myacc[(16 + e) * 512 + 128];
-          base[(size_t)(16 * h + e) * a.ldh + col] = c;
-          base[(size_t)(32 + 16 * h + e) * a.ldh + col] = sm - c;
+        for (int e = 0; e < HALF; ++e) {                               // column j of row k: coalesced across the warp
+          const float qv = myacc[e * 512] + myacc[e * 512 + 128];
+          const float sm = myacc[(HALF + e) * 512] + myacc[(HALF + e) * 512 + 128];
+          const float other = sm - qv;
+          base[(size_t)(HALF * h + e) * a.ldh + col] = (FLIP && fmask) ? other : qv;
+          base[(size_t)(32 + HALF * h + e) * a.ldh + col] = (FLIP && fmask) ? qv : other;
+        }
+        if constexpr (KB == 16) {                                      // rows 16..31 of the K <= 32 layout: padding
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            base[(size_t)(16 + 8 * h + e) * a.ldh + col] = 0.f;
+            base[(size_t)(48 + 8 * h + e) * a.ldh + col] = 0.f;
+          }
         }
       }
     }
@@ -462,7 +502,9 @@ constexpr int WTC_OFF_X = WTC_STAGES * WTC_STAGE_BYTES;           // group 1 -> 
 constexpr int WTC_OFF_Q = WTC_OFF_X + 16 * 256 * 4;
 constexpr int WTC_SMEM = WTC_OFF_Q + 4 * 128 * 4 + 1024;
 
+template <int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs a) {
+  static_assert(KB == 16 || KB == 32, "KB");
   using namespace tc;
   if (*a.done) return;
   extern __shared__ unsigned char smem_raw[];
@@ -495,7 +537,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const uint32_t tA = tb, tTheta = tb + 64, tS = tb + 192, tG = tb + 448;
-  constexpr uint32_t id1 = idesc_tf32(128, 64), id1b = idesc_bf16(128, 64), id2 = idesc_tf32(128, 32), id2b = idesc_bf16(128, 32);
+  constexpr uint32_t id1 = idesc_tf32(128, 64), id1b = idesc_bf16(128, 64), id2 = idesc_tf32(128, KB), id2b = idesc_bf16(128, KB);
+  constexpr int KS = KB / 8, NG = KB / 2;                              // K steps of MMA1; G columns one SIMT thread owns
 
   if (warp == TC_MMA1_WARP || warp == TC_MMA1_WARP + 1) {
     // ------------------------------------------------------------- MMA1 issuer of group g + producer of its stages
@@ -527,9 +570,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
         const uint32_t st = smem_u32(smem + s * WTC_STAGE_BYTES);
         const uint64_t dHh = desc_kmajor_sw128(st), dHc = desc_kmajor_sw128(st + 8192);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts(tT, tA + 8 * ks, dHh + 2 * ks, id1, ks > 0);           // hi . hi, tf32
+        for (int ks = 0; ks < KS; ++ks) mma_ts(tT, tA + 8 * ks, dHh + 2 * ks, id1, ks > 0);          // hi . hi, tf32
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_ts_bf16(tT, tA + 32 + 8 * ks, dHc + 2 * ks, id1b, 1);    // hi.lo + lo.hi, bf16
+        for (int i = 0; i < KS; ++i) {                                 // hi.lo + lo.hi, bf16 (KB = 16: see the H pass)
+          const int ks = KB == 16 ? 2 * i : i;
+          mma_ts_bf16(tT, tA + 32 + 8 * ks, dHc + 2 * ks, id1b, 1);
+        }
         commit(&bar_theta[g]);
       }
       __syncwarp();
@@ -554,9 +600,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
           const uint64_t dBc = desc_kmajor_sw128(st + 24576 + (ks >> 2) * 4096) + 2 * (ks & 3);
           const uint32_t ts = tSb + 16 * ks;                             // S_hi +0, S_c +8
           mma_ts(tGa, ts, dBh, id2, (ks > 0 || !chain_start) ? 1u : 0u); // hi . hi, tf32
-#if !defined(TC_EXP) || TC_EXP < 1
           mma_ts_bf16(tGa, ts + 8, dBc, id2b, 1);                        // hi.lo + lo.hi, bf16
-#endif
         }
         commit(&bar_sfree[g]);
         commit(&bar_empty[s]);
@@ -598,18 +642,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);
     }
-    float accG[16];                                                    // k = 16 h .. 16 h + 15 of the group's G, fp32
+    float accG[NG];                                                    // k = NG h .. NG h + NG - 1 of the group's G, fp32
 #pragma unroll
-    for (int e = 0; e < 16; ++e) accG[e] = 0.f;
+    for (int e = 0; e < NG; ++e) accG[e] = 0.f;
     int flushed = 0;
     auto flush = [&]() {                                               // TMEM chain -> fp32 register accumulators
       mbar_wait(&bar_g[g], flushed & 1);
       fence_after_sync();
-      uint32_t c[16];
-      tmem_ld16(tG + 32 * g + lane_off + 16 * h, c);
-      wait_ld();
+      if constexpr (KB == 32) {
+        uint32_t c[16];
+        tmem_ld16(tG + 32 * g + lane_off + 16 * h, c);
+        wait_ld();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) accG[e] += __uint_as_float(c[e]);
+        for (int e = 0; e < 16; ++e) accG[e] += __uint_as_float(c[e]);
+      } else {
+        uint32_t c[8];
+        tmem_ld8(tG + 32 * g + lane_off + 8 * h, c);
+        wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) accG[e] += __uint_as_float(c[e]);
+      }
       ++flushed;
     };
     const uint2* __restrict__ pm = a.PM + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5) + h) * 128 + tl;
@@ -666,13 +718,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     const int t = h * 128 + tl;                                        // same (lane, k range) in both groups
     if (g == 1) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) sX[e * 256 + t] = accG[e];
+      for (int e = 0; e < NG; ++e) sX[e * 256 + t] = accG[e];
     }
     asm volatile("bar.sync 1, 512;" ::: "memory");                     // the 16 SIMT warps only
     if (g == 0 && row < a.m) {                                         // group 0 + group 1, fixed order
-      float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * 32 + 16 * h;
+      float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * 32 + NG * h;
 #pragma unroll
-      for (int e = 0; e < 16; e += 4)
+      for (int e = 0; e < NG; e += 4)
         *reinterpret_cast<float4*>(Gg + e) =
             make_float4(accG[e] + sX[e * 256 + t], accG[e + 1] + sX[(e + 1) * 256 + t],
                         accG[e + 2] + sX[(e + 2) * 256 + t], accG[e + 3] + sX[(e + 3) * 256 + t]);
@@ -685,26 +737,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   if (warp == TC_MMA1_WARP) tmem_dealloc(tb, 512);
 }
 
+template <int KB>
 inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_set{0};
-  ensure_dynamic_smem(w_pass_tc_kernel, WTC_SMEM, attr_set);
+  ensure_dynamic_smem(w_pass_tc_kernel<KB>, WTC_SMEM, attr_set);
   dim3 grid((unsigned)((a.m + 127) / 128), (unsigned)nsplit);
-  w_pass_tc_kernel<<<grid, TC_THREADS, WTC_SMEM, st>>>(a);
+  w_pass_tc_kernel<KB><<<grid, TC_THREADS, WTC_SMEM, st>>>(a);
 }
+// One thread block decides, per H pass, which columns accumulate the zeros' plane directly (density of ones above the
+// mean of the column of H, see h_pass_tc_kernel) and whether any does.  n loads of K values: microseconds.
+__global__ void __launch_bounds__(1024) flip_cols_kernel(const float* __restrict__ H, int64_t ldh, int64_t n, int k, int64_t m,
+                                                         const uint32_t* __restrict__ colcnt, uint32_t* __restrict__ flipcol,
+                                                         int* __restrict__ flip_any, const int* __restrict__ done) {
+  if (*done) return;
+  int any = 0;
+  for (int64_t j = threadIdx.x; j < ldh; j += blockDim.x) {
+    uint32_t f = 0u;
+    if (j < n) {
+      float hsum = 0.f;
+      for (int kk = 0; kk < k; ++kk) hsum += H[(size_t)kk * ldh + j];
+      if ((float)colcnt[j] * (float)k > hsum * (float)m) f = 0xffffffffu;      // density > mean H
+    }
+    flipcol[j] = f;
+    any |= (f != 0u);
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) *flip_any = any;
+}
+
+template <int KB>
 inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, cudaStream_t st) {
-  static std::atomic<unsigned long long> attr_set[4];
-  ensure_dynamic_smem(h_pass_tc_kernel<false, true>, HTC_SMEM, attr_set[0]);
-  ensure_dynamic_smem(h_pass_tc_kernel<true, true>, HTC_SMEM, attr_set[1]);
-  ensure_dynamic_smem(h_pass_tc_kernel<false, false>, HTC_SMEM, attr_set[2]);
-  ensure_dynamic_smem(h_pass_tc_kernel<true, false>, HTC_SMEM, attr_set[3]);
+  static std::atomic<unsigned long long> attr_set[6];
+  ensure_dynamic_smem(h_pass_tc_kernel<KB, false, true, false>, HTC_SMEM, attr_set[0]);
+  ensure_dynamic_smem(h_pass_tc_kernel<KB, true, true, false>, HTC_SMEM, attr_set[1]);
+  ensure_dynamic_smem(h_pass_tc_kernel<KB, false, false, false>, HTC_SMEM, attr_set[2]);
+  ensure_dynamic_smem(h_pass_tc_kernel<KB, true, false, false>, HTC_SMEM, attr_set[3]);
+  ensure_dynamic_smem(h_pass_tc_kernel<KB, false, true, true>, HTC_SMEM, attr_set[4]);
+  ensure_dynamic_smem(h_pass_tc_kernel<KB, true, true, true>, HTC_SMEM, attr_set[5]);
   dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit);
   if (a.compute_cd) {
-    if (a.Mc) h_pass_tc_kernel<true, true><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
-    else h_pass_tc_kernel<false, true><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+    const bool flips = a.colcnt != nullptr && a.flipcol != nullptr && a.flip_any != nullptr;
+    HTcArgs b = a;
+    if (!flips) b.flip_any = nullptr;                                  // no decision data: the FLIP = false kernel always runs
+    else flip_cols_kernel<<<1, 1024, 0, st>>>(a.H, a.ldh, a.n, a.k, a.m, a.colcnt, const_cast<uint32_t*>(a.flipcol),
+                                              const_cast<int*>(a.flip_any), a.done);
+    if (a.Mc) h_pass_tc_kernel<KB, true, true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
+    else h_pass_tc_kernel<KB, false, true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
+    if (flips) {
+      if (a.Mc) h_pass_tc_kernel<KB, true, true, true><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
+      else h_pass_tc_kernel<KB, false, true, true><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
+    }
   } else {
-    if (a.Mc) h_pass_tc_kernel<true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
-    else h_pass_tc_kernel<false, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(a);
+    HTcArgs b = a;
+    b.flip_any = nullptr;
+    if (a.Mc) h_pass_tc_kernel<KB, true, false, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
+    else h_pass_tc_kernel<KB, false, false, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
   }
 }
 
+}  // namespace k32
 }  // namespace nbmf

@@ -344,14 +344,31 @@ class DeviceProblem:
         self._call("nbmf_ingest_bits_end", C.byref(cnt))
         return float(cnt.value)
 
+    def release_planes(self) -> bool:
+        """Drop this object's references to the caller's bit planes when the context no longer reads them (tensor engine:
+        it works on re-tiled copies).  Returns True if they were dropped; the memory goes back to torch's pool as soon as
+        the caller holds no other reference."""
+        if self._ctx and not self.lib.nbmf_planes_in_use(self._ctx):
+            torch = _torch()
+            for t in self._keep:                        # frees are stream-ordered after the re-tiling that reads them
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream(self.dev))
+            self._keep = []
+            return True
+        return False
+
     def set_n_obs(self, n_obs):
         self._call("nbmf_set_n_obs", float(n_obs))
 
-    def set_dense(self, Vm, M: BitMatrix | None = None):
+    def set_dense(self, Vm, M: BitMatrix | None = None, Wm=None):
+        """Dense layout: ``Vm`` = V * mask, ``M`` = bit plane of (mask != 0), ``Wm`` = the VALUES of a weighted mask in the
+        same dense layout (``None`` for a 0/1 mask)."""
         if M is not None:
             M = M if M.is_device else M.to_device(self.dev)
-        self._keep = [Vm, None if M is None else M.words]
+        self._keep = [Vm, None if M is None else M.words, Wm]
         self._call("nbmf_set_data_dense", _ptr(Vm), _ptr(None if M is None else M.words))
+        if Wm is not None:
+            self._call("nbmf_set_mask_weights", _ptr(Wm))
 
     # -- factors
     def _to_dev(self, A, shape):

@@ -83,7 +83,7 @@ class NBMFMM(BaseEstimator, TransformerMixin):
     dense_storage : {None, "float16"}: device layout of probabilistic X (values strictly inside (0,1)); None = the
         compute dtype, "float16" halves the bytes each pass reads (float32 arithmetic only).
     engine : {"auto", "simt", "tensor"}: CUDA-core (packed FFMA2) kernels or the tcgen05/TMEM split-precision (TF32 + bf16)
-        kernels (float32, binary X, K <= 32 only); "auto" picks tensor when eligible and m, n >= 512.
+        kernels (float32, binary X, K <= 64); "auto" picks tensor when eligible and m, n >= 512.
     """
 
     def __init__(self, n_components=10, alpha=1.2, beta=1.2, max_iter=2000, tol=1e-5,

@@ -39,9 +39,9 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     ``jobs``: sequence of dicts with ``n_components`` and optionally ``alpha``, ``beta`` (default 1.2),
     ``random_state``, ``W_init``, ``H_init``, ``max_iter``, ``tol`` (defaults: the keyword arguments).  Returns a
     list of ``(W, H, losses, 0.0, n_iter)`` in job order, each identical to
-    ``nbmf_mm_solver(Y, mask=mask, orientation=orientation, **job)``.  ``batch``: jobs that differ only in their
-    inits (same K, alpha, beta, max_iter, tol: restarts) advance together on small problems, one launch per kernel
-    for the whole group (``nbmf_batch_bind``).  ``n_streams``: concurrent fits for the remaining jobs
+    ``nbmf_mm_solver(Y, mask=mask, orientation=orientation, **job)``.  ``batch``: jobs with the same K, max_iter and
+    tol (restarts, alpha / beta grids) advance together on small problems, one launch per kernel for the whole group
+    (``nbmf_batch_bind``).  ``n_streams``: concurrent fits for the remaining jobs
     (default: one per hardware queue, 8..32, for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own)."""
     import torch
     if orientation not in _CANON:
@@ -102,7 +102,7 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
         """Fits with the same K and hyper-parameters advance TOGETHER: contexts with workspaces at a uniform stride in one
         allocation, one launch per kernel for the whole group (``nbmf_batch_bind``).  Returns None when the group is not
         eligible (tensor engine), else the results in the order of ``idxs``."""
-        k, alpha, beta, mi, tl = prepared[idxs[0]][:5]
+        k, _, _, mi, tl = prepared[idxs[0]][:5]
         B = len(idxs)
         big = {}
 
@@ -120,7 +120,7 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
             stream.wait_event(ready)
             try:
                 for b, idx in enumerate(idxs):
-                    prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps,
+                    prob = make_problem(data, k, dtype=dtype, alpha=prepared[idx][1], beta=prepared[idx][2], eps=eps,
                                         mask_semantics=mask_semantics, projection=projection_method, max_iter_cap=mi,
                                         device=device, engine=engine, workspace=slice_of(b))
                     probs.append(prob)
@@ -152,13 +152,14 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                     prob.close()
         return out
 
-    # groups of fits that can advance together (restarts: same K, alpha, beta, max_iter, tol) on small problems
+    # groups of fits that can advance together (same K, max_iter, tol: restarts AND alpha / beta grids -- the Beta prior
+    # lives in each fit's device-side state) on small problems
     results = [None] * len(jobs)
     batched = 0
     if batch and m * n <= (1 << 24) and data.vkind == "bits":
         groups = {}
         for i, pj in enumerate(prepared):
-            groups.setdefault(pj[:5], []).append(i)
+            groups.setdefault((pj[0], pj[3], pj[4]), []).append(i)
         for idxs in groups.values():
             if len(idxs) < 2:
                 continue

@@ -30,6 +30,7 @@ class PreparedData:
     Vm: object                 # torch tensor V*mask  (dense)
     n_obs: float               # Y.size or count_nonzero(mask), _solver.py:151,155
     h2d_bytes: int = 0
+    Wm: object = None          # torch tensor: values of a weighted (non-0/1) mask, dense layout (vkind "dense" only)
     pending: object = None     # deferred device work (P &= M, orientation, n_obs): see finish()
 
     def finish(self):
@@ -45,13 +46,17 @@ def _densify(a):
     return a.toarray() if hasattr(a, "toarray") else a
 
 
+_WEIGHTED_BITS = ("a weighted (non-0/1) mask needs dense X / mask arrays: the reference multiplies by the mask values "
+                  "(_solver.py:30-32), which the bit-packed inputs cannot carry")
+
+
 def _as_bool_mask(mask, shape):
     mask = np.asarray(_densify(mask))
     if mask.shape != tuple(shape):
         raise ValueError(f"mask has shape {mask.shape}, expected {tuple(shape)}")
     if mask.dtype != np.bool_:
         if not np.all((mask == 0) | (mask == 1)):
-            raise ValueError("mask must be binary (0/1 or bool): weighted masks are not supported by the bit-packed path")
+            raise ValueError(_WEIGHTED_BITS)
         mask = mask != 0
     return mask
 
@@ -76,15 +81,21 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storag
         if flags & 1:
             Y = Y.toarray()                                           # values strictly inside (0,1): dense layout
             extra_h2d = 0
+        elif (mask is not None and not isinstance(mask, BitMatrix) and not hasattr(mask, "tocsr")
+              and np.asarray(mask).dtype != np.bool_ and not np.all((np.asarray(mask) == 0) | (np.asarray(mask) == 1))):
+            Y, extra_h2d = Y.toarray(), 0                             # dense weighted mask: the dense layout carries it
         else:
             if mask is not None and hasattr(mask, "tocsr"):
                 if mask.shape != Y.shape:
                     raise ValueError(f"mask has shape {mask.shape}, expected {tuple(Y.shape)}")
-                mask, mflags, mh = pack_csr_device(mask, dev)
-                if mflags & 1:
-                    raise ValueError("mask must be binary (0/1 or bool): weighted masks are not supported by the bit-packed path")
-                extra_h2d += mh
-            Y = Pd
+                mflags = 1 if (mask.data.size and not np.all((mask.data == 0) | (mask.data == 1))) else 0
+                if mflags & 1:                                        # weighted sparse mask: the dense layout carries it
+                    Y, mask, extra_h2d = Y.toarray(), mask.toarray(), 0
+                else:
+                    mask, mflags, mh = pack_csr_device(mask, dev)
+                    extra_h2d += mh
+            if hasattr(Y, "tocsr"):
+                Y = Pd
     if isinstance(Y, BitMatrix):
         P = Y
         M = mask
@@ -122,11 +133,10 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storag
     # dense host arrays: the value checks and the packing run on the device, on row chunks of the arrays as they are
     # (external orientation; dir-beta transposes the packed planes)
     P, M, flags, h2d = pack_host_dense_checked(Y, mask, dev)
-    if flags & 4:
-        raise ValueError("mask must be binary (0/1 or bool): weighted masks are not supported by the bit-packed path")
+    weighted = bool(flags & 4)                                        # mask values other than 0 / 1: dense layout below
     if check_range and (flags & 2):
         raise ValueError("X must be binary")                          # _base.py:90-91
-    if not (flags & 1):
+    if not (flags & 1) and not weighted:
         if transpose:
             P = P.transpose()
             M = None if M is None else M.transpose()
@@ -141,7 +151,7 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storag
         mk = None if mk is None else mk.T
     m, n = Y.shape
     n_obs = float(Y.size) if mk is None else float(np.count_nonzero(mk))
-    # probabilistic V: dense V*mask in the compute dtype + mask bits
+    # probabilistic V (or a weighted mask): dense V*mask in the compute dtype + mask bits
     Yd = torch.from_numpy(np.ascontiguousarray(Y)).to(dev)
     h2d = Y.nbytes
     md = None
@@ -150,6 +160,18 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storag
         md = torch.from_numpy(np.ascontiguousarray(mk).view(np.uint8)).to(dev)
         h2d += mk.nbytes
         M, _ = pack_bits_device(md, None)
+    if weighted:
+        # the reference multiplies by the mask VALUES (_solver.py:30-32): V * mask for the H half-step and the loss,
+        # (1 - V) * mask = mask - V * mask for the W half-step; the bit plane (mask != 0) only counts the observed entries
+        if dense_storage == "float16":
+            raise ValueError("a weighted mask needs the dense layout in the compute dtype (dense_storage=None)")
+        wv = np.asarray(mask, dtype=np.float64)
+        wv = np.ascontiguousarray(wv.T if transpose else wv)
+        wd = torch.from_numpy(wv).to(dev)
+        h2d += wv.nbytes
+        Vm = pack_dense_device(Yd, wd, dtype)
+        Wm = pack_dense_device(wd, None, dtype)
+        return PreparedData(m, n, "dense", None, M, Vm, n_obs, h2d, Wm=Wm)
     if dense_storage not in (None, "float16", "float32", "float64"):
         raise ValueError(f"dense_storage must be None, 'float16', 'float32' or 'float64', got {dense_storage!r}")
     if dense_storage == "float16":                             # fp16 layout: half the HBM bytes per pass
@@ -169,11 +191,13 @@ def make_problem(data: PreparedData, k, *, dtype, alpha, beta, eps, mask_semanti
     if data.vkind == "bits":
         prob.set_bits(data.P, data.M)
     else:
-        prob.set_dense(data.Vm, data.M)
+        if data.Wm is not None and mask_semantics == "strict":
+            raise ValueError("weighted masks are defined for mask_semantics='reference' only")
+        prob.set_dense(data.Vm, data.M, data.Wm)
     return prob
 
 
-TENSOR_MAX_K = 32            # largest n_components the tcgen05 engine covers (capi.cu make_plan)
+TENSOR_MAX_K = 64            # largest n_components the tcgen05 engine covers (capi.cu make_plan)
 
 
 def resolve_engine(engine, *, dtype, vkind, k, eps, m_total, n):
@@ -262,7 +286,7 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     ``distributed``: ``Y``/``mask`` are already this rank's row block of an ``m_total``-row
     problem in internal orientation; the returned W is the local block, H is global),
     ``engine`` ("auto" | "simt" | "tensor": packed-FFMA2 CUDA-core kernels or the tcgen05/TMEM
-    split-precision kernels; the tensor engine needs float32, binary V, K <= 32), ``dense_storage`` ("float16":
+    split-precision kernels; the tensor engine needs float32, binary V, K <= 64), ``dense_storage`` ("float16":
     probabilistic V is stored as fp16 on the device, float32 arithmetic; default = the compute dtype),
     ``check_range`` (raise the estimator's ``ValueError("X must be binary")``, ``_base.py:90-91``, when a dense ``Y``
     holds a value outside [0, 1]: the test runs on the device, in the pass that packs ``Y``).
@@ -405,7 +429,8 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
             data = PreparedData(r1 - r0, n, data.vkind,
                                 None if data.P is None else data.P.rows(r0, r1),
                                 None if data.M is None else data.M.rows(r0, r1),
-                                None if data.Vm is None else data.Vm[r0:r1], n_obs_global, data.h2d_bytes)
+                                None if data.Vm is None else data.Vm[r0:r1], n_obs_global, data.h2d_bytes,
+                                Wm=None if data.Wm is None else data.Wm[r0:r1])
         if world > 1:
             engine = resolve_engine(engine, dtype=dtype, vkind=data.vkind, k=k, eps=eps, m_total=m, n=n)
         prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
@@ -418,6 +443,8 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
         if streamed:                                       # count_nonzero(mask) of this shard, _solver.py:151,155
             n_obs_local = prob.finish_bits()
             prob.set_n_obs(all_ranks_sum(n_obs_local) if world > 1 else n_obs_local)
+        if prob.release_planes() and data is not None and data.vkind == "bits" and not isinstance(Y, BitMatrix):
+            data.P = data.M = None                         # tensor engine: the row-major planes packed from X are not read again
         losses_arr, n_iter, converged = prob.fit(max_iter, tol)
         # tail of the reference solver (_solver.py:192-213) on the device: the simplex factor is the internal W in
         # both orientations; it is renormalised (fp64) only when its worst deviation exceeds 1e-9 -- the worst over

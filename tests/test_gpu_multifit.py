@@ -92,3 +92,23 @@ def test_batched_restarts_equal_sequential_solver_calls(orientation, dtype, proj
                              projection_method=projection, batch=False)
     for a, b in zip(got, plain):
         assert a[4] == b[4] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_batched_alpha_beta_grid_equals_sequential_solver_calls(dtype):
+    """The 36-point alpha / beta grid of the reference's experiment driver (examples/reproduce_magron2022.py:87-117): the
+    Beta prior lives in each fit's device-side state, so the whole grid (same K, max_iter, tol) advances with one launch
+    per kernel.  Bit-identical to the loop of solver calls."""
+    X, mask = _data(seed=3)
+    grid = [1.0, 1.2, 1.4, 1.6, 1.8, 2.0]
+    jobs = [dict(n_components=8, alpha=a, beta=b, random_state=12345) for a in grid for b in grid]
+    stats = {}
+    got = nbmf_mm_multifit(X, jobs, mask=mask, max_iter=30, tol=1e-5, dtype=dtype, stats=stats)
+    assert stats["batched"] == 36
+    finals = set()
+    for j, out in list(zip(jobs, got))[::5]:
+        W, H, losses, _, n_iter = nbmf_mm_solver(X, mask=mask, max_iter=30, tol=1e-5, dtype=dtype, **j)
+        assert n_iter == out[4] and np.array_equal(losses, out[2]), j
+        assert np.array_equal(W, out[0]) and np.array_equal(H, out[1]), j
+        finals.add(float(losses[-1]))
+    assert len(finals) > 3                                        # the priors did differ

@@ -1,4 +1,4 @@
-"""The tcgen05/TMEM engine (tc_passes.cuh; float32, bit-packed V, K <= 32, TF32 + bf16 split precision) against the
+"""The tcgen05/TMEM engine (tc_passes.cuh; float32, bit-packed V, K <= 64, TF32 + bf16 split precision) against the
 oracle, the golden reference trajectories and the SIMT engine.  Same FP32-mode bars as the SIMT
 kernels: one step <= 5e-5 relative, final NLL <= 1e-4 relative after the same iteration count,
 simplex <= 1e-6, monotone objective."""
@@ -30,6 +30,12 @@ def problem(m, n, k, seed, masked=True, density=0.2):
     (1000, 333, 6, False),
     (77, 4100, 1, True),
     (2500, 190, 25, True),
+    (300, 700, 8, True),           # K <= 16 instantiation (skips the padded half of the K extent)
+    (1111, 300, 16, False),
+    (517, 1300, 33, True),         # K <= 64 instantiation (three pipelines, one accumulator set)
+    (2200, 400, 48, True),
+    (700, 2111, 64, False),
+    (130, 70, 64, True),
 ])
 def test_one_step_against_oracle(m, n, k, masked):
     Y, mask, W, H = problem(m, n, k, seed=m + n + k, masked=masked)
@@ -41,7 +47,7 @@ def test_one_step_against_oracle(m, n, k, masked):
     assert rel_err(H1, Hs) < 2e-5 and rel_err(W1, Ws) < 2e-5
 
 
-@pytest.mark.parametrize("m,n,k", [(517, 1300, 32), (130, 70, 10), (900, 600, 17)])
+@pytest.mark.parametrize("m,n,k", [(517, 1300, 32), (130, 70, 10), (900, 600, 17), (640, 900, 40)])
 def test_strict_mask_semantics_on_the_tensor_engine(m, n, k):
     """README / paper mask semantics (unobserved entries contribute nothing to the H step and the loss): the strict
     variant of the tensor H pass against the oracle, one step, the fused objective and a short monotone fit."""
@@ -63,7 +69,7 @@ def test_strict_mask_semantics_on_the_tensor_engine(m, n, k):
     assert n_iter == 30 and np.all(np.diff(losses) <= 2e-6 * np.abs(losses[:-1]))   # strict semantics is a true MM
 
 
-@pytest.mark.parametrize("m,n,k", [(517, 1300, 32), (130, 70, 10)])
+@pytest.mark.parametrize("m,n,k", [(517, 1300, 32), (130, 70, 10), (700, 333, 57)])
 def test_fused_objective(m, n, k):
     Y, mask, W, H = problem(m, n, k, seed=5)
     want = orc.map_objective(Y, W, H, mask, 1.2, 1.3)
@@ -113,7 +119,7 @@ def test_auto_engine_selection_and_ineligible_requests():
     with make_problem(data, 8, dtype="float32", mask_semantics="strict", **kw) as p:
         assert p.engine == "tensor"                                  # strict H pass variant reads the mask plane too
     with make_problem(data, 40, dtype="float32", mask_semantics="reference", **kw) as p:
-        assert p.engine == "simt"
+        assert p.engine == "tensor"                                  # K <= 64: the 3-pipeline instantiation
     d64 = prepare_data(Y, mask, transpose=False, dtype="float64", device=None)
     with make_problem(d64, 8, dtype="float64", mask_semantics="reference", **kw) as p:
         assert p.engine == "simt"

@@ -4,8 +4,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
-#include "tc_passes.cuh"
+#include "tc_passes_k32.cuh"
 using namespace nbmf;
+using namespace nbmf::k32;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
 __global__ void fill(float* p, size_t n, float scale) {
@@ -29,11 +30,11 @@ int main(int argc, char** argv) {
   fill<<<1024, 256>>>(H, 32 * ldh, 0.9f); fill<<<1024, 256>>>(Wf, mpad * 128, 0.03f); fillu<<<1024, 256>>>(Pc, ldh * mpad / 32);
   set_trace<<<1, 1>>>(tr);
   HTcArgs a; a.H = H; a.Wf = Wf; a.Pc = Pc; a.Mc = nullptr; a.m = m; a.n = n; a.ldh = ldh; a.nrb = mpad / 32; a.rows_per_split = mpad;
-  a.CD = CD; a.LL = LL; a.eps = 1e-8f; a.done = done; a.compute_cd = 1;
+  a.CD = CD; a.LL = LL; a.eps = 1e-8f; a.done = done; a.compute_cd = 1; a.k = 32; a.colcnt = nullptr; a.flipcol = nullptr; a.flip_any = nullptr;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  launch_h_pass_tc(a, 1, 0);
+  launch_h_pass_tc<32>(a, 1, 0);
   CK(cudaDeviceSynchronize());
-  cudaEventRecord(e0); launch_h_pass_tc(a, 1, 0); cudaEventRecord(e1);
+  cudaEventRecord(e0); launch_h_pass_tc<32>(a, 1, 0); cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("H pass: %d blocks/CTA, %.3f ms, %.1f cycles/block at 1.965 GHz, %.2f entries/clk/SM\n", nblocks, ms,
