@@ -744,25 +744,32 @@ inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
   dim3 grid((unsigned)((a.m + 127) / 128), (unsigned)nsplit);
   w_pass_tc_kernel<KB><<<grid, TC_THREADS, WTC_SMEM, st>>>(a);
 }
-// One thread block decides, per H pass, which columns accumulate the zeros' plane directly (density of ones above the
-// mean of the column of H, see h_pass_tc_kernel) and whether any does.  n loads of K values: microseconds.
-__global__ void __launch_bounds__(1024) flip_cols_kernel(const float* __restrict__ H, int64_t ldh, int64_t n, int k, int64_t m,
-                                                         const uint32_t* __restrict__ colcnt, uint32_t* __restrict__ flipcol,
-                                                         int* __restrict__ flip_any, const int* __restrict__ done) {
+// Decides, per H pass, which columns accumulate the zeros' plane directly (density of ones above the mean of the column
+// of H, see h_pass_tc_kernel) and whether any does.  One thread per column (K coalesced loads); the grid-wide "any" is an
+// integer OR collected by the last block to finish (order-independent: deterministic).  flag[0] = result, flag[1] =
+// OR in progress, flag[2] = blocks finished; the last block resets [1], [2] for the next launch.
+__global__ void __launch_bounds__(256) flip_cols_kernel(const float* __restrict__ H, int64_t ldh, int64_t n, int k, int64_t m,
+                                                        const uint32_t* __restrict__ colcnt, uint32_t* __restrict__ flipcol,
+                                                        int* __restrict__ flag, const int* __restrict__ done) {
   if (*done) return;
-  int any = 0;
-  for (int64_t j = threadIdx.x; j < ldh; j += blockDim.x) {
-    uint32_t f = 0u;
-    if (j < n) {
-      float hsum = 0.f;
-      for (int kk = 0; kk < k; ++kk) hsum += H[(size_t)kk * ldh + j];
-      if ((float)colcnt[j] * (float)k > hsum * (float)m) f = 0xffffffffu;      // density > mean H
-    }
-    flipcol[j] = f;
-    any |= (f != 0u);
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t f = 0u;
+  if (j < n) {
+    float hsum = 0.f;
+    for (int kk = 0; kk < k; ++kk) hsum += H[(size_t)kk * ldh + j];
+    if ((float)colcnt[j] * (float)k > hsum * (float)m) f = 0xffffffffu;        // density > mean H
   }
-  any = __syncthreads_or(any);
-  if (threadIdx.x == 0) *flip_any = any;
+  if (j < ldh) flipcol[j] = f;
+  const int any = __syncthreads_or(f != 0u);
+  if (threadIdx.x == 0) {
+    if (any) atomicOr(&flag[1], 1);
+    __threadfence();
+    if (atomicAdd(&flag[2], 1) == (int)gridDim.x - 1) {                        // last block: publish and reset
+      __threadfence();
+      flag[0] = atomicExch(&flag[1], 0);
+      flag[2] = 0;
+    }
+  }
 }
 
 template <int KB>
@@ -779,8 +786,9 @@ inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, cudaStream_t st) {
     const bool flips = a.colcnt != nullptr && a.flipcol != nullptr && a.flip_any != nullptr;
     HTcArgs b = a;
     if (!flips) b.flip_any = nullptr;                                  // no decision data: the FLIP = false kernel always runs
-    else flip_cols_kernel<<<1, 1024, 0, st>>>(a.H, a.ldh, a.n, a.k, a.m, a.colcnt, const_cast<uint32_t*>(a.flipcol),
-                                              const_cast<int*>(a.flip_any), a.done);
+    else flip_cols_kernel<<<(unsigned)((a.ldh + 255) / 256), 256, 0, st>>>(a.H, a.ldh, a.n, a.k, a.m, a.colcnt,
+                                                                         const_cast<uint32_t*>(a.flipcol),
+                                                                         const_cast<int*>(a.flip_any), a.done);
     if (a.Mc) h_pass_tc_kernel<KB, true, true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
     else h_pass_tc_kernel<KB, false, true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
     if (flips) {

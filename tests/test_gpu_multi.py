@@ -103,3 +103,48 @@ def test_restarts_partitioned_over_two_gpus_match_sequential(tmp_path):
     assert int(got["best"]) == seq.best_init_
     assert np.array_equal(got["W"], seq.W_) and np.array_equal(got["H"], seq.components_)
     assert np.array_equal(got["losses"], np.asarray(seq.loss_curve_))
+
+
+def _unseeded_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from nbmf_mm_b200 import nbmf_mm_solver
+        X, mask = _problem()
+        np.random.seed(100 + rank)                               # every rank's own global stream is in a different state
+        W, H, losses, _, n_iter = nbmf_mm_solver(X, 9, max_iter=50, tol=1e-5, mask=mask, random_state=None,
+                                                 dtype="float32", distributed=True)
+        # dir-beta with dense inputs: each rank uploads only its block of COLUMNS of X (internal rows)
+        Wd, Hd, ld, _, nd = nbmf_mm_solver(X, 7, max_iter=30, tol=0.0, mask=mask, random_state=4, dtype="float64",
+                                           distributed=True, orientation="dir-beta")
+        np.savez(f"{out}.{rank}.npz", W=W, H=H, losses=np.asarray(losses), n_iter=n_iter, Wd=Wd, Hd=Hd, ld=np.asarray(ld))
+    finally:
+        from nbmf_mm_b200.device import destroy_cached_comms
+        destroy_cached_comms()
+        dist.destroy_process_group()
+
+
+def test_unseeded_row_shards_agree_and_dir_beta_slices_columns(tmp_path):
+    """random_state=None: every rank is its own process with its own global NumPy stream; rank 0's seed is broadcast so
+    that all ranks start from the same H (they would otherwise diverge, and ranks that stop at different iterations
+    enqueue different numbers of collectives).  And dir-beta on dense inputs: a rank's row block of the internal problem
+    is a block of columns of X."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nbmf_mm_b200 import nbmf_mm_solver
+    out = str(tmp_path / "unseeded")
+    mp.spawn(_unseeded_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = np.load(f"{out}.0.npz"), np.load(f"{out}.1.npz")
+    assert int(a["n_iter"]) == int(b["n_iter"]) and np.array_equal(a["losses"], b["losses"])
+    assert np.array_equal(a["H"], b["H"]) and np.array_equal(a["W"], b["W"])
+    assert np.all(np.diff(a["losses"]) <= 2e-6 * np.abs(a["losses"][:-1]))
+    X, mask = _problem()
+    W1, H1, l1, _, _ = nbmf_mm_solver(X, 7, max_iter=30, tol=0.0, mask=mask, random_state=4, dtype="float64", orientation="dir-beta")
+    assert np.array_equal(a["Wd"], b["Wd"]) and np.max(np.abs(a["Wd"] - W1)) < 1e-10 and np.max(np.abs(a["Hd"] - H1)) < 1e-10
+    assert np.max(np.abs(a["ld"] - np.asarray(l1)) / np.abs(l1)) < 1e-11

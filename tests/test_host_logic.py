@@ -153,3 +153,18 @@ def test_solver_rejects_bad_shapes_before_touching_the_device():
         nbmf_mm_solver(np.zeros((4, 4)), 2, max_iter=0)
     with pytest.raises(ValueError, match="shard"):
         nbmf_mm_solver(np.zeros((4, 4)), 2, shard=(0, 8))
+
+
+def test_engine_is_resolved_from_the_global_problem_size():
+    """Row shards must agree on the engine (the tensor engine pads K to its own tile: ranks that disagreed would
+    all-reduce differently shaped buffers).  m = 2000 on 4 ranks gives shards of 512, 512, 512 and 464 rows: decided per
+    shard, three ranks would take the tensor engine and one the SIMT engine."""
+    from nbmf_mm_b200.solver import resolve_engine
+    kw = dict(dtype="float32", vkind="bits", k=20, eps=1e-8, n=4096)
+    assert [_row_shard(2000, r, 4) for r in range(4)] == [(0, 512), (512, 1024), (1024, 1536), (1536, 2000)]
+    assert resolve_engine("auto", m_total=2000, **kw) == "tensor"
+    assert resolve_engine("auto", m_total=400, **kw) == "simt"
+    assert resolve_engine("simt", m_total=2000, **kw) == "simt"
+    assert resolve_engine("auto", m_total=2000, dtype="float64", vkind="bits", k=20, eps=1e-8, n=4096) == "simt"
+    assert resolve_engine("auto", m_total=2000, dtype="float32", vkind="dense", k=20, eps=1e-8, n=4096) == "simt"
+    assert resolve_engine("auto", m_total=2000, dtype="float32", vkind="bits", k=65, eps=1e-8, n=4096) == "simt"

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--cols", type=int, default=100_000)
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--tag", default="r02")
+    ap.add_argument("--from-csv", default=None, help="re-derive the table from a CSV of an earlier run instead of running ncu")
     a = ap.parse_args()
     shape = f"{a.rows}x{a.cols}x{a.k}"
     out_csv = ROOT / "profiles" / f"{a.tag}_ncu_pass_kernel_counters_{a.rows}x{a.cols}_k{a.k}.csv"
@@ -34,8 +35,11 @@ def main():
     cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-k", "regex:(h|w)_pass_tc_kernel|(h|w)_pass_kernel",
            "--csv", "--log-file", str(out_csv), sys.executable, str(ROOT / "bench.py"), "--rows", str(a.rows), "--cols", str(a.cols),
            "--k", str(a.k), "--steps", "1", "--warmup", "1", "--no-e2e", "--no-cpu", "--no-parity"]
-    print(" ".join(cmd), flush=True)
-    subprocess.run(cmd, check=True, cwd=ROOT, stdout=subprocess.DEVNULL)
+    if a.from_csv:
+        out_csv = Path(a.from_csv).resolve()
+    else:
+        print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True, cwd=ROOT, stdout=subprocess.DEVNULL)
     rows = [r for r in csv.reader(io.StringIO("".join(l for l in out_csv.read_text().splitlines(True) if l.startswith('"'))))]
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -52,14 +56,21 @@ def main():
         agg.setdefault(kind, []).append(dict(m, block=block, grid=grid, name=name))
     entry = {}
     for kind, launches in agg.items():
+        # several instantiations of a pass may be launched per iteration (the H pass launches its FLIP = false and FLIP =
+        # true kernels; the one that does not match the device-side flag returns at once): keep the one that did the work
+        by_name = {}
+        for l in launches:
+            by_name.setdefault(l["name"], []).append(l)
+        launches = max(by_name.values(), key=lambda ls: sum(l["gpu__time_duration.sum"] for l in ls))
         n = len(launches)
+        entry[kind + "_ms_under_ncu"] = sum(l["gpu__time_duration.sum"] for l in launches) / n * 1e-6
         entry[kind] = sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in launches) / n
         entry[kind + "_warp_instructions"] = sum(l["smsp__inst_executed.sum"] for l in launches) / n
         entry[kind + "_kernel"] = {"name": launches[0]["name"], "block": launches[0]["block"], "grid": launches[0]["grid"], "launches": n}
     wpr = (a.cols + 1023) // 1024 * 32
     entry["h_pass_algorithmic"] = a.rows * wpr * 4                 # P plane, one pass
     entry["w_pass_algorithmic"] = 2 * a.rows * wpr * 4             # P and M planes
-    entry["source"] = str(out_csv.relative_to(ROOT))
+    entry["source"] = str(out_csv.relative_to(ROOT)) if str(out_csv).startswith(str(ROOT)) else out_csv.name
     path = ROOT / "profiles" / "dram_traffic.json"
     try:
         table = json.loads(path.read_text())
