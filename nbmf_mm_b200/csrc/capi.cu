@@ -205,6 +205,11 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   p->kb = c.k <= 16 ? 16 : (c.k <= 32 ? 32 : 64);
   if (p->tensor) { p->pl.kp = c.k <= 32 ? 32 : 64; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
   const int occ = 1;
+  // batched small fits (nbmf_batch_bind): gridDim.z = bh fits share every launch, so the SMs are filled by the batch and
+  // a fit should NOT be cut into many small row / column splits (each CTA pays the prologue that loads its factor
+  // slice).  NBMF_BATCH_HINT is an experiment knob (tools/multifit_bench.py).
+  int bh = 1;
+  if (const char* e = getenv("NBMF_BATCH_HINT")) bh = std::max(1, atoi(e));
   p->sz = c.dtype == NBMF_F32 ? 4 : 8;
   p->wpr = nbmf_words_per_row(c.n);
   p->ldh = p->wpr * 32;
@@ -213,15 +218,15 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   p->h_ncb = (int)((c.n + p->pl.h_bn - 1) / p->pl.h_bn);
   // row splits of at least 128 rows, or 32 rows when the problem is too small to fill the GPU otherwise
   int64_t max_split = std::min<int64_t>(64, (c.m + 127) / 128);
-  if ((int64_t)p->h_ncb * max_split < 148) max_split = std::min<int64_t>(64, (c.m + 31) / 32);
+  if ((int64_t)p->h_ncb * bh * max_split < 148) max_split = std::min<int64_t>(64, (c.m + 31) / 32);
   const size_t cd_one = (size_t)2 * kp * p->ldh * p->sz;
   while (max_split > 1 && cd_one * (size_t)max_split > ((size_t)2 << 30)) --max_split;
-  p->h_nsplit = choose_split(p->h_ncb, max_split, occ);
+  p->h_nsplit = choose_split((int64_t)p->h_ncb * bh, max_split, occ);
   p->h_rows_per_split = ((c.m + p->h_nsplit - 1) / p->h_nsplit + 31) / 32 * 32;
   p->h_nsplit = (int)((c.m + p->h_rows_per_split - 1) / p->h_rows_per_split);
   // W pass: row blocks x column splits
   const int64_t nrb = (c.m + p->pl.w_bmr - 1) / p->pl.w_bmr;
-  p->w_nsplit = choose_split(nrb, std::min<int64_t>(32, (c.n + 127) / 128), occ);
+  p->w_nsplit = choose_split(nrb * bh, std::min<int64_t>(32, (c.n + 127) / 128), occ);
   p->w_cols_per_split = ((c.n + p->w_nsplit - 1) / p->w_nsplit + 127) / 128 * 128;
   p->w_nsplit = (int)((c.n + p->w_cols_per_split - 1) / p->w_cols_per_split);
   p->n_prior = h_epilogue_blocks(c.n, kp);

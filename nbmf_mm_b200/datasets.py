@@ -1,11 +1,13 @@
-"""Minimal stdlib reader for the R ``.rda`` files the reference ships in ``data/``.
+"""Data side of the reference's experiment driver: the paper's data sets and their splits.
 
-TEST INFRASTRUCTURE (used by ``oracle/make_golden.py`` only).  The reference
-loads these with ``pyreadr`` (``examples/reproduce_magron2022.py:28-29``), which
-is not installed here.  The files are bz2-compressed ``RDX2`` XDR
-serialisations of one named numeric matrix each (column-major, with ``dim`` and
-``dimnames`` attributes).  Only the node types those three files use are parsed.
-"""
+``read_rda_matrix``: minimal stdlib reader for the R ``.rda`` files the reference ships in ``data/`` (``animals.rda``,
+``lastfm.rda``, ``paleo.rda``).  The reference loads them with ``pyreadr`` (``examples/reproduce_magron2022.py:28-29``);
+the files are bz2-compressed ``RDX2`` XDR serialisations of one named numeric matrix each (column-major, with ``dim`` and
+``dimnames`` attributes), and only the node types those three files use are parsed.  ``load_dataset_and_splits`` mirrors
+the driver's function of that name (``:25-38``): the matrix plus the train / validation / test masks of
+``data/magron2022/<name>_split.npz``; the reference ships that file for ``animals`` only, for the other two data sets
+``make_split`` draws a seeded 70 / 15 / 15 partition of the entries (the driver's seed 12345; the partition itself is
+this package's definition -- the reference has no generator to follow)."""
 from __future__ import annotations
 
 import bz2
@@ -106,3 +108,29 @@ def read_rda_matrix(path):
     dims = obj["attrs"]["dim"]["value"]
     mat = np.asarray(obj["value"], dtype=np.float64).reshape(int(dims[1]), int(dims[0])).T
     return tag, np.ascontiguousarray(mat)
+
+
+def make_split(shape, seed=12345, fractions=(0.70, 0.15, 0.15)):
+    """Disjoint train / validation / test masks (float 0/1) covering every entry of a ``shape`` matrix, drawn from
+    ``np.random.RandomState(seed)``.  Unpinned: the reference only ships a stored split for ``animals``."""
+    rs = np.random.RandomState(seed)
+    u = rs.uniform(size=shape)
+    a, b = fractions[0], fractions[0] + fractions[1]
+    return (u < a).astype(np.float64), ((u >= a) & (u < b)).astype(np.float64), (u >= b).astype(np.float64)
+
+
+def load_dataset_and_splits(dataset_name, data_dir="data", split_dir=None, seed=12345):
+    """``(Y, train_mask, val_mask, test_mask)`` as ``examples/reproduce_magron2022.py:25-38`` returns them: the stored
+    split when ``<split_dir>/<name>_split.npz`` exists, else ``make_split(Y.shape, seed)``."""
+    from pathlib import Path
+    data_dir = Path(data_dir)
+    split_dir = data_dir / "magron2022" if split_dir is None else Path(split_dir)
+    Y = read_rda_matrix(str(data_dir / f"{dataset_name}.rda"))
+    if isinstance(Y, tuple):
+        Y = Y[1]
+    Y = np.asarray(Y, dtype=np.float64)
+    f = split_dir / f"{dataset_name}_split.npz"
+    if f.is_file():
+        with np.load(f) as z:
+            return Y, z["train_mask"].astype(np.float64), z["val_mask"].astype(np.float64), z["test_mask"].astype(np.float64)
+    return (Y,) + make_split(Y.shape, seed)

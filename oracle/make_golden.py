@@ -23,7 +23,11 @@ sys.path.insert(0, str(REF / "src"))
 sys.path.insert(0, str(ROOT / "oracle"))
 
 import nbmf_oracle as orc                       # noqa: E402
-from rda_reader import read_rda_matrix          # noqa: E402
+import importlib.util as _ilu                   # noqa: E402
+_spec = _ilu.spec_from_file_location("nbmf_datasets", ROOT / "nbmf_mm_b200" / "datasets.py")   # the product's .rda reader,
+_ds = _ilu.module_from_spec(_spec)              # loaded by path: ROOT must not enter sys.path here (its nbmf_mm/ shim
+_spec.loader.exec_module(_ds)                   # would shadow the real reference package imported below)
+read_rda_matrix = _ds.read_rda_matrix
 from nbmf_mm import NBMF                        # noqa: E402  (the reference)
 from nbmf_mm._solver import nbmf_mm_solver, nbmf_mm_update_beta_dir   # noqa: E402
 

@@ -168,3 +168,21 @@ def test_engine_is_resolved_from_the_global_problem_size():
     assert resolve_engine("auto", m_total=2000, dtype="float64", vkind="bits", k=20, eps=1e-8, n=4096) == "simt"
     assert resolve_engine("auto", m_total=2000, dtype="float32", vkind="dense", k=20, eps=1e-8, n=4096) == "simt"
     assert resolve_engine("auto", m_total=2000, dtype="float32", vkind="bits", k=65, eps=1e-8, n=4096) == "simt"
+
+
+def test_dataset_reader_and_splits(datasets):
+    """The data side of the experiment driver (examples/reproduce_magron2022.py:25-38): the stdlib .rda reader (checked
+    against the committed bit-packed fixtures where the reference tree is present) and the seeded split."""
+    from pathlib import Path
+    from nbmf_mm_b200.datasets import load_dataset_and_splits, make_split
+    tr, va, te = make_split((50, 85), seed=12345)
+    assert np.array_equal(tr + va + te, np.ones((50, 85))) and abs(tr.mean() - 0.70) < 0.03 and abs(va.mean() - 0.15) < 0.03
+    tr2, _, _ = make_split((50, 85), seed=12345)
+    assert np.array_equal(tr, tr2)
+    ref = Path("/root/reference/data")
+    if ref.is_dir():
+        Y, trm, vam, tem = load_dataset_and_splits("animals", ref)
+        assert np.array_equal(Y, datasets["animals"]) and np.array_equal(trm, datasets["animals_train_mask"])
+        assert np.array_equal(trm + vam + tem, np.ones_like(Y))
+        Yl, a, b, c = load_dataset_and_splits("lastfm", ref)
+        assert np.array_equal(Yl, datasets["lastfm"]) and np.array_equal(a + b + c, np.ones_like(Yl))
