@@ -73,6 +73,10 @@ typedef struct nbmf_config {
   double n_obs;          /* loss denominator: Y.size or count_nonzero(mask) over ALL shards (_solver.py:151,155) */
   int32_t max_iter_cap;  /* capacity of the on-device loss history */
   int32_t engine;        /* NBMF_ENGINE_AUTO | _SIMT | _TENSOR (env NBMF_ENGINE=auto|simt|tensor overrides) */
+  int32_t batch_hint;    /* 0 / 1: plan the launches for this fit alone.  n > 1: the context will be one of n fits that
+                          * advance together (nbmf_batch_bind): the batch fills the SMs, so a fit is cut into fewer, larger
+                          * row / column splits (config 5: 64 restarts 25 % faster).  Changes the summation order of the
+                          * split partials, i.e. results agree with an unbatched fit to rounding, not bit for bit. */
 } nbmf_config;
 
 int nbmf_version(void);

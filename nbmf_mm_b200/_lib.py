@@ -27,6 +27,7 @@ class NbmfConfig(C.Structure):
         ("vkind", C.c_int32), ("mask_semantics", C.c_int32), ("projection", C.c_int32),
         ("has_mask", C.c_int32), ("alpha", C.c_double), ("beta", C.c_double), ("eps", C.c_double),
         ("n_obs", C.c_double), ("max_iter_cap", C.c_int32), ("engine", C.c_int32),
+        ("batch_hint", C.c_int32),
     ]
 
 

@@ -208,7 +208,7 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   // batched small fits (nbmf_batch_bind): gridDim.z = bh fits share every launch, so the SMs are filled by the batch and
   // a fit should NOT be cut into many small row / column splits (each CTA pays the prologue that loads its factor
   // slice).  NBMF_BATCH_HINT is an experiment knob (tools/multifit_bench.py).
-  int bh = 1;
+  int bh = std::max(1, (int)c.batch_hint);
   if (const char* e = getenv("NBMF_BATCH_HINT")) bh = std::max(1, atoi(e));
   p->sz = c.dtype == NBMF_F32 ? 4 : 8;
   p->wpr = nbmf_words_per_row(c.n);

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sAcc = reinterpret_cast<float*>(smem + HTC_OFF_ACC);      // thread t: 16 C then 16 S sums at [e * 512 + t]
   __shared__ uint64_t bar_full[HTC_STAGES], bar_empty[HTC_STAGES];
-  __shared__ uint64_t bar_a, bar_theta[2], bar_tfree[2], bar_s[2], bar_rfree[2], bar_cd[2];
+  __shared__ uint64_t bar_a, bar_theta[2], bar_tfree[2], bar_s[2], bar_rfree[2][2], bar_cd[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ double red_scratch[TC_THREADS / 32];
 
@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
     mbar_init(&bar_a, TC_SIMT_WARPS);
     for (int g = 0; g < 2; ++g) {
       mbar_init(&bar_theta[g], 1); mbar_init(&bar_tfree[g], TC_SIMT_WARPS / 2);
-      mbar_init(&bar_s[g], TC_SIMT_WARPS / 2); mbar_init(&bar_rfree[g], 1); mbar_init(&bar_cd[g], 1);
+      mbar_init(&bar_s[g], TC_SIMT_WARPS / 2);
+      mbar_init(&bar_rfree[g][0], 1); mbar_init(&bar_rfree[g][1], 1); mbar_init(&bar_cd[g], 1);
     }
     mbar_fence_init();
   }
@@ -299,8 +300,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
             mma_ts(tS, tr + 8, dTh + 2 * ks, id2, acc);
             mma_ts_bf16(tC, tr + 16, dTc + 2 * ks, id2b, 1);           // hi.lo + lo.hi, bf16, K = 16 = 8 rows x (hi, lo)
             mma_ts_bf16(tS, tr + 24, dTc + 2 * ks, id2b, 1);
+            // The h = 0 warps get their half of R[g] (rows 0..15) back after 8 of the 16 MMAs: the wait for MMA2(b - 2)
+            // was 13 % of the stall samples of the SIMT warps (ncu); H pass -5 % (1.37 -> 1.29 ms at 65 536 x 32 768).
+            // Handing the halves OVER separately as well (MMA2 starting on the first half alone) gave it back: 1.37 ms.
+            if (ks == 1) commit(&bar_rfree[g][0]);
           }
-          commit(&bar_rfree[g]);
+          commit(&bar_rfree[g][1]);
           commit(&bar_empty[s]);
           if (b + 2 >= nb || ((ob + 1) % kFlush) == 0) commit(&bar_cd[g]);   // a chain ends here
         }
@@ -431,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
         if (cd) {
           if (u == 0) {                                                // MMA2(b-2) must be done reading R[g]
             TC_EV(1 + g, b, 3);
-            if (!ok_rfree) mbar_wait(&bar_rfree[g], (ob - 1) & 1);
+            if (!ok_rfree) mbar_wait(&bar_rfree[g][h], (ob - 1) & 1);
             fence_after_sync();
             TC_EV(1 + g, b, 4);
           }
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
   float* sX = reinterpret_cast<float*>(smem + WTC_OFF_X);           // [16 accumulators][256 threads of group 1]
   float* sQ = reinterpret_cast<float*>(smem + WTC_OFF_Q);           // [4 (group, half)][128 lanes]
   __shared__ uint64_t bar_full[WTC_STAGES], bar_empty[WTC_STAGES];
-  __shared__ uint64_t bar_a, bar_theta[2], bar_tfree[2], bar_s[2], bar_sfree[2], bar_g[2];
+  __shared__ uint64_t bar_a, bar_theta[2], bar_tfree[2], bar_s[2], bar_sfree[2][2], bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     mbar_init(&bar_a, TC_SIMT_WARPS);
     for (int g = 0; g < 2; ++g) {
       mbar_init(&bar_theta[g], 1); mbar_init(&bar_tfree[g], TC_SIMT_WARPS / 2);
-      mbar_init(&bar_s[g], TC_SIMT_WARPS / 2); mbar_init(&bar_sfree[g], 1); mbar_init(&bar_g[g], 1);
+      mbar_init(&bar_s[g], TC_SIMT_WARPS / 2); mbar_init(&bar_sfree[g][0], 1); mbar_init(&bar_sfree[g][1], 1); mbar_init(&bar_g[g], 1);
     }
     mbar_fence_init();
   }
@@ -601,8 +606,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
           const uint32_t ts = tSb + 16 * ks;                             // S_hi +0, S_c +8
           mma_ts(tGa, ts, dBh, id2, (ks > 0 || !chain_start) ? 1u : 0u); // hi . hi, tf32
           mma_ts_bf16(tGa, ts + 8, dBc, id2b, 1);                        // hi.lo + lo.hi, bf16
+          if (ks == 3) commit(&bar_sfree[g][0]);                         // columns 0..31 (the h = 0 warps' half of S[g]) are read
         }
-        commit(&bar_sfree[g]);
+        commit(&bar_sfree[g][1]);
         commit(&bar_empty[s]);
         if (b + 2 >= nb || ((ob + 1) % kFlush) == 0) commit(&bar_g[g]);
       }
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
       for (int u = 0; u < 2; ++u) {
         uint32_t v[16];
         tmem_ld16(tTheta + 64 * g + lane_off + 32 * h + 16 * u, v);
-        if (u == 0 && b >= 2) ok_sfree = mbar_try(smem_u32(&bar_sfree[g]), (ob - 1) & 1);
+        if (u == 0 && b >= 2) ok_sfree = mbar_try(smem_u32(&bar_sfree[g][h]), (ob - 1) & 1);
         wait_ld();
         if (u == 1) {                                                  // Theta[g] may be overwritten by MMA1(b+2)
           fence_before_sync();
@@ -699,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
             out[8 + e] = pack_bf16x2(hi, sv - hi);                       // (hi, lo) of s in one column
           }
           if (u == 0 && w == 0) {                                      // MMA2(b-2) must be done reading S[g]
-            if (!ok_sfree) mbar_wait(&bar_sfree[g], (ob - 1) & 1);
+            if (!ok_sfree) mbar_wait(&bar_sfree[g][h], (ob - 1) & 1);
             fence_after_sync();
           }
           tmem_st16(tS + 128 * g + lane_off + 16 * (4 * h + 2 * u + w), out);

@@ -227,7 +227,7 @@ class DeviceProblem:
 
     def __init__(self, m, n, k, *, dtype="float64", vkind="bits", has_mask=False, alpha=1.2, beta=1.2,
                  eps=1e-8, n_obs=None, mask_semantics="reference", projection="normalize",
-                 max_iter_cap=2000, device=None, engine="auto", workspace=None):
+                 max_iter_cap=2000, device=None, engine="auto", workspace=None, batch_hint=0):
         torch = _torch()
         self.lib = _lib.load()
         self.dev = require_cuda(device)
@@ -253,6 +253,7 @@ class DeviceProblem:
         if engine not in _lib.ENGINES:
             raise ValueError(f"engine must be one of {sorted(_lib.ENGINES)}, got {engine!r}")
         cfg.engine = _lib.ENGINES[engine]
+        cfg.batch_hint = int(batch_hint)
         self.cfg = cfg
         nbytes = self.lib.nbmf_workspace_bytes(C.byref(cfg))
         if nbytes < 0:

@@ -33,7 +33,7 @@ def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
 def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500, tol=1e-5, eps=1e-8,
                      projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
                      engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False, batch=True,
-                     verbose=0):
+                     batch_plan="fit", verbose=0):
     """Fit ``len(jobs)`` models to the same ``Y`` / ``mask``.
 
     ``jobs``: sequence of dicts with ``n_components`` and optionally ``alpha``, ``beta`` (default 1.2),
@@ -41,11 +41,19 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     list of ``(W, H, losses, 0.0, n_iter)`` in job order, each identical to
     ``nbmf_mm_solver(Y, mask=mask, orientation=orientation, **job)``.  ``batch``: jobs with the same K, max_iter and
     tol (restarts, alpha / beta grids) advance together on small problems, one launch per kernel for the whole group
-    (``nbmf_batch_bind``).  ``n_streams``: concurrent fits for the remaining jobs
+    (``nbmf_batch_bind``).  ``batch_plan``: "fit" (default) keeps the launch plan of a single fit, so every result is
+    bit-identical to the solver call whatever the batch size (and the number of GPUs the restarts are dealt to);
+    "batch" plans the launches of a group for the whole group -- the batch fills the SMs, so every fit is cut into
+    fewer, larger row / column splits (config 5: 64 restarts 25 % faster, profiles/r02_batch_plan_cfg5.txt); the split
+    partials are then summed in a different order, so results agree with the solver call to rounding (fp64 ~1e-15, fp32
+    ~1e-7) instead of bit for bit.
+    ``n_streams``: concurrent fits for the remaining jobs
     (default: one per hardware queue, 8..32, for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own)."""
     import torch
     if orientation not in _CANON:
         raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
+    if batch_plan not in ("batch", "fit"):
+        raise ValueError(f"batch_plan must be 'batch' or 'fit', got {batch_plan!r}")
     jobs = [dict(j) for j in jobs]
     if not jobs:
         return []
@@ -122,7 +130,8 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                 for b, idx in enumerate(idxs):
                     prob = make_problem(data, k, dtype=dtype, alpha=prepared[idx][1], beta=prepared[idx][2], eps=eps,
                                         mask_semantics=mask_semantics, projection=projection_method, max_iter_cap=mi,
-                                        device=device, engine=engine, workspace=slice_of(b))
+                                        device=device, engine=engine, workspace=slice_of(b),
+                                        batch_hint=B if batch_plan == "batch" else 0)
                     probs.append(prob)
                     if prob.engine != "simt":
                         return None

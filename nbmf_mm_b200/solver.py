@@ -183,11 +183,11 @@ def prepare_data(Y, mask, *, transpose, dtype, device, defer=False, dense_storag
 
 
 def make_problem(data: PreparedData, k, *, dtype, alpha, beta, eps, mask_semantics, projection, max_iter_cap,
-                 device, n_obs=None, engine="auto", workspace=None) -> DeviceProblem:
+                 device, n_obs=None, engine="auto", workspace=None, batch_hint=0) -> DeviceProblem:
     prob = DeviceProblem(data.m, data.n, k, dtype=dtype, vkind=data.vkind, has_mask=data.M is not None,
                          alpha=alpha, beta=beta, eps=eps, n_obs=data.n_obs if n_obs is None else n_obs,
                          mask_semantics=mask_semantics, projection=projection, max_iter_cap=max_iter_cap,
-                         device=device, engine=engine, workspace=workspace)
+                         device=device, engine=engine, workspace=workspace, batch_hint=batch_hint)
     if data.vkind == "bits":
         prob.set_bits(data.P, data.M)
     else:

@@ -30,13 +30,16 @@ def _run(data, k, dtype, engine, W0, H0, iters):
     return H1, W1, np.asarray(losses), plan
 
 
-@pytest.mark.parametrize("m,n,what", [
-    (400_000, 18_944, "H pass: 148 column blocks x 1 row split -> 12 500 row blocks per CTA (config 4: 10 417)"),
-    (18_944, 100_000, "W pass: 148 row blocks x 1 column split -> 1 563 column blocks per CTA (config 4: 1 563)"),
+@pytest.mark.parametrize("m,n,k,what", [
+    (400_000, 18_944, 32, "H pass: 148 column blocks x 1 row split -> 12 500 row blocks per CTA (config 4: 10 417)"),
+    (18_944, 100_000, 32, "W pass: 148 row blocks x 1 column split -> 1 563 column blocks per CTA (config 4: 1 563)"),
+    (131_072, 18_944, 64, "K <= 64 kernels, H pass: 4 096 row blocks = 8 192 half-blocks per CTA over three pipelines"),
+    (18_944, 50_048, 48, "K <= 64 kernels, W pass: 782 column blocks per CTA"),
+    (200_000, 18_944, 12, "K <= 16 instantiation, H pass: 6 250 row blocks per CTA"),
 ])
-def test_tensor_engine_at_config4_depth_vs_fp64(m, n, what):
-    k, iters = 32, 3
-    hstar = (np.random.default_rng(4).random((k, n)) * 0.2).astype(np.float32)
+def test_tensor_engine_at_config4_depth_vs_fp64(m, n, k, what):
+    iters = 3
+    hstar = (np.random.default_rng(4).random((min(k, 32), n)) * 0.2).astype(np.float32)
     P, M = synth_bits_device(4, 0, m, n, hstar, 0.9, "cuda")
     data = PreparedData(m, n, "bits", P, M, None, float(M.count()))
     rs = np.random.RandomState(0)

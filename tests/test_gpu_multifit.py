@@ -112,3 +112,20 @@ def test_batched_alpha_beta_grid_equals_sequential_solver_calls(dtype):
         assert np.array_equal(W, out[0]) and np.array_equal(H, out[1]), j
         finals.add(float(losses[-1]))
     assert len(finals) > 3                                        # the priors did differ
+
+
+@pytest.mark.parametrize("dtype,tol_f", [("float64", 1e-12), ("float32", 2e-5)])
+def test_batch_planned_launches_agree_with_solver_calls_to_rounding(dtype, tol_f):
+    """``batch_plan="batch"``: the launches of a group are planned for the whole group (fewer, larger splits per fit),
+    which changes the summation order of the split partials -- same results to rounding, same iteration counts."""
+    rng = np.random.default_rng(0)
+    X = (rng.random((1226, 285)) < 0.0435).astype(np.float64)            # config-5 shape
+    jobs = [dict(n_components=16, random_state=r) for r in range(12)]
+    stats = {}
+    got = nbmf_mm_multifit(X, jobs, max_iter=40, tol=0.0, dtype=dtype, stats=stats, batch_plan="batch")
+    assert stats["batched"] == 12
+    for j, out in list(zip(jobs, got))[::4]:
+        W, H, losses, _, n_iter = nbmf_mm_solver(X, max_iter=40, tol=0.0, dtype=dtype, **j)
+        assert n_iter == out[4]
+        assert np.max(np.abs(np.asarray(losses) - np.asarray(out[2])) / np.abs(losses)) < tol_f
+        assert np.max(np.abs(W - out[0])) < 50 * tol_f and np.max(np.abs(H - out[1])) < 50 * tol_f
