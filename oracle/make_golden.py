@@ -133,6 +133,26 @@ def trajectories(data, animals_train):
     M3 = (rng.random((120, 70)) < 0.9).astype(float)
     out["cfg3s/X"], out["cfg3s/mask"] = X3, M3
     run("cfg3s", X3, 7, orientation="dir-beta", max_iter=150, tol=1e-7, alpha=1.2, beta=1.2, random_state=0, mask=M3)
+    # config 2 with train masks for the two data sets the reference ships no split for (seeded 70 / 15 / 15 partition of
+    # the product's datasets.make_split; the masks are stored bit-packed so that the tests use exactly these)
+    for name in ("lastfm", "paleo"):
+        tr, _, _ = _ds.make_split(data[name].shape, seed=12345)
+        out[f"cfg2_{name}_train/mask_bits"] = np.packbits(tr.astype(bool), axis=1, bitorder="little")
+        run(f"cfg2_{name}_train", data[name], 10, orientation="beta-dir", max_iter=500, tol=1e-5, random_state=0, mask=tr)
+    # weighted (non-0/1) mask: the reference multiplies by the mask values (_solver.py:30-32)
+    rng = np.random.default_rng(8)
+    Xw = (rng.random((90, 110)) < 0.25).astype(float)
+    Mw = rng.choice([0.0, 0.25, 0.5, 1.0, 1.0], size=Xw.shape)
+    out["wmask/X"], out["wmask/mask"] = Xw, Mw
+    run("wmask", Xw, 6, orientation="beta-dir", max_iter=80, tol=1e-8, alpha=1.2, beta=1.4, random_state=2, mask=Mw)
+    run("wmask_dirbeta", Xw, 6, orientation="dir-beta", max_iter=60, tol=1e-8, alpha=1.2, beta=1.4, random_state=2, mask=Mw)
+    # K = 40: the 32 < K <= 64 kernels in float32 mode
+    rng = np.random.default_rng(9)
+    Xk = (rng.random((700, 600)) < 0.1).astype(float)
+    Mk = (rng.random(Xk.shape) < 0.9).astype(float)
+    out["k40/X_bits"] = np.packbits(Xk.astype(bool), axis=1, bitorder="little")
+    out["k40/mask_bits"] = np.packbits(Mk.astype(bool), axis=1, bitorder="little")
+    run("k40", Xk, 40, orientation="beta-dir", max_iter=40, tol=0.0, random_state=1, mask=Mk)
     # probabilistic X through the estimator
     Xp = np.random.default_rng(5).random((45, 60))
     out["prob/X"] = Xp

@@ -14,8 +14,23 @@ from nbmf_mm_b200 import NBMF, nbmf_mm_solver
 pytestmark = pytest.mark.gpu
 
 
+def _bits(a, n):
+    return np.unpackbits(a, axis=1, bitorder="little")[:, :n].astype(np.float64)
+
+
 def _cases(datasets, golden_traj):
+    g = golden_traj
     return {
+        "cfg2_lastfm_train": (datasets["lastfm"], _bits(g["cfg2_lastfm_train"]["mask_bits"], datasets["lastfm"].shape[1]),
+                              dict(n_components=10, max_iter=500, tol=1e-5, random_state=0)),
+        "cfg2_paleo_train": (datasets["paleo"], _bits(g["cfg2_paleo_train"]["mask_bits"], datasets["paleo"].shape[1]),
+                             dict(n_components=10, max_iter=500, tol=1e-5, random_state=0)),
+        "wmask": (g["wmask"]["X"], g["wmask"]["mask"],
+                  dict(n_components=6, max_iter=80, tol=1e-8, alpha=1.2, beta=1.4, random_state=2)),
+        "wmask_dirbeta": (g["wmask"]["X"], g["wmask"]["mask"],
+                          dict(n_components=6, orientation="dir-beta", max_iter=60, tol=1e-8, alpha=1.2, beta=1.4, random_state=2)),
+        "k40": (_bits(g["k40"]["X_bits"], 600), _bits(g["k40"]["mask_bits"], 600),
+                dict(n_components=40, max_iter=40, tol=0.0, random_state=1)),
         "cfg1": (cfg1_matrix(), None, dict(n_components=6, alpha=1.2, beta=1.2, random_state=0)),
         "cfg2_animals": (datasets["animals"], None, dict(n_components=10, max_iter=500, tol=1e-5, random_state=0)),
         "cfg2_lastfm": (datasets["lastfm"], None, dict(n_components=10, max_iter=500, tol=1e-5, random_state=0)),
@@ -29,7 +44,8 @@ def _cases(datasets, golden_traj):
     }
 
 
-NAMES = ["cfg1", "cfg2_animals", "cfg2_lastfm", "cfg2_paleo", "cfg2_animals_train", "cfg3s", "prob"]
+NAMES = ["cfg1", "cfg2_animals", "cfg2_lastfm", "cfg2_paleo", "cfg2_animals_train", "cfg3s", "prob",
+         "cfg2_lastfm_train", "cfg2_paleo_train", "wmask", "wmask_dirbeta", "k40"]
 
 
 @pytest.mark.parametrize("name", NAMES)

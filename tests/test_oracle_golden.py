@@ -103,3 +103,25 @@ def test_restart_schedule():
     best = orc.fit_restarts(X, 4, n_init=3, random_state=5, max_iter=40, tol=0)
     finals = [orc.fit(X, 4, random_state=5 + r, max_iter=40, tol=0)[2][-1] for r in range(3)]
     assert best[2][-1] == min(finals)
+
+
+def test_weighted_mask_train_splits_and_k40(golden_traj, datasets):
+    """Round-2 golden cases from the real reference: weighted (non-0/1) masks in both orientations (the reference
+    multiplies by the mask values, _solver.py:30-32), the seeded train masks on lastfm / paleo (a prefix of the 500
+    iterations), K = 40."""
+    g = golden_traj["wmask"]
+    W, H, losses, n_iter = orc.fit(g["X"], 6, max_iter=80, tol=1e-8, alpha=1.2, beta=1.4, random_state=2, mask=g["mask"])
+    assert n_iter == int(g["n_iter"]) and np.array_equal(np.asarray(losses), g["losses"]) and np.array_equal(W, g["W"])
+    gd = golden_traj["wmask_dirbeta"]
+    W, H, losses, n_iter = orc.fit(g["X"], 6, max_iter=60, tol=1e-8, alpha=1.2, beta=1.4, random_state=2, mask=g["mask"],
+                                   orientation="dir-beta")
+    assert np.array_equal(np.asarray(losses), gd["losses"]) and np.array_equal(H, gd["H"])
+    unbits = lambda a, n: np.unpackbits(a, axis=1, bitorder="little")[:, :n].astype(np.float64)
+    for name, prefix in (("lastfm", 12), ("paleo", 20)):
+        gt = golden_traj[f"cfg2_{name}_train"]
+        mask = unbits(gt["mask_bits"], datasets[name].shape[1])
+        _, _, losses, _ = orc.fit(datasets[name], 10, max_iter=prefix, tol=1e-5, random_state=0, mask=mask)
+        assert np.array_equal(np.asarray(losses), gt["losses"][:prefix])
+    gk = golden_traj["k40"]
+    _, _, losses, _ = orc.fit(unbits(gk["X_bits"], 600), 40, max_iter=6, tol=0.0, random_state=1, mask=unbits(gk["mask_bits"], 600))
+    assert np.array_equal(np.asarray(losses), gk["losses"][:6])
