@@ -52,7 +52,7 @@ extern "C" {
 #define NBMF_PROJ_NORMALIZE 0 /* multiplicative step, /n, L1 renormalisation (_solver.py:53-57) */
 #define NBMF_PROJ_DUCHI 1     /* multiplicative step / n_obs(row), Euclidean simplex projection; unpinned */
 
-#define NBMF_ENGINE_AUTO 0   /* tensor engine when eligible and m, n >= 512, else SIMT */
+#define NBMF_ENGINE_AUTO 0   /* tensor engine when eligible and m >= 512, n >= 128, else SIMT */
 #define NBMF_ENGINE_SIMT 1   /* packed-FFMA2 CUDA-core kernels: every dtype / K <= 64 / layout */
 #define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, TF32 + bf16 split precision: float32, bit-packed V, K <= 64, eps >= 1e-9 */
 

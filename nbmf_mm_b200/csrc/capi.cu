@@ -201,7 +201,12 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   if (engine == NBMF_ENGINE_TENSOR && !eligible)
     return fail(NBMF_ERR_UNSUPPORTED, "tensor engine needs float32, bit-packed V, k <= 64 and eps >= 1e-9");
   p->strict = strict != 0;
-  p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR || (engine == NBMF_ENGINE_AUTO && c.m >= 512 && c.n >= 512));
+  // auto rule: measured on the config-5 shape (1226 x 285, tools/small_fit_bench.py) the tensor engine wins from K = 16
+  // for a single fit (12.6 vs 14.1 ms per 200 iterations; K = 6: 12.5 vs 10.8) and at every K for a batch of restarts
+  int64_t min_m = 512, min_n = 128;
+  if (const char* e = getenv("NBMF_TENSOR_MIN_M")) min_m = atoll(e);
+  if (const char* e = getenv("NBMF_TENSOR_MIN_N")) min_n = atoll(e);
+  p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR || (engine == NBMF_ENGINE_AUTO && c.m >= min_m && c.n >= min_n));
   p->kb = c.k <= 16 ? 16 : (c.k <= 32 ? 32 : 64);
   if (p->tensor) { p->pl.kp = c.k <= 32 ? 32 : 64; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
   const int occ = 1;
@@ -219,6 +224,10 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   // row splits of at least 128 rows, or 32 rows when the problem is too small to fill the GPU otherwise
   int64_t max_split = std::min<int64_t>(64, (c.m + 127) / 128);
   if ((int64_t)p->h_ncb * bh * max_split < 148) max_split = std::min<int64_t>(64, (c.m + 31) / 32);
+  // tensor engine, small problems: a CTA pays ~4 us of set-up (TMEM allocation, barriers, resident operand, pipeline
+  // fill) against ~0.4 us per 32-row block, so a row split is at least 512 rows -- also when that leaves SMs idle (a
+  // batch of small fits fills them; the plan does not depend on the batch, so batched and single fits stay bit-identical)
+  if (p->tensor && (int64_t)p->h_ncb * ((c.m + 127) / 128) < 148) max_split = std::max<int64_t>(1, std::min<int64_t>(64, c.m / 512));
   const size_t cd_one = (size_t)2 * kp * p->ldh * p->sz;
   while (max_split > 1 && cd_one * (size_t)max_split > ((size_t)2 << 30)) --max_split;
   p->h_nsplit = choose_split((int64_t)p->h_ncb * bh, max_split, occ);
@@ -226,7 +235,9 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   p->h_nsplit = (int)((c.m + p->h_rows_per_split - 1) / p->h_rows_per_split);
   // W pass: row blocks x column splits
   const int64_t nrb = (c.m + p->pl.w_bmr - 1) / p->pl.w_bmr;
-  p->w_nsplit = choose_split(nrb * bh, std::min<int64_t>(32, (c.n + 127) / 128), occ);
+  int64_t w_max_split = std::min<int64_t>(32, (c.n + 127) / 128);
+  if (p->tensor && nrb * w_max_split < 148) w_max_split = std::max<int64_t>(1, std::min<int64_t>(32, c.n / 512));
+  p->w_nsplit = choose_split(nrb * bh, w_max_split, occ);
   p->w_cols_per_split = ((c.n + p->w_nsplit - 1) / p->w_nsplit + 127) / 128 * 128;
   p->w_nsplit = (int)((c.n + p->w_cols_per_split - 1) / p->w_cols_per_split);
   p->n_prior = h_epilogue_blocks(c.n, kp);
@@ -601,13 +612,15 @@ extern "C" int nbmf_get_factors_f64(nbmf_ctx* c, double* w, double* h, int norma
 // ------------------------------------------------------------------------------------ steps
 static int format_w(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;
-  launch_format_w(c->W(), c->cfg.m, c->p.mpad, c->p.pl.kp, c->ws + c->p.oWf, guarded ? c->state() : nullptr, c->st);
+  launch_format_w(c->W(), c->cfg.m, c->p.mpad, c->p.pl.kp, c->ws + c->p.oWf, guarded ? c->state() : nullptr, c->st,
+                  guarded ? c->batch_n : 1, guarded ? c->batch_stride : 0);     // unguarded = per-context set-up calls
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }
 static int format_h(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;
-  launch_format_h(c->H(), c->p.ldh, c->p.pl.kp, c->ws + c->p.oHf, guarded ? c->state() : nullptr, c->st);
+  launch_format_h(c->H(), c->p.ldh, c->p.pl.kp, c->ws + c->p.oHf, guarded ? c->state() : nullptr, c->st,
+                  guarded ? c->batch_n : 1, guarded ? c->batch_stride : 0);
   CHECK_LAUNCH(1);
   return NBMF_OK;
 }
@@ -882,12 +895,12 @@ extern "C" int nbmf_fit_poll(nbmf_ctx* c, int wait, int32_t* done_host, int32_t*
 // factors (nbmf_set_factors) and calls nbmf_fit_begin on each with the same max_iter / tol.  After nbmf_batch_bind
 // the leader's nbmf_fit_enqueue drives all of them: every kernel of the loop runs with gridDim.z = n and shifts its
 // workspace pointers by blockIdx.z * stride; each fit keeps its own device-side state (loss history, stop rule,
-// done flag), so fits that converge early simply turn into no-ops.  SIMT engine, single GPU.
+// done flag), so fits that converge early simply turn into no-ops.  Both engines, single GPU.
 extern "C" int nbmf_batch_bind(nbmf_ctx* c, int32_t n, int64_t stride_bytes) {
   if (!c || n < 1 || (n > 1 && stride_bytes < (int64_t)c->p.total) || (stride_bytes % 16) != 0 || n > 65535)
     return fail(NBMF_ERR_ARG, "nbmf_batch_bind: bad arguments");
-  if (n > 1 && (c->p.tensor || c->world != 1))
-    return fail(NBMF_ERR_ARG, "nbmf_batch_bind: batches run on the SIMT engine of a single GPU");
+  if (n > 1 && c->world != 1)
+    return fail(NBMF_ERR_ARG, "nbmf_batch_bind: batches run on a single GPU");
   c->batch_n = n;
   c->batch_stride = n > 1 ? stride_bytes : 0;
   graph_drop(c);

@@ -21,70 +21,132 @@
 #include <algorithm>
 
 #include "internal.h"
+#include "common.cuh"
 #include "tc_common.cuh"
 
 namespace nbmf {
 
 // KT = 32 (K <= 32) or 64 (K <= 64): K extent of the formatted operands.  A K-major operand wider than 128 bytes per row is
 // stored as KT/32 slabs (one SWIZZLE_128B tile per 32 k / per 64 bf16), slab after slab.
-template <int KT>
-__global__ void format_w_kernel(const float* __restrict__ W, int64_t m, int64_t mpad, float* __restrict__ Wf,
-                                const FitState* __restrict__ state) {
-  if (state && state->done) return;
-  constexpr int REGF = (KT / 32) * 1024;                           // floats per operand region of a 32-row block
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= mpad * KT) return;
-  const int64_t i = e / KT;
-  const int k = (int)(e % KT);
-  const float x = i < m ? W[e] : 0.0f;
-  const float hi = tc::tf32_trunc(x), lo = x - hi;
-  const int r = (int)(i & 31);
-  float* blk = Wf + (size_t)(i >> 5) * (4 * REGF);
-  blk[(k >> 5) * 1024 + tc::sw128_offset(r, k & 31) / 4] = hi;                       // rows i x k, tf32 hi
-  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + REGF);             // rows i: [lo (KT) | hi (KT)] bf16
-  const int il = k, ih = KT + k;
-  corr[(il >> 6) * 2048 + tc::sw128_offset_b16(r, il & 63) / 2] = (unsigned short)tc::bf16_bits(lo);
-  corr[(ih >> 6) * 2048 + tc::sw128_offset_b16(r, ih & 63) / 2] = (unsigned short)tc::bf16_bits(hi);
-  blk[2 * REGF + tc::sw128_offset(k, r) / 4] = hi;                                   // rows k x i, tf32 hi
-  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 3 * REGF);        // row k: (lo, hi) pairs per i
-  corr2[tc::sw128_offset_b16(k, 2 * r) / 2] = (unsigned short)tc::bf16_bits(lo);
-  corr2[tc::sw128_offset_b16(k, 2 * r + 1) / 2] = (unsigned short)tc::bf16_bits(hi);
+//
+// Both kernels stage the source block in shared memory and then walk the DESTINATION linearly (thread t writes 32-bit word
+// t, t + 256, ..: full coalesced lines), inverting the swizzle to find the source element -- the first version walked the
+// source and scattered 2- and 4-byte stores into the transposed regions (67 us per iteration for a batch of 64 small fits,
+// more than the H pass itself; 0.8 ms per iteration at config 4).
+__device__ __forceinline__ void unswizzle(uint32_t byte_off, int& row, int& chunk, int& within) {
+  // inverse of sw128_offset*: byte offset inside a tile of 128-byte rows -> (row, logical 16-byte chunk, byte in chunk)
+  row = (int)((byte_off >> 10) << 3) + (int)((byte_off & 1023u) >> 7);
+  chunk = (int)(((byte_off & 127u) >> 4) ^ (uint32_t)(row & 7));
+  within = (int)(byte_off & 15u);
 }
 
 template <int KT>
-__global__ void format_h_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Hf,
-                                const FitState* __restrict__ state) {
+__global__ void __launch_bounds__(256) format_w_kernel(const float* __restrict__ W, int64_t m, int64_t mpad, float* __restrict__ Wf,
+                                                       const FitState* __restrict__ state, int64_t bstride) {
+  if (bstride) {                                  // fit blockIdx.z of a batch: its own workspace
+    const size_t sh = (size_t)blockIdx.z * (size_t)bstride;
+    W = batch_shift(W, sh); Wf = batch_shift(Wf, sh);
+    if (state) state = batch_shift(state, sh);
+  }
   if (state && state->done) return;
-  constexpr int RWF = (KT / 32) * 2048;                            // floats per operand region of a 64-column block
-  constexpr int RBF = KT * 32;                                     // floats per K-block (32 columns) of the H operand
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = blockIdx.y;
-  if (j >= ldh) return;
-  const float x = H[(size_t)k * ldh + j];
-  const float hi = tc::tf32_trunc(x), lo = x - hi;
-  const int r = (int)(j & 63);
-  float* blk = Hf + (size_t)(j >> 6) * (4 * RWF);
-  blk[(k >> 5) * 2048 + tc::sw128_offset(r, k & 31) / 4] = hi;                       // rows j x k, tf32 hi
-  unsigned short* corr = reinterpret_cast<unsigned short*>(blk + RWF);              // rows j: [lo (KT) | hi (KT)] bf16
-  const int il = k, ih = KT + k;
-  corr[(il >> 6) * 4096 + tc::sw128_offset_b16(r, il & 63) / 2] = (unsigned short)tc::bf16_bits(lo);
-  corr[(ih >> 6) * 4096 + tc::sw128_offset_b16(r, ih & 63) / 2] = (unsigned short)tc::bf16_bits(hi);
-  const int rr = r & 31, hb = r >> 5;
-  blk[2 * RWF + hb * RBF + tc::sw128_offset(k, rr) / 4] = hi;                         // 2 K-blocks of rows k x 32 j
-  unsigned short* corr2 = reinterpret_cast<unsigned short*>(blk + 3 * RWF + hb * RBF);   // row k: (lo, hi) pairs per j
-  corr2[tc::sw128_offset_b16(k, 2 * rr) / 2] = (unsigned short)tc::bf16_bits(lo);
-  corr2[tc::sw128_offset_b16(k, 2 * rr + 1) / 2] = (unsigned short)tc::bf16_bits(hi);
+  constexpr int REGF = (KT / 32) * 1024;                           // 32-bit words per operand region of a 32-row block
+  __shared__ float tile[32][KT + 1];
+  const int64_t rb = blockIdx.x;
+  for (int e = threadIdx.x; e < 32 * KT; e += 256) {
+    const int r = e / KT, k = e % KT;
+    const int64_t row = rb * 32 + r;
+    tile[r][k] = row < m ? W[row * KT + k] : 0.0f;
+  }
+  __syncthreads();
+  uint32_t* blk = reinterpret_cast<uint32_t*>(Wf + (size_t)rb * (4 * REGF));
+  for (int d = threadIdx.x; d < REGF; d += 256) {
+    int r, c, w;
+    unswizzle((uint32_t)(d & 1023) * 4u, r, c, w);
+    const int slab = d >> 10;
+    // region 0: rows i x k, tf32 hi (slab = 32 k)
+    blk[d] = __float_as_uint(tc::tf32_trunc(tile[r][32 * slab + 4 * c + (w >> 2)]));
+    // region 1: rows i: [lo (KT) | hi (KT)] bf16, two per word (slab = 64 bf16)
+    {
+      uint32_t word = 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int idx = 64 * slab + 8 * c + (w >> 1) + q;
+        const float x = tile[r][idx < KT ? idx : idx - KT];
+        const float hi = tc::tf32_trunc(x);
+        word |= tc::bf16_bits(idx < KT ? x - hi : hi) << (16 * q);
+      }
+      blk[REGF + d] = word;
+    }
+    // regions 2, 3: rows k (KT of them, 128 bytes each) x i: tf32 hi, and (lo, hi) bf16 pairs per i
+    {
+      int k, ci, wi;
+      unswizzle((uint32_t)d * 4u, k, ci, wi);
+      blk[2 * REGF + d] = __float_as_uint(tc::tf32_trunc(tile[4 * ci + (wi >> 2)][k]));
+      const float x = tile[(8 * ci + (wi >> 1)) >> 1][k];
+      const float hi = tc::tf32_trunc(x);
+      blk[3 * REGF + d] = tc::bf16_bits(x - hi) | (tc::bf16_bits(hi) << 16);
+    }
+  }
 }
 
-void launch_format_w(const void* W, int64_t m, int64_t mpad, int kt, void* Wf, const FitState* state, cudaStream_t st) {
-  const unsigned grid = (unsigned)((mpad * kt + 255) / 256);
-  if (kt == 64) format_w_kernel<64><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state);
-  else format_w_kernel<32><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state);
+template <int KT>
+__global__ void __launch_bounds__(256) format_h_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Hf,
+                                                       const FitState* __restrict__ state, int64_t bstride) {
+  if (bstride) {
+    const size_t sh = (size_t)blockIdx.z * (size_t)bstride;
+    H = batch_shift(H, sh); Hf = batch_shift(Hf, sh);
+    if (state) state = batch_shift(state, sh);
+  }
+  if (state && state->done) return;
+  constexpr int RWF = (KT / 32) * 2048;                            // words per operand region of a 64-column block
+  constexpr int RBF = KT * 32;                                     // words per K-block (32 columns) of the H operand
+  __shared__ float tile[KT][64 + 1];
+  const int64_t jb = blockIdx.x;
+  for (int e = threadIdx.x; e < KT * 64; e += 256) {
+    const int k = e >> 6, c = e & 63;
+    tile[k][c] = H[(size_t)k * ldh + jb * 64 + c];
+  }
+  __syncthreads();
+  uint32_t* blk = reinterpret_cast<uint32_t*>(Hf + (size_t)jb * (4 * RWF));
+  for (int d = threadIdx.x; d < RWF; d += 256) {
+    {  // regions 0, 1: rows j (64) x k: tf32 hi (slab = 32 k) and [lo (KT) | hi (KT)] bf16 (slab = 64 bf16)
+      int r, c, w;
+      unswizzle((uint32_t)(d & 2047) * 4u, r, c, w);
+      const int slab = d >> 11;
+      blk[d] = __float_as_uint(tc::tf32_trunc(tile[32 * slab + 4 * c + (w >> 2)][r]));
+      uint32_t word = 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int idx = 64 * slab + 8 * c + (w >> 1) + q;
+        const float x = tile[idx < KT ? idx : idx - KT][r];
+        const float hi = tc::tf32_trunc(x);
+        word |= tc::bf16_bits(idx < KT ? x - hi : hi) << (16 * q);
+      }
+      blk[RWF + d] = word;
+    }
+    {  // regions 2, 3: two K-blocks of rows k x 32 j: tf32 hi, and (lo, hi) bf16 pairs per j
+      const int hb = d / RBF;
+      int k, cj, wj;
+      unswizzle((uint32_t)(d % RBF) * 4u, k, cj, wj);
+      blk[2 * RWF + d] = __float_as_uint(tc::tf32_trunc(tile[k][32 * hb + 4 * cj + (wj >> 2)]));
+      const float x = tile[k][32 * hb + ((8 * cj + (wj >> 1)) >> 1)];
+      const float hi = tc::tf32_trunc(x);
+      blk[3 * RWF + d] = tc::bf16_bits(x - hi) | (tc::bf16_bits(hi) << 16);
+    }
+  }
 }
-void launch_format_h(const void* H, int64_t ldh, int kt, void* Hf, const FitState* state, cudaStream_t st) {
-  dim3 grid((unsigned)((ldh + 255) / 256), (unsigned)kt);
-  if (kt == 64) format_h_kernel<64><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state);
-  else format_h_kernel<32><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state);
+
+void launch_format_w(const void* W, int64_t m, int64_t mpad, int kt, void* Wf, const FitState* state, cudaStream_t st,
+                     int batch_n, int64_t bstride) {
+  const dim3 grid((unsigned)(mpad / 32), 1, (unsigned)batch_n);       // one block per 32-row block of W
+  if (kt == 64) format_w_kernel<64><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state, bstride);
+  else format_w_kernel<32><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state, bstride);
+}
+void launch_format_h(const void* H, int64_t ldh, int kt, void* Hf, const FitState* state, cudaStream_t st,
+                     int batch_n, int64_t bstride) {
+  dim3 grid((unsigned)(ldh / 64), 1, (unsigned)batch_n);              // one block per 64-column block of H
+  if (kt == 64) format_h_kernel<64><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state, bstride);
+  else format_h_kernel<32><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state, bstride);
 }
 
 // Ones per column of a re-tiled plane (Pc layout), accumulated over the row blocks [rb0, rb1): the H pass uses the

@@ -22,6 +22,10 @@ struct HTcArgs {
                              // that is accumulated directly, see h_pass_tc_kernel (K <= 64 kernels decide in the kernel)
   const uint32_t* flipcol;   // [ldh] K <= 32 kernels: the decision per column (0 / ~0), made by flip_cols_kernel per H pass
   const int* flip_any;       // 1 if any column of flipcol is set: selects the kernel instantiation that does the work
+  // batched small fits: gridDim.z fits whose workspaces lie batch_stride bytes apart advance with one launch; EVERY pointer
+  // above lives in the fit's workspace (factors, formatted operands, re-tiled planes, partials, flags) and is shifted by
+  // blockIdx.z * batch_stride
+  int64_t batch_stride = 0;
 };
 
 struct WTcArgs {
@@ -34,6 +38,7 @@ struct WTcArgs {
   float* Q;                  // [nsplit][m]
   float eps;
   const int* done;
+  int64_t batch_stride = 0;  // see HTcArgs: W, Hf, PM, G, Q, done are shifted per fit
 };
 
 }  // namespace nbmf

@@ -15,9 +15,10 @@ void launch_w_pass_tensor(const WPassArgs& a, const void* Hf, const void* PM, in
   t.m = a.m; t.n = a.n; t.wpr = a.wpr;
   t.cols_per_split = a.cols_per_split;
   t.G = (float*)a.G; t.Q = (float*)a.Q; t.eps = (float)a.eps; t.done = a.done;
-  if (kb == 16) k32::launch_w_pass_tc<16>(t, nsplit, st);
-  else if (kb == 32) k32::launch_w_pass_tc<32>(t, nsplit, st);
-  else k64::launch_w_pass_tc_kb<64>(t, nsplit, st);
+  t.batch_stride = a.batch_n > 1 ? a.batch_stride : 0;
+  if (kb == 16) k32::launch_w_pass_tc<16>(t, nsplit, a.batch_n, st);
+  else if (kb == 32) k32::launch_w_pass_tc<32>(t, nsplit, a.batch_n, st);
+  else k64::launch_w_pass_tc_kb<64>(t, nsplit, a.batch_n, st);
 }
 
 void launch_h_pass_tensor(const HPassArgs& a, const void* Wf, const uint32_t* Pc, const uint32_t* Mc, int64_t nrb,
@@ -28,9 +29,10 @@ void launch_h_pass_tensor(const HPassArgs& a, const void* Wf, const uint32_t* Pc
   t.rows_per_split = a.rows_per_split;
   t.CD = (float*)a.CD; t.LL = a.LL; t.eps = (float)a.eps; t.done = a.done; t.compute_cd = a.compute_cd;
   t.k = k; t.colcnt = colcnt; t.flipcol = flipcol; t.flip_any = flip_any;
-  if (kb == 16) k32::launch_h_pass_tc<16>(t, nsplit, st);
-  else if (kb == 32) k32::launch_h_pass_tc<32>(t, nsplit, st);
-  else k64::launch_h_pass_tc_kb<64>(t, nsplit, st);
+  t.batch_stride = a.batch_n > 1 ? a.batch_stride : 0;
+  if (kb == 16) k32::launch_h_pass_tc<16>(t, nsplit, a.batch_n, st);
+  else if (kb == 32) k32::launch_h_pass_tc<32>(t, nsplit, a.batch_n, st);
+  else k64::launch_h_pass_tc_kb<64>(t, nsplit, a.batch_n, st);
 }
 
 }  // namespace nbmf

@@ -36,6 +36,9 @@
 
 #include <type_traits>
 
+// pointer `ptr` of the kernel arguments `a` for fit blockIdx.z of a batch (workspaces batch_stride bytes apart)
+#define NBMF_TSH(ptr) batch_shift(ptr, (size_t)blockIdx.z * (size_t)a.batch_stride)
+
 namespace nbmf {
 namespace k32 {
 
@@ -189,9 +192,9 @@ template <int KB, bool STRICT, bool CD, bool FLIP>   // CD = false: loss-only pa
 __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs a) {
   static_assert(KB == 16 || KB == 32, "KB");
   static_assert(CD || !FLIP, "the loss-only pass has no planes to choose");
-  if (CD && a.flip_any != nullptr && (*a.flip_any != 0) != FLIP) return;
+  if (CD && a.flip_any != nullptr && (*NBMF_TSH(a.flip_any) != 0) != FLIP) return;
   using namespace tc;
-  if (*a.done) return;
+  if (*NBMF_TSH(a.done)) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sAcc = reinterpret_cast<float*>(smem + HTC_OFF_ACC);      // thread t: 16 C then 16 S sums at [e * 512 + t]
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
     const int g = warp - TC_MMA1_WARP;
     const bool leader = elect_one();
     const uint32_t tT = tTheta + 32 * g;
-    const float* src = a.Wf + (size_t)(r0 >> 5) * 4096;
+    const float* src = NBMF_TSH(a.Wf) + (size_t)(r0 >> 5) * 4096;
     auto produce = [&](int bp) {
       if (bp >= nb) return;
       const int s = bp % HTC_STAGES;
@@ -325,7 +328,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       uint32_t hi[8], bh[4], bl[4];
 #pragma unroll
       for (int e = 0; e < 8; e += 2) {
-        const float x0 = a.H[(size_t)(8 * w4 + e) * a.ldh + col], x1 = a.H[(size_t)(8 * w4 + e + 1) * a.ldh + col];
+        const float* __restrict__ Hb = NBMF_TSH(a.H);
+        const float x0 = Hb[(size_t)(8 * w4 + e) * a.ldh + col], x1 = Hb[(size_t)(8 * w4 + e + 1) * a.ldh + col];
         const float h0 = tf32_trunc(x0), h1 = tf32_trunc(x1);
         hi[e] = __float_as_uint(h0);
         hi[e + 1] = __float_as_uint(h1);
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       if (lane == 0) mbar_arrive(&bar_a);
     }
     uint32_t fmask = 0u;                                               // all ones: this column accumulates the zeros' plane
-    if constexpr (FLIP) fmask = a.flipcol[col];
+    if constexpr (FLIP) fmask = NBMF_TSH(a.flipcol)[col];
     // fp32 sums of this thread's accumulator slice (k = HALF h .. of the group's Q and S, HALF = KB / 2) live in
     // shared memory: they are touched once per chain, registers are what the hot loop is short of
     constexpr int HALF = KB / 2;
@@ -372,12 +376,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       }
       ++flushed;
     };
-    const uint32_t* __restrict__ pc = a.Pc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
+    const uint32_t* __restrict__ pc = NBMF_TSH(a.Pc) + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
     uint32_t word = g < nb ? pc[(size_t)g * 128] : 0u;
     const uint32_t* __restrict__ mc = nullptr;
     uint32_t mword = 0u;
     if constexpr (STRICT) {
-      mc = a.Mc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
+      mc = NBMF_TSH(a.Mc) + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
       mword = g < nb ? mc[(size_t)g * 128] : 0u;
     }
     float ll = 0.f, ll_sum = 0.f, ll_c = 0.f;                          // fp64 is slow here: compensated fp32 sum
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
       if (g < nb) flush();                                             // the group's last chain
       asm volatile("bar.sync 1, 512;" ::: "memory");                   // the 16 SIMT warps only
       if (g == 0) {                                                    // group 0 + group 1 (thread tid + 128), fixed order
-        float* __restrict__ base = a.CD + (size_t)(split * 2) * 32 * a.ldh;   // C rows 0..31 then D rows 0..31
+        float* __restrict__ base = NBMF_TSH(a.CD) + (size_t)(split * 2) * 32 * a.ldh;   // C rows 0..31 then D rows 0..31
 #pragma unroll
         for (int e = 0; e < HALF; ++e) {                               // column j of row k: coalesced across the warp
           const float qv = myacc[e * 512] + myacc[e * 512 + 128];
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) h_pass_tc_kernel(const HTcArgs 
   __syncthreads();
   if (warp == TC_MMA1_WARP) tmem_dealloc(tb, 512);
   const double tot = block_sum<TC_THREADS>(ll_total, red_scratch);
-  if (tid == 0) a.LL[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<float>();
+  if (tid == 0) NBMF_TSH(a.LL)[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<float>();
 }
 
 // =====================================================================================
@@ -511,7 +515,7 @@ template <int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs a) {
   static_assert(KB == 16 || KB == 32, "KB");
   using namespace tc;
-  if (*a.done) return;
+  if (*NBMF_TSH(a.done)) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sX = reinterpret_cast<float*>(smem + WTC_OFF_X);           // [16 accumulators][256 threads of group 1]
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     const int g = warp - TC_MMA1_WARP;
     const bool leader = elect_one();
     const uint32_t tT = tTheta + 64 * g;
-    const float* src = a.Hf + (size_t)(c0 >> 6) * 8192;
+    const float* src = NBMF_TSH(a.Hf) + (size_t)(c0 >> 6) * 8192;
     auto produce = [&](int bp) {
       if (bp >= nb) return;
       const int s = bp % WTC_STAGES;
@@ -624,8 +628,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     {  // resident A operand: this thread's row of W, k = 8 w4 .. 8 w4 + 7 (zero beyond m)
       float x[8];
       if (row < a.m) {
-        const float4 x0 = *reinterpret_cast<const float4*>(a.W + (size_t)row * 32 + 8 * w4);
-        const float4 x1 = *reinterpret_cast<const float4*>(a.W + (size_t)row * 32 + 8 * w4 + 4);
+        const float* __restrict__ Wb = NBMF_TSH(a.W);
+        const float4 x0 = *reinterpret_cast<const float4*>(Wb + (size_t)row * 32 + 8 * w4);
+        const float4 x1 = *reinterpret_cast<const float4*>(Wb + (size_t)row * 32 + 8 * w4 + 4);
         x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
       } else {
 #pragma unroll
@@ -670,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
       }
       ++flushed;
     };
-    const uint2* __restrict__ pm = a.PM + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5) + h) * 128 + tl;
+    const uint2* __restrict__ pm = NBMF_TSH(a.PM) + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5) + h) * 128 + tl;
     uint2 word = g < nb ? pm[(size_t)(2 * g) * 128] : make_uint2(0u, 0u);
     float qsum = 0.f;
     bool ok_theta = false;                                             // early barrier probes, see the H pass
@@ -728,14 +733,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     }
     asm volatile("bar.sync 1, 512;" ::: "memory");                     // the 16 SIMT warps only
     if (g == 0 && row < a.m) {                                         // group 0 + group 1, fixed order
-      float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * 32 + NG * h;
+      float* __restrict__ Gg = NBMF_TSH(a.G) + ((size_t)blockIdx.y * a.m + row) * 32 + NG * h;
 #pragma unroll
       for (int e = 0; e < NG; e += 4)
         *reinterpret_cast<float4*>(Gg + e) =
             make_float4(accG[e] + sX[e * 256 + t], accG[e + 1] + sX[(e + 1) * 256 + t],
                         accG[e + 2] + sX[(e + 2) * 256 + t], accG[e + 3] + sX[(e + 3) * 256 + t]);
       if (h == 0)
-        a.Q[(size_t)blockIdx.y * a.m + row] = ((sQ[tl] + sQ[128 + tl]) + sQ[256 + tl]) + sQ[384 + tl];
+        NBMF_TSH(a.Q)[(size_t)blockIdx.y * a.m + row] = ((sQ[tl] + sQ[128 + tl]) + sQ[256 + tl]) + sQ[384 + tl];
     }
   }
   fence_before_sync();
@@ -744,10 +749,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
 }
 
 template <int KB>
-inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
+inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, int batch_n, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_set{0};
   ensure_dynamic_smem(w_pass_tc_kernel<KB>, WTC_SMEM, attr_set);
-  dim3 grid((unsigned)((a.m + 127) / 128), (unsigned)nsplit);
+  dim3 grid((unsigned)((a.m + 127) / 128), (unsigned)nsplit, (unsigned)batch_n);
   w_pass_tc_kernel<KB><<<grid, TC_THREADS, WTC_SMEM, st>>>(a);
 }
 // Decides, per H pass, which columns accumulate the zeros' plane directly (density of ones above the mean of the column
@@ -756,7 +761,12 @@ inline void launch_w_pass_tc(const WTcArgs& a, int nsplit, cudaStream_t st) {
 // OR in progress, flag[2] = blocks finished; the last block resets [1], [2] for the next launch.
 __global__ void __launch_bounds__(256) flip_cols_kernel(const float* __restrict__ H, int64_t ldh, int64_t n, int k, int64_t m,
                                                         const uint32_t* __restrict__ colcnt, uint32_t* __restrict__ flipcol,
-                                                        int* __restrict__ flag, const int* __restrict__ done) {
+                                                        int* __restrict__ flag, const int* __restrict__ done, int64_t bstride) {
+  if (bstride) {                                  // fit blockIdx.y of a batch: its own workspace
+    const size_t sh = (size_t)blockIdx.y * (size_t)bstride;
+    H = batch_shift(H, sh); colcnt = batch_shift(colcnt, sh); flipcol = batch_shift(flipcol, sh);
+    flag = batch_shift(flag, sh); done = batch_shift(done, sh);
+  }
   if (*done) return;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t f = 0u;
@@ -779,7 +789,7 @@ __global__ void __launch_bounds__(256) flip_cols_kernel(const float* __restrict_
 }
 
 template <int KB>
-inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, cudaStream_t st) {
+inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, int batch_n, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_set[6];
   ensure_dynamic_smem(h_pass_tc_kernel<KB, false, true, false>, HTC_SMEM, attr_set[0]);
   ensure_dynamic_smem(h_pass_tc_kernel<KB, true, true, false>, HTC_SMEM, attr_set[1]);
@@ -787,14 +797,13 @@ inline void launch_h_pass_tc(const HTcArgs& a, int nsplit, cudaStream_t st) {
   ensure_dynamic_smem(h_pass_tc_kernel<KB, true, false, false>, HTC_SMEM, attr_set[3]);
   ensure_dynamic_smem(h_pass_tc_kernel<KB, false, true, true>, HTC_SMEM, attr_set[4]);
   ensure_dynamic_smem(h_pass_tc_kernel<KB, true, true, true>, HTC_SMEM, attr_set[5]);
-  dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit);
+  dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit, (unsigned)batch_n);
   if (a.compute_cd) {
     const bool flips = a.colcnt != nullptr && a.flipcol != nullptr && a.flip_any != nullptr;
     HTcArgs b = a;
     if (!flips) b.flip_any = nullptr;                                  // no decision data: the FLIP = false kernel always runs
-    else flip_cols_kernel<<<(unsigned)((a.ldh + 255) / 256), 256, 0, st>>>(a.H, a.ldh, a.n, a.k, a.m, a.colcnt,
-                                                                         const_cast<uint32_t*>(a.flipcol),
-                                                                         const_cast<int*>(a.flip_any), a.done);
+    else flip_cols_kernel<<<dim3((unsigned)((a.ldh + 255) / 256), (unsigned)batch_n), 256, 0, st>>>(
+        a.H, a.ldh, a.n, a.k, a.m, a.colcnt, const_cast<uint32_t*>(a.flipcol), const_cast<int*>(a.flip_any), a.done, a.batch_stride);
     if (a.Mc) h_pass_tc_kernel<KB, true, true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
     else h_pass_tc_kernel<KB, false, true, false><<<grid, TC_THREADS, HTC_SMEM, st>>>(b);
     if (flips) {

@@ -39,6 +39,9 @@
 
 #include <type_traits>
 
+// pointer `ptr` of the kernel arguments `a` for fit blockIdx.z of a batch (workspaces batch_stride bytes apart)
+#define NBMF_TSH(ptr) batch_shift(ptr, (size_t)blockIdx.z * (size_t)a.batch_stride)
+
 namespace nbmf {
 namespace k64 {
 
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) h_pass_tc_kernel(const 
   using C = TcCfg<KB>;
   using L = HTc<KB>;
   constexpr int P = C::P, NSETS = C::NSETS, KT = C::KT, NACC = C::NACC, STAGES = L::STAGES;
-  if (*a.done) return;
+  if (*NBMF_TSH(a.done)) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sAcc = reinterpret_cast<float*>(smem + L::OFF_ACC);        // [NV][NFT]
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) h_pass_tc_kernel(const 
     constexpr int NM1 = C::NM1;
     const int e = warp - C::MMA1_WARP;
     const bool leader = elect_one();
-    const float* src = a.Wf + (size_t)(r0 >> 5) * (L::STAGE_BYTES / 4);
+    const float* src = NBMF_TSH(a.Wf) + (size_t)(r0 >> 5) * (L::STAGE_BYTES / 4);
     auto produce = [&](int bp) {
       if (bp >= nb) return;
       const int s = bp % STAGES;
@@ -357,12 +360,13 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) h_pass_tc_kernel(const 
     // resident A operand: this thread's column of H; the pipelines of a lane quarter share the K chunks of 8:
     // tf32 hi plane (KT columns) and the bf16 correction plane [hi (k = 0..KT-1) | lo], two elements per column
     float hsum = 0.f;
+    const float* __restrict__ Hb = NBMF_TSH(a.H);
 #pragma unroll
     for (int c = p; c < KT / 8; c += P) {
       uint32_t hi[8], bh[4], bl[4];
 #pragma unroll
       for (int e = 0; e < 8; e += 2) {
-        const float x0 = a.H[(size_t)(8 * c + e) * a.ldh + col], x1 = a.H[(size_t)(8 * c + e + 1) * a.ldh + col];
+        const float x0 = Hb[(size_t)(8 * c + e) * a.ldh + col], x1 = Hb[(size_t)(8 * c + e + 1) * a.ldh + col];
         const float h0 = tf32_trunc(x0), h1 = tf32_trunc(x1);
         hi[e] = __float_as_uint(h0);
         hi[e + 1] = __float_as_uint(h1);
@@ -381,8 +385,8 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) h_pass_tc_kernel(const 
     // decides the same way from the same inputs
     uint32_t fmask = 0u;
     if (CD && a.colcnt != nullptr && col < a.n) {
-      for (int k = 0; k < a.k; ++k) hsum += a.H[(size_t)k * a.ldh + col];
-      const float hbar = hsum / (float)a.k, d = (float)a.colcnt[col] / (float)a.m;
+      for (int k = 0; k < a.k; ++k) hsum += Hb[(size_t)k * a.ldh + col];
+      const float hbar = hsum / (float)a.k, d = (float)NBMF_TSH(a.colcnt)[col] / (float)a.m;
       if (d > hbar) fmask = 0xffffffffu;
     }
     const bool any_flip = __any_sync(0xffffffffu, fmask != 0u);
@@ -432,9 +436,9 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) h_pass_tc_kernel(const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_flushed[set]);                   // the next chain may overwrite the accumulators
     };
-    const uint32_t* __restrict__ pc = a.Pc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
+    const uint32_t* __restrict__ pc = NBMF_TSH(a.Pc) + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
     const uint32_t* __restrict__ mc = nullptr;
-    if constexpr (STRICT) mc = a.Mc + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
+    if constexpr (STRICT) mc = NBMF_TSH(a.Mc) + ((size_t)blockIdx.x * a.nrb + (size_t)(r0 >> 5)) * 128 + tl;
     const int nhb = 2 * nb;
     uint32_t word = p < nhb ? pc[(size_t)(p >> 1) * 128] : 0u, mword = 0u;
     if constexpr (STRICT) mword = p < nhb ? mc[(size_t)(p >> 1) * 128] : 0u;
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) h_pass_tc_kernel(const 
       const int chains = (nblk_set + kFlush - 1) / kFlush;
       while (flusher && flushed < chains) flush();                     // the set's last chain(s)
       asm volatile("bar.sync 1, %0;" ::"n"(32 * C::SIMT_WARPS) : "memory");   // the SIMT warps only
-      float* __restrict__ base = a.CD + (size_t)(split * 2) * KT * a.ldh;     // C rows 0..KT-1 then D rows 0..KT-1
+      float* __restrict__ base = NBMF_TSH(a.CD) + (size_t)(split * 2) * KT * a.ldh;     // C rows 0..KT-1 then D rows 0..KT-1
       if constexpr (KB == 64) {
         if (p == 0) {                                                  // Q from this thread, S from pipeline 1's (+128)
 #pragma unroll 8
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) h_pass_tc_kernel(const 
   __syncthreads();
   if (warp == C::MMA1_WARP) tmem_dealloc(tb, 512);
   const double tot = block_sum<C::THREADS>(ll_total, red_scratch);
-  if (tid == 0) a.LL[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<float>();
+  if (tid == 0) NBMF_TSH(a.LL)[(size_t)split * gridDim.x + blockIdx.x] = tot * log_unit<float>();
 }
 
 // =====================================================================================
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) w_pass_tc_kernel(const 
   using C = TcCfg<KB>;
   using L = WTc<KB>;
   constexpr int P = C::P, NSETS = C::NSETS, KT = C::KT, NACC = C::NACC, STAGES = L::STAGES, NG = L::NG;
-  if (*a.done) return;
+  if (*NBMF_TSH(a.done)) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sX = reinterpret_cast<float*>(smem + L::OFF_X);            // [NG][256 threads of set 1]
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) w_pass_tc_kernel(const 
     constexpr int NM1 = C::NM1;
     const int e = warp - C::MMA1_WARP;
     const bool leader = elect_one();
-    const float* src = a.Hf + (size_t)(c0 >> 6) * (L::STAGE_BYTES / 4);
+    const float* src = NBMF_TSH(a.Hf) + (size_t)(c0 >> 6) * (L::STAGE_BYTES / 4);
     auto produce = [&](int bp) {
       if (bp >= nb) return;
       const int s = bp % STAGES;
@@ -723,8 +727,9 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) w_pass_tc_kernel(const 
     for (int c = p; c < KT / 8; c += P) {
       float x[8];
       if (row < a.m) {
-        const float4 x0 = *reinterpret_cast<const float4*>(a.W + (size_t)row * KT + 8 * c);
-        const float4 x1 = *reinterpret_cast<const float4*>(a.W + (size_t)row * KT + 8 * c + 4);
+        const float* __restrict__ Wb = NBMF_TSH(a.W);
+        const float4 x0 = *reinterpret_cast<const float4*>(Wb + (size_t)row * KT + 8 * c);
+        const float4 x1 = *reinterpret_cast<const float4*>(Wb + (size_t)row * KT + 8 * c + 4);
         x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
       } else {
 #pragma unroll
@@ -782,7 +787,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) w_pass_tc_kernel(const 
       if (lane == 0) mbar_arrive(&bar_flushed[set]);
     };
     const int nhb = 2 * nb;
-    const uint2* __restrict__ pm = a.PM + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5)) * 128 + tl;
+    const uint2* __restrict__ pm = NBMF_TSH(a.PM) + ((size_t)blockIdx.x * a.wpr + (size_t)(c0 >> 5)) * 128 + tl;
     uint2 word = p < nhb ? pm[(size_t)p * 128] : make_uint2(0u, 0u);
     float qsum = 0.f;
     bool ok_theta = false;                                             // early barrier probes, see the H pass
@@ -842,7 +847,7 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) w_pass_tc_kernel(const 
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * C::SIMT_WARPS) : "memory");   // the SIMT warps only
       if (set == 0 && row < a.m) {                                     // set 0 + set 1, fixed order
-        float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * KT + gcol;
+        float* __restrict__ Gg = NBMF_TSH(a.G) + ((size_t)blockIdx.y * a.m + row) * KT + gcol;
 #pragma unroll
         for (int e = 0; e < NG; e += 4)
           *reinterpret_cast<float4*>(Gg + e) =
@@ -853,16 +858,16 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) w_pass_tc_kernel(const 
           for (int e = 0; e < 8; e += 4) *reinterpret_cast<float4*>(Gg + 16 - gcol + 8 * (p & 1) + e) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (p == 0)
-          a.Q[(size_t)blockIdx.y * a.m + row] = ((sQ[tl] + sQ[128 + tl]) + sQ[256 + tl]) + sQ[384 + tl];
+          NBMF_TSH(a.Q)[(size_t)blockIdx.y * a.m + row] = ((sQ[tl] + sQ[128 + tl]) + sQ[256 + tl]) + sQ[384 + tl];
       }
     } else {
       asm volatile("bar.sync 1, %0;" ::"n"(32 * C::SIMT_WARPS) : "memory");
       if (p < 2 && row < a.m) {                                        // pipelines 0, 1 hold G columns 0..31, 32..63
-        float* __restrict__ Gg = a.G + ((size_t)blockIdx.y * a.m + row) * KT + gcol;
+        float* __restrict__ Gg = NBMF_TSH(a.G) + ((size_t)blockIdx.y * a.m + row) * KT + gcol;
 #pragma unroll
         for (int e = 0; e < NG; e += 4)
           *reinterpret_cast<float4*>(Gg + e) = make_float4(accG[e], accG[e + 1], accG[e + 2], accG[e + 3]);
-        if (p == 0) a.Q[(size_t)blockIdx.y * a.m + row] = (sQ[tl] + sQ[128 + tl]) + sQ[256 + tl];
+        if (p == 0) NBMF_TSH(a.Q)[(size_t)blockIdx.y * a.m + row] = (sQ[tl] + sQ[128 + tl]) + sQ[256 + tl];
       }
     }
   }
@@ -873,20 +878,20 @@ __global__ void __launch_bounds__(TcCfg<KB>::THREADS, 1) w_pass_tc_kernel(const 
 
 // ------------------------------------------------------------------------------------------------------------------ launchers
 template <int KB>
-inline void launch_w_pass_tc_kb(const WTcArgs& a, int nsplit, cudaStream_t st) {
+inline void launch_w_pass_tc_kb(const WTcArgs& a, int nsplit, int batch_n, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_set{0};
   ensure_dynamic_smem(w_pass_tc_kernel<KB>, WTc<KB>::SMEM, attr_set);
-  dim3 grid((unsigned)((a.m + 127) / 128), (unsigned)nsplit);
+  dim3 grid((unsigned)((a.m + 127) / 128), (unsigned)nsplit, (unsigned)batch_n);
   w_pass_tc_kernel<KB><<<grid, TcCfg<KB>::THREADS, WTc<KB>::SMEM, st>>>(a);
 }
 template <int KB>
-inline void launch_h_pass_tc_kb(const HTcArgs& a, int nsplit, cudaStream_t st) {
+inline void launch_h_pass_tc_kb(const HTcArgs& a, int nsplit, int batch_n, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_set[4];
   ensure_dynamic_smem(h_pass_tc_kernel<KB, false, true>, HTc<KB>::SMEM, attr_set[0]);
   ensure_dynamic_smem(h_pass_tc_kernel<KB, true, true>, HTc<KB>::SMEM, attr_set[1]);
   ensure_dynamic_smem(h_pass_tc_kernel<KB, false, false>, HTc<KB>::SMEM, attr_set[2]);
   ensure_dynamic_smem(h_pass_tc_kernel<KB, true, false>, HTc<KB>::SMEM, attr_set[3]);
-  dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit);
+  dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)nsplit, (unsigned)batch_n);
   constexpr int T = TcCfg<KB>::THREADS, S = HTc<KB>::SMEM;
   if (a.compute_cd) {
     if (a.Mc) h_pass_tc_kernel<KB, true, true><<<grid, T, S, st>>>(a);

@@ -405,6 +405,11 @@ class DeviceProblem:
         self._call("nbmf_simplex_deviation", C.byref(dev))
         return float(dev.value)
 
+    def get_factors_f64_device(self, W_out, H_out, normalize_w=False):
+        """fp64 export (+ the optional row renormalisation of the solver tail) into caller-provided DEVICE tensors: no
+        copy to the host, no synchronisation (batched fits collect all results and cross PCIe once)."""
+        self._call("nbmf_get_factors_f64", _ptr(W_out), _ptr(H_out), 1 if normalize_w else 0)
+
     def get_factors_f64(self, normalize_w=False, out=None, gather=None):
         """Host fp64 copies of W (m x k) and H (k x n); conversion to fp64 and the optional row renormalisation
         of the solver tail (``_solver.py:200-204``) run on the device.  ``out`` = (W, H) pinned host fp64 tensors

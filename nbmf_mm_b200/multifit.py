@@ -70,15 +70,41 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
             queues = 8
         n_streams = max(8, min(queues, 32)) if m * n <= (1 << 24) else 1
     n_streams = max(1, min(int(n_streams), len(jobs)))
-    # inits are drawn on this thread, in job order: the global NumPy RNG is not thread-safe and every job must see
-    # the stream the reference would give it
-    prepared = []
+    # Every job must see the init stream the reference would give it.  Seeded jobs (the usual case: restart r uses
+    # random_state + r) are independent streams, drawn concurrently from private generators (NumPy releases the GIL;
+    # 64 x (1226 x 32 + 32 x 285) doubles cost 30 ms on one thread, as much as the fits themselves on the tensor engine);
+    # the global stream is left where the last seeded job would leave it.  Unseeded jobs use the global stream, in order.
     for j in jobs:
+        if int(j.get("max_iter", max_iter)) < 1:
+            raise UnboundLocalError("max_iter must be >= 1")
+    inits = [None] * len(jobs)
+    seeded = [i for i, j in enumerate(jobs) if j.get("random_state") is not None
+              and (j.get("W_init") is None or j.get("H_init") is None)]
+    if len(seeded) > 1 and all(jobs[i].get("random_state") is not None for i in range(len(jobs))):
+        def draw(i):
+            j = jobs[i]
+            rs = np.random.RandomState(j["random_state"])
+            W_i, H_i = j.get("W_init"), j.get("H_init")
+            k_i = int(j["n_components"])
+            if transpose and W_i is not None and H_i is not None:
+                W_i, H_i = np.asarray(H_i).T, np.asarray(W_i).T
+            if W_i is None:
+                W_i = rs.uniform(0.1, 0.9, (m, k_i))
+            if H_i is None:
+                H_i = rs.uniform(0.1, 0.9, (k_i, n))
+            return np.asarray(W_i, dtype=np.float64), np.asarray(H_i, dtype=np.float64), rs
+        import os
+        with ThreadPoolExecutor(max_workers=min(len(seeded), max(1, (os.cpu_count() or 2) // 2))) as pool:
+            for i, (W_i, H_i, rs) in zip(seeded, pool.map(draw, seeded)):
+                inits[i] = (W_i, H_i)
+                last_state = rs.get_state() if i == seeded[-1] else None
+        np.random.set_state(last_state)                      # as np.random.seed(last seed) + its draws would leave it
+    prepared = []
+    for i, j in enumerate(jobs):
         k = int(j["n_components"])
         mi = int(j.get("max_iter", max_iter))
-        if mi < 1:
-            raise UnboundLocalError("max_iter must be >= 1")
-        W0, H0 = _draw_inits(j.get("random_state"), m, n, k, j.get("W_init"), j.get("H_init"), transpose)
+        W0, H0 = inits[i] if inits[i] is not None else _draw_inits(j.get("random_state"), m, n, k, j.get("W_init"),
+                                                                   j.get("H_init"), transpose)
         prepared.append((k, float(j.get("alpha", 1.2)), float(j.get("beta", 1.2)), mi, float(j.get("tol", tol)), W0, H0))
 
     main_stream = torch.cuda.current_stream(dev)
@@ -108,8 +134,8 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
 
     def run_batch(idxs):
         """Fits with the same K and hyper-parameters advance TOGETHER: contexts with workspaces at a uniform stride in one
-        allocation, one launch per kernel for the whole group (``nbmf_batch_bind``).  Returns None when the group is not
-        eligible (tensor engine), else the results in the order of ``idxs``."""
+        allocation, one launch per kernel for the whole group (``nbmf_batch_bind``; both engines).  Returns the results in
+        the order of ``idxs``."""
         k, _, _, mi, tl = prepared[idxs[0]][:5]
         B = len(idxs)
         big = {}
@@ -124,19 +150,32 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
 
         stream = torch.cuda.Stream(device=dev)               # not the default stream: the loop is replayed from a graph
         probs, out = [], []
+        tdt = getattr(torch, np.dtype(dtype).name)
+        import os, time
+        timing = os.environ.get("NBMF_MULTIFIT_TIMING")
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize(dev)
+                marks.append((name, time.perf_counter()))
         with torch.cuda.stream(stream):
             stream.wait_event(ready)
             try:
+                # the inits of the whole batch cross PCIe in two copies, the results in two (per-fit copies and their
+                # synchronisations cost more than the fits themselves once a batch of small fits runs on the tensor engine)
+                W0s = torch.from_numpy(np.stack([prepared[i][5] for i in idxs])).to(dev).to(tdt)
+                H0s = torch.from_numpy(np.stack([prepared[i][6] for i in idxs])).to(dev).to(tdt)
+                mark("inits uploaded")
                 for b, idx in enumerate(idxs):
                     prob = make_problem(data, k, dtype=dtype, alpha=prepared[idx][1], beta=prepared[idx][2], eps=eps,
                                         mask_semantics=mask_semantics, projection=projection_method, max_iter_cap=mi,
                                         device=device, engine=engine, workspace=slice_of(b),
                                         batch_hint=B if batch_plan == "batch" else 0)
                     probs.append(prob)
-                    if prob.engine != "simt":
-                        return None
-                    prob.set_factors(prepared[idx][5], prepared[idx][6], normalize_w=True)
+                    prob.set_factors(W0s[b], H0s[b], normalize_w=True)
                     prob.fit_begin(mi, tl)
+                mark("contexts created")
                 leader = probs[0]
                 leader.batch_bind(B, big["S"])
                 chunk, n_iters = 16, [0] * B
@@ -149,16 +188,32 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                 else:
                     raise RuntimeError("batched fit loop did not terminate")
                 leader.batch_bind(1, 0)
-                for prob, n_iter in zip(probs, n_iters):
+                mark("loop")
+                Wd = torch.empty((B, m, k), dtype=torch.float64, device=dev)
+                Hd = torch.empty((B, k, n), dtype=torch.float64, device=dev)
+                meta = []
+                for b, (prob, n_iter) in enumerate(zip(probs, n_iters)):
                     losses_arr, converged = prob.fit_history(n_iter)
                     dv = prob.simplex_deviation()            # solver tail, _solver.py:192-213
-                    W, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dv) and dv > 1e-9))
+                    prob.get_factors_f64_device(Wd[b], Hd[b], normalize_w=bool(np.isfinite(dv) and dv > 1e-9))
+                    meta.append(([np.float64(v) for v in losses_arr], n_iter, converged, prob.engine))
+                mark("tails")
+                Wh, Hh = Wd.cpu().numpy(), Hd.cpu().numpy()
+                mark("results downloaded")
+                for b, (losses, n_iter, converged, eng) in enumerate(meta):
+                    W, H = Wh[b], Hh[b]
                     if transpose:                            # _solver.py:182-184
                         W, H = np.ascontiguousarray(H.T), np.ascontiguousarray(W.T)
-                    out.append((W, H, [np.float64(v) for v in losses_arr], 0.0, n_iter, converged, prob.engine))
+                    else:
+                        W, H = np.ascontiguousarray(W), np.ascontiguousarray(H)
+                    out.append((W, H, losses, 0.0, n_iter, converged, eng))
             finally:
                 for prob in probs:
                     prob.close()
+        if timing:
+            marks.append(("closed", time.perf_counter()))
+            print("[multifit batch of %d, K=%d] " % (B, k) + ", ".join(f"{n} {1e3 * (t - marks[i][1]):.1f} ms" for i, (n, t) in enumerate(marks[1:])),
+                  flush=True)
         return out
 
     # groups of fits that can advance together (same K, max_iter, tol: restarts AND alpha / beta grids -- the Beta prior

@@ -207,7 +207,7 @@ def resolve_engine(engine, *, dtype, vkind, k, eps, m_total, n):
     if engine != "auto":
         return engine
     eligible = np.dtype(dtype) == np.float32 and vkind == "bits" and k <= TENSOR_MAX_K and eps >= 1e-9
-    return "tensor" if eligible and m_total >= 512 and n >= 512 else "simt"
+    return "tensor" if eligible and m_total >= 512 and n >= 128 else "simt"
 
 
 def draw_shard_inits(seed, m, n, k, r0, r1, *, h_part=(0, 1), set_global_state=True):

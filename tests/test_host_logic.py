@@ -164,6 +164,7 @@ def test_engine_is_resolved_from_the_global_problem_size():
     assert [_row_shard(2000, r, 4) for r in range(4)] == [(0, 512), (512, 1024), (1024, 1536), (1536, 2000)]
     assert resolve_engine("auto", m_total=2000, **kw) == "tensor"
     assert resolve_engine("auto", m_total=400, **kw) == "simt"
+    assert resolve_engine("auto", m_total=2000, dtype="float32", vkind="bits", k=20, eps=1e-8, n=100) == "simt"
     assert resolve_engine("simt", m_total=2000, **kw) == "simt"
     assert resolve_engine("auto", m_total=2000, dtype="float64", vkind="bits", k=20, eps=1e-8, n=4096) == "simt"
     assert resolve_engine("auto", m_total=2000, dtype="float32", vkind="dense", k=20, eps=1e-8, n=4096) == "simt"
