@@ -546,11 +546,20 @@ def run_configs():
 
     # configs[4]: 64 restarts, K sweep on lastfm-shaped data
     L = (np.random.default_rng(0).random((1226, 285)) < 0.0435).astype(np.float64)
+    # (the GPU legs first, back to back: after a minute of CPU-only work the GPU has dropped to its idle clocks and the
+    # first calls, tens of milliseconds long, are over before it has ramped up again)
+    gpu_s = {}
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 1.5:                  # untimed: clocks back up after the CPU leg of configs[2]
+        nbmf_mm_multifit(L, [dict(n_components=32, random_state=r) for r in range(64)], max_iter=200, tol=0.0, dtype="float32")
     for k in (6, 16, 32, 64):
         jobs = [dict(n_components=k, random_state=r) for r in range(64)]
-        gs, _ = timed(lambda: nbmf_mm_multifit(L, jobs, max_iter=200, tol=0.0, dtype="float32"))
-        cs, _ = cpu_time(lambda: orc.fit(L, k, max_iter=200, tol=0.0, random_state=0))
-        line(f"cfg5 64 restarts 1226x285 K={k} float32", gs, 200 * 64, cs * 64, 200 * 64, L.size, "(CPU: one restart timed, x 64)")
+        gpu_s[k], res = timed(lambda: nbmf_mm_multifit(L, jobs, max_iter=200, tol=0.0, dtype="float32"), reps=4)
+        gpu_s[k] = (gpu_s[k], min(r[2][-1] for r in res))
+    for k in (6, 16, 32, 64):
+        cs, ref = cpu_time(lambda: orc.fit(L, k, max_iter=200, tol=0.0, random_state=0))
+        line(f"cfg5 64 restarts 1226x285 K={k} float32", gpu_s[k][0], 200 * 64, cs * 64, 200 * 64, L.size,
+             f"(CPU: one restart timed, x 64; best final loss {gpu_s[k][1]:.9f}, restart 0 on the CPU {ref[2][-1]:.9f})")
 
 
 def run_config5_restarts(a):
