@@ -52,9 +52,13 @@ extern "C" {
 #define NBMF_PROJ_NORMALIZE 0 /* multiplicative step, /n, L1 renormalisation (_solver.py:53-57) */
 #define NBMF_PROJ_DUCHI 1     /* multiplicative step / n_obs(row), Euclidean simplex projection; unpinned */
 
-#define NBMF_ENGINE_AUTO 0   /* tensor engine when eligible and m >= 512, n >= 128, else SIMT */
+#define NBMF_ENGINE_AUTO 0   /* a single small fit: FUSED; else TENSOR when eligible and m >= 512, n >= 128; else SIMT */
 #define NBMF_ENGINE_SIMT 1   /* packed-FFMA2 CUDA-core kernels: every dtype / K <= 64 / layout */
 #define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, TF32 + bf16 split precision: float32, bit-packed V, K <= 64, eps >= 1e-9 */
+#define NBMF_ENGINE_FUSED 3  /* SIMT arithmetic, but the fit loop (nbmf_fit / nbmf_fit_enqueue) runs whole iterations inside one
+                              * persistent cooperative kernel: bit-packed V, K <= 32, single GPU.  AUTO picks it while
+                              * m * n * padded K <= 1.6e7 (fp64) / 1.2e7 (fp32): a fit that small is bound by launch latency.
+                              * The half-step / transform entry points of such a context use the SIMT kernels. */
 
 typedef struct nbmf_ctx nbmf_ctx;
 
@@ -72,7 +76,7 @@ typedef struct nbmf_config {
   double eps;            /* 1e-8 in the reference */
   double n_obs;          /* loss denominator: Y.size or count_nonzero(mask) over ALL shards (_solver.py:151,155) */
   int32_t max_iter_cap;  /* capacity of the on-device loss history */
-  int32_t engine;        /* NBMF_ENGINE_AUTO | _SIMT | _TENSOR (env NBMF_ENGINE=auto|simt|tensor overrides) */
+  int32_t engine;        /* NBMF_ENGINE_AUTO | _SIMT | _TENSOR | _FUSED (env NBMF_ENGINE=auto|simt|tensor|fused overrides) */
   int32_t batch_hint;    /* 0 / 1: plan the launches for this fit alone.  n > 1: the context will be one of n fits that
                           * advance together (nbmf_batch_bind): the batch fills the SMs, so a fit is cut into fewer, larger
                           * row / column splits (config 5: 64 restarts 25 % faster).  Changes the summation order of the
@@ -204,8 +208,13 @@ int nbmf_comm_world(nbmf_ctx* ctx);
 int nbmf_comm_create(const void* id128_host, int32_t rank, int32_t world, void** comm_out);
 int nbmf_comm_attach(nbmf_ctx* ctx, void* comm, int32_t rank, int32_t world);
 int nbmf_comm_destroy(void* comm);
-/* engine actually selected for this context: NBMF_ENGINE_SIMT or NBMF_ENGINE_TENSOR */
+/* engine actually selected for this context: NBMF_ENGINE_SIMT, NBMF_ENGINE_TENSOR or NBMF_ENGINE_FUSED */
 int nbmf_engine(nbmf_ctx* ctx);
+/* 1 when nbmf_fit / nbmf_fit_enqueue of this context run whole iterations inside the persistent small-fit kernel right
+ * now (engine FUSED, no communicator attached, per-launch profiling off; env NBMF_NO_FUSED=1 at nbmf_create keeps AUTO
+ * away from it): same arithmetic per entry as the SIMT pass kernels, one cooperative launch per nbmf_fit_enqueue call
+ * instead of six launches per iteration (reference: the loop body of _solver.py:140-175) */
+int nbmf_fit_is_fused(nbmf_ctx* ctx);
 
 /* ---- the init stream of the reference for one row shard (host function, no GPU) ----
  * out[i] = lo + (hi - lo) * u_i for the `count` doubles that follow `skip` doubles in the stream of

@@ -17,8 +17,8 @@ NBMF_F32, NBMF_F64, NBMF_U8, NBMF_F16 = 0, 1, 2, 3
 NBMF_V_BITS, NBMF_V_DENSE, NBMF_V_DENSE_F16 = 0, 1, 2
 NBMF_MASK_REFERENCE, NBMF_MASK_STRICT = 0, 1
 NBMF_PROJ_NORMALIZE, NBMF_PROJ_DUCHI = 0, 1
-NBMF_ENGINE_AUTO, NBMF_ENGINE_SIMT, NBMF_ENGINE_TENSOR = 0, 1, 2
-ENGINES = {"auto": NBMF_ENGINE_AUTO, "simt": NBMF_ENGINE_SIMT, "tensor": NBMF_ENGINE_TENSOR}
+NBMF_ENGINE_AUTO, NBMF_ENGINE_SIMT, NBMF_ENGINE_TENSOR, NBMF_ENGINE_FUSED = 0, 1, 2, 3
+ENGINES = {"auto": NBMF_ENGINE_AUTO, "simt": NBMF_ENGINE_SIMT, "tensor": NBMF_ENGINE_TENSOR, "fused": NBMF_ENGINE_FUSED}
 
 
 class NbmfConfig(C.Structure):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "nbmf_comm_attach": (_INT, [_P, _P, _I32, _I32]),
     "nbmf_comm_destroy": (_INT, [_P]),
     "nbmf_engine": (_INT, [_P]),
+    "nbmf_fit_is_fused": (_INT, [_P]),
     "nbmf_mt19937_uniform": (_INT, [C.c_uint32, C.c_uint64, C.c_uint64, _DBL, _DBL, _P, _P]),
     "nbmf_fma_peak": (_INT, [_INT, _I32, _P, _P, C.POINTER(_DBL)]),
     "nbmf_profile_enable": (_INT, [_P, _INT]),

@@ -12,6 +12,7 @@
 
 #include "../../include/nbmf_b200.h"
 #include "internal.h"
+#include "fused_args.h"
 
 namespace nbmf {
 bool lookup_f32_bits(int strict, int k, PassLaunch* out);
@@ -112,6 +113,11 @@ struct Plan {
   size_t oW, oH, oHt, oCDpart, oCDsum, oLLpart, oLLsum, oPrior, oG, oQ, oRowcount, oHist, oState, oLoss, total;
   size_t oWf, oHf, oPc, oMc, oPM, oColcnt, oFlipcol, oFlipAny;   // tensor engine: formatted factor blocks, re-tiled bit planes, ones per column
   bool strict;
+  // fused small-fit kernel (fused_small.cu): whole iterations in one persistent launch
+  bool fused;
+  int f_rows_per_warp, f_nsuper, f_nwords, f_h_in_smem;
+  int f_wsplit;
+  size_t f_smem, oFCD, oFLL, oBar, oFPrior2;
 };
 
 struct nbmf_ctx {
@@ -128,6 +134,8 @@ struct nbmf_ctx {
   // small problems: kGraphIters MM iterations captured once per fit into a CUDA graph (their ~7 launches per iteration
   // are what bounds many concurrent small fits); 0 = not built, 1 = ready, -1 = capture not possible on this stream
   int graph_state = 0;
+  int fused_max_blocks = -1;        // co-resident CTAs of the fused small-fit kernel on this device (-1: not asked yet)
+  unsigned long long* fused_trace = nullptr;   // development hook (env NBMF_FUSED_TRACE=1): phase time stamps, printed at destroy
   cudaGraphExec_t graph_exec = nullptr;
   long long graph_launches = 0;     // kernel launches per replay (for nbmf_launch_count)
   // batched small fits: this context leads batch_n contexts of identical configuration whose workspaces lie
@@ -194,6 +202,7 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   if (const char* e = getenv("NBMF_ENGINE")) {
     if (!strcmp(e, "simt")) engine = NBMF_ENGINE_SIMT;
     else if (!strcmp(e, "tensor")) engine = NBMF_ENGINE_TENSOR;
+    else if (!strcmp(e, "fused")) engine = NBMF_ENGINE_FUSED;
     else if (!strcmp(e, "auto")) engine = NBMF_ENGINE_AUTO;
   }
   // eps >= 1e-9: the tensor H pass takes one log per product of four x >= eps (no underflow)
@@ -206,7 +215,24 @@ static int make_plan(const nbmf_config& c, Plan* p) {
   int64_t min_m = 512, min_n = 128;
   if (const char* e = getenv("NBMF_TENSOR_MIN_M")) min_m = atoll(e);
   if (const char* e = getenv("NBMF_TENSOR_MIN_N")) min_n = atoll(e);
-  p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR || (engine == NBMF_ENGINE_AUTO && c.m >= min_m && c.n >= min_n));
+  // A single small fit is bound by launch latency on either engine: the fused small-fit kernel (fused_small.cu) takes
+  // it when the work is small enough (measured crossover, tools/fused_sweep.py: entries x padded K of about 1.6e7 in fp64,
+  // 1.2e7 in fp32 where the alternative is the tensor engine at 55-65 us per iteration).  NBMF_FUSED_MAX_WORK: experiment
+  // knob; NBMF_NO_FUSED=1 keeps the launch-per-kernel paths.  fp32 takes one log per product of four x >= eps, fp64 per
+  // eight: eps must keep the product a normal number.  An explicit engine = tensor wins (batches of fits: multifit.py).
+  bool fused_fits = false;
+  {
+    int64_t max_work = c.dtype == NBMF_F32 ? (int64_t)12 << 20 : (int64_t)16 << 20;
+    if (const char* e = getenv("NBMF_FUSED_MAX_WORK")) max_work = atoll(e);
+    const bool no_fused = getenv("NBMF_NO_FUSED") != nullptr && strcmp(getenv("NBMF_NO_FUSED"), "0") != 0;
+    const bool can_fuse = c.vkind == NBMF_V_BITS && c.k <= 32 && c.eps >= (c.dtype == NBMF_F32 ? 1e-9 : 1e-30);
+    if (engine == NBMF_ENGINE_FUSED && !can_fuse)
+      return fail(NBMF_ERR_UNSUPPORTED, "fused engine needs bit-packed V, k <= 32 and eps >= 1e-9 (float32) / 1e-30 (float64)");
+    fused_fits = engine == NBMF_ENGINE_FUSED ||
+                 (engine == NBMF_ENGINE_AUTO && !no_fused && can_fuse && c.m * c.n <= max_work / fused_kp(c.k));
+  }
+  p->tensor = eligible && (engine == NBMF_ENGINE_TENSOR ||
+                           (engine == NBMF_ENGINE_AUTO && !fused_fits && c.m >= min_m && c.n >= min_n));
   p->kb = c.k <= 16 ? 16 : (c.k <= 32 ? 32 : 64);
   if (p->tensor) { p->pl.kp = c.k <= 32 ? 32 : 64; p->pl.h_bn = 128; p->pl.w_bmr = 128; }
   const int occ = 1;
@@ -269,6 +295,34 @@ static int make_plan(const nbmf_config& c, Plan* p) {
     p->oPc = take((size_t)p->ldh * p->mpad / 8);
     if (p->strict) p->oMc = take((size_t)p->ldh * p->mpad / 8);
     p->oPM = take((size_t)p->mpad * p->wpr * 8);
+  }
+  // fused small-fit kernel (decided above): its launch shape and workspace
+  p->fused = false;
+  p->oFCD = p->oFLL = p->oBar = p->oFPrior2 = 0;
+  {
+    if (fused_fits && !p->tensor) {
+      // a CTA unit of the H phase = 8 warps x R rows x one 32-column word; about one unit per SM, 4 <= R <= 16
+      const int nwords = (int)((c.n + 31) / 32);
+      const int64_t target = std::max<int64_t>(1, 148 / nwords);
+      const int64_t rows_per_unit = (c.m + target - 1) / target;
+      const int R = (int)std::min<int64_t>(16, std::max<int64_t>(4, (rows_per_unit + 7) / 8));
+      p->f_rows_per_warp = R;
+      p->f_nsuper = (int)((c.m + 8 * R - 1) / (8 * R));
+      p->f_nwords = nwords;
+      p->f_h_in_smem = (size_t)c.k * nwords * 32 * p->sz <= (size_t)160 * 1024 ? 1 : 0;
+      p->f_smem = fused_smem_bytes(c.dtype, c.k, R, nwords, p->f_h_in_smem);
+      p->fused = p->f_smem <= (size_t)200 * 1024;
+      if (p->fused) {
+        p->oFCD = take((size_t)p->f_nsuper * 2 * kp * nwords * 32 * p->sz);
+        p->oFLL = take((size_t)nwords * p->f_nsuper * 8);
+        p->oBar = take(64);
+        p->oFPrior2 = take((size_t)p->n_prior * 16);
+        // W phase: warps that share a row, so that a problem with few rows still uses every warp of the (nominal) grid
+        int ws = 1;
+        while (ws < 8 && (int64_t)ws * 2 * c.m <= 148 * 8 && ws * 2 <= nwords) ws *= 2;
+        p->f_wsplit = ws;
+      }
+    }
   }
   p->total = o;
   return NBMF_OK;
@@ -429,6 +483,27 @@ static void graph_drop(nbmf_ctx* c) {
 extern "C" int nbmf_destroy(nbmf_ctx* c) {
   if (!c) return NBMF_OK;
   cudaStreamSynchronize(c->st);     // the caller frees the workspace next (not a device-wide sync: other streams may be capturing)
+  if (c->fused_trace) {             // mean nanoseconds per phase of CTA 0 over the traced iterations
+    std::vector<unsigned long long> t(4096 * 16);
+    if (cudaMemcpy(t.data(), c->fused_trace, t.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      double sum[8] = {0}, sub[6] = {0}; int cnt = 0;
+      for (int it = 1; it < 4096; ++it) {
+        const unsigned long long* r = &t[(size_t)it * 16];
+        if (!r[0] || !r[7]) continue;
+        for (int s = 1; s < 8; ++s) sum[s] += (double)(r[s] - r[s - 1]);
+        sub[0] += (double)(r[8] - r[0]); sub[1] += (double)(r[9] - r[8]); sub[2] += (double)(r[10] - r[9]);
+        sub[3] += (double)(r[11] - r[5]); sub[4] += (double)(r[12] - r[11]); sub[5] += (double)(r[13] - r[12]);
+        ++cnt;
+      }
+      if (cnt) {
+        fprintf(stderr, "[nbmf fused trace] %d iterations, ns: H phase %.0f | barrier %.0f | finalize %.0f | H epilogue %.0f | barrier %.0f | W phase %.0f | barrier %.0f\n",
+                cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt, sum[6] / cnt, sum[7] / cnt);
+        fprintf(stderr, "[nbmf fused trace]   H phase: stage %.0f, rows %.0f, reduce+store %.0f; W phase: stage %.0f, words %.0f, warp sums %.0f\n",
+                sub[0] / cnt, sub[1] / cnt, sub[2] / cnt, sub[3] / cnt, sub[4] / cnt, sub[5] / cnt);
+      }
+    }
+    cudaFree(c->fused_trace);
+  }
   graph_drop(c);
   if (c->comm && c->owns_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   prof_clear(c->prof_h);
@@ -838,9 +913,65 @@ static int graph_build(nbmf_ctx* c) {
   return rc;
 }
 
+// Small fits: whole iterations inside one persistent cooperative launch (fused_small.cu) instead of ~6 launches each.
+// A batch of fits (nbmf_batch_bind) shares the launch, a few CTAs per fit; batches larger than the co-resident grid run in
+// slices.  The results do not depend on the grid (see the kernel), so batched and single fits stay bit-identical.
+static bool fused_ok(const nbmf_ctx* c) { return c->p.fused && c->world == 1 && !c->profile; }
+
+static int enqueue_fused(nbmf_ctx* c, int n_passes) {
+  const Plan& p = c->p;
+  int rc = eager_rowcount(c);
+  if (rc) return rc;
+  FusedArgs a;
+  a.W = c->W(); a.H = c->H(); a.Ht = c->Ht(); a.P = c->P; a.M = c->M;
+  a.m = c->cfg.m; a.n = c->cfg.n; a.ldh = p.ldh; a.wpr = p.wpr;
+  a.k = c->cfg.k; a.kp = p.pl.kp; a.strict = p.strict ? 1 : 0; a.projection = c->cfg.projection;
+  a.rows_per_warp = p.f_rows_per_warp; a.nsuper = p.f_nsuper; a.nwords = p.f_nwords;
+  a.CDpart = c->ws + p.oFCD; a.LLpart = c->at<double>(p.oFLL);
+  a.prior_part = c->at<double>(p.oPrior); a.prior_part2 = c->at<double>(p.oFPrior2); a.n_prior = p.n_prior;
+  a.wsplit = p.f_wsplit;
+  a.state = c->state(); a.history = c->at<double>(p.oHist);
+  a.rowcount = (c->cfg.projection == NBMF_PROJ_DUCHI && c->M) ? (const void*)(c->ws + p.oRowcount) : nullptr;
+  a.eps = c->cfg.eps; a.n_obs = c->cfg.n_obs; a.tol = c->tol; a.max_iter = c->max_iter;
+  a.bar = c->at<unsigned>(p.oBar); a.n_passes = n_passes; a.h_in_smem = p.f_h_in_smem;
+  a.batch_stride = c->batch_n > 1 ? c->batch_stride : 0;
+  if (!c->fused_trace && getenv("NBMF_FUSED_TRACE")) {
+    if (cudaMalloc((void**)&c->fused_trace, 4096 * 16 * 8) == cudaSuccess) cudaMemsetAsync(c->fused_trace, 0, 4096 * 16 * 8, c->st);
+    else c->fused_trace = nullptr;
+  }
+  a.trace = c->fused_trace;
+  if (c->fused_max_blocks < 0) c->fused_max_blocks = fused_max_blocks(c->cfg.dtype, a, p.f_smem);
+  if (c->fused_max_blocks < 1) return fail(NBMF_ERR_CUDA, "fused small-fit kernel: no co-resident grid on this device");
+  const int want = std::max(std::max(p.f_nwords * p.f_nsuper, (int)((c->cfg.m + 7) / 8)), p.n_prior);
+  for (int f0 = 0; f0 < c->batch_n; f0 += c->fused_max_blocks) {
+    const int nf = std::min(c->batch_n - f0, c->fused_max_blocks);
+    const int grid_x = std::max(1, std::min(want, c->fused_max_blocks / nf));
+    FusedArgs b = a;
+    const size_t sh = (size_t)f0 * (size_t)a.batch_stride;
+    b.W = (unsigned char*)a.W + sh; b.H = (unsigned char*)a.H + sh; b.Ht = (unsigned char*)a.Ht + sh;
+    b.CDpart = (unsigned char*)a.CDpart + sh; b.LLpart = (double*)((unsigned char*)a.LLpart + sh);
+    b.prior_part = (double*)((unsigned char*)a.prior_part + sh); b.prior_part2 = (double*)((unsigned char*)a.prior_part2 + sh);
+    b.state = (FitState*)((unsigned char*)a.state + sh);
+    b.history = (double*)((unsigned char*)a.history + sh); b.bar = (unsigned*)((unsigned char*)a.bar + sh);
+    CUDA_TRY(cudaMemset2DAsync(b.bar, nf > 1 ? (size_t)a.batch_stride : 64, 0, 4, (size_t)nf, c->st));
+    const int e = launch_fused_fit(c->cfg.dtype, b, grid_x, nf, p.f_smem, c->st);
+    if (e) return cuda_fail((cudaError_t)e, "cudaLaunchCooperativeKernel(fused_fit_kernel)");
+    g_launches += 1;
+  }
+  return NBMF_OK;
+}
+
 extern "C" int nbmf_fit_enqueue(nbmf_ctx* c, int32_t n_iters) {
   if (!c || c->max_iter < 1) return fail(NBMF_ERR_ARG, "nbmf_fit_begin was not called");
   int rc;
+  if (fused_ok(c)) {
+    const int iters = std::max(0, std::min((int)n_iters, c->max_iter - c->enqueued));
+    const bool tail = c->enqueued + iters >= c->max_iter && !c->tail_enqueued;   // + the loss-only pass after the last iteration
+    if (iters + (tail ? 1 : 0) > 0 && (rc = enqueue_fused(c, iters + (tail ? 1 : 0)))) return rc;
+    c->enqueued += iters;
+    if (tail) c->tail_enqueued = true;
+    return NBMF_OK;
+  }
   for (int i = 0; i < n_iters && c->enqueued < c->max_iter;) {
     // the first iteration always runs uncaptured (lazy one-time setup: kernel attributes, row counts)
     if (graph_eligible(c) && c->enqueued >= 1 && n_iters - i >= kGraphIters && c->max_iter - c->enqueued >= kGraphIters) {
@@ -1026,7 +1157,10 @@ extern "C" int nbmf_comm_destroy(void* comm) {
   return NBMF_OK;
 }
 extern "C" int nbmf_comm_world(nbmf_ctx* c) { return c ? c->world : 0; }
-extern "C" int nbmf_engine(nbmf_ctx* c) { return !c ? 0 : (c->p.tensor ? NBMF_ENGINE_TENSOR : NBMF_ENGINE_SIMT); }
+extern "C" int nbmf_engine(nbmf_ctx* c) {
+  return !c ? 0 : (c->p.tensor ? NBMF_ENGINE_TENSOR : (c->p.fused ? NBMF_ENGINE_FUSED : NBMF_ENGINE_SIMT));
+}
+extern "C" int nbmf_fit_is_fused(nbmf_ctx* c) { return c && fused_ok(c) ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------ measurement
 static void prof_clear(std::vector<cudaEvent_t>& v) {

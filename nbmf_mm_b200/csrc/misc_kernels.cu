@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "epilogue.cuh"
 
 namespace nbmf {
 
@@ -93,25 +94,7 @@ __device__ __forceinline__ void finalize_body(const FinalizeArgs& f, double ll) 
     pb += __shfl_xor_sync(0xffffffffu, pb, o);
   }
   if (threadIdx.x != 0) return;
-  const int it = state->it;
-  int done = 0;
-  if (it >= 1) {
-    // alpha, beta from the fit's own state (== f.alpha, f.beta for a single fit; per fit in a batch)
-    const double loss = -(ll + (state->alpha - 1.0) * pa + (state->beta - 1.0) * pb) / f.n_obs;
-    f.history[it - 1] = loss;
-    state->n_hist = it;
-    if (it >= 2) {
-      const double prev = state->prev_loss;
-      const double rel = fabs(prev - loss) / fabs(prev);
-      if (rel < f.tol) { done = 1; state->converged = 1; }
-    }
-    state->prev_loss = loss;
-    if (it >= f.max_iter) done = 1;
-  }
-  state->prior_a = pa;
-  state->prior_b = pb;
-  if (done) state->done = 1;
-  else state->it = it + 1;
+  finalize_core(*state, ll, pa, pb, f.n_obs, f.tol, f.max_iter, f.history);
 }
 
 template <typename Real>
@@ -200,12 +183,7 @@ __global__ void h_epilogue_kernel(const Real* __restrict__ CD, int64_t n, int k,
     const int64_t o = (int64_t)kk * ldh + j;
     Real hn = H[o];
     if (UPDATE) {
-      const Real eps = (Real)eps_d;
-      const Real h = hn;
-      const Real num = h * CD[o] + (Real)(alpha - 1.0);
-      const Real den = (Real(1) - h) * CD[(int64_t)kp * ldh + o] + (Real)(beta - 1.0);
-      hn = num / (num + den + eps);
-      hn = fmin(fmax(hn, eps), Real(1) - eps);
+      hn = h_update_elem<Real>(hn, CD[o], CD[(int64_t)kp * ldh + o], alpha, beta, eps_d);
       H[o] = hn;
       Ht[j * kp + kk] = hn;
     }
@@ -250,22 +228,6 @@ void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64
 // two 64-element local arrays and stride-K global access: on small problems (config 5) it cost as much as the H pass.
 // Duchi: descending bitonic sort of the row across the warp's registers, inclusive prefix sums in sorted order, rho =
 // last index whose value exceeds the running threshold (Duchi et al. 2008), then w = max(v - theta, 0).
-template <typename Real>
-__device__ __forceinline__ Real warp_sum(Real v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-template <typename Real>
-__device__ __forceinline__ Real warp_scan_incl(Real v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const Real t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
-
 template <typename Real, int EPL>
 __global__ void __launch_bounds__(256) w_epilogue_kernel(const Real* __restrict__ Gpart, const Real* __restrict__ Qpart, int nsplit,
                                                          int64_t m, int64_t n, int k, int kp, int projection,
@@ -295,72 +257,7 @@ __global__ void __launch_bounds__(256) w_epilogue_kernel(const Real* __restrict_
     }
     part += v[e];
   }
-  if (projection == 0) {
-    const Real sum = warp_sum(part);
-#pragma unroll
-    for (int e = 0; e < EPL; ++e)
-      if (lane + 32 * e < k) W[row * kp + lane + 32 * e] = v[e] / sum;
-    return;
-  }
-  // ---- Duchi: bitonic sort (descending) of the 32 * EPL values held one (two) per lane; padding sorts last
-  const Real NEG = -INFINITY;
-  Real u[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) u[e] = (lane + 32 * e < k) ? v[e] : NEG;
-  constexpr int NEL = 32 * EPL;
-#pragma unroll
-  for (int size = 2; size <= NEL; size <<= 1) {
-#pragma unroll
-    for (int j = size >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {                               // partner is this lane's other register (EPL == 2, j == 32)
-        if constexpr (EPL == 2) {
-          // element indices lane and lane + 32; direction of the merge: descending when (index & size) == 0
-          const bool desc = ((lane & size) == 0);   // size == 64 here: always descending
-          const Real lo = fmin(u[0], u[1]), hi = fmax(u[0], u[1]);
-          u[0] = desc ? hi : lo;
-          u[1] = desc ? lo : hi;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          const int idx = lane + 32 * e;
-          const Real other = __shfl_xor_sync(0xffffffffu, u[e], j);
-          const bool desc = ((idx & size) == 0);
-          const bool lower = ((lane & j) == 0);     // this element is the lower index of the pair
-          const Real mx = fmax(u[e], other), mn = fmin(u[e], other);
-          u[e] = (lower == desc) ? mx : mn;
-        }
-      }
-    }
-  }
-  // inclusive prefix sums in sorted order (element index = lane + 32 e), padding contributes nothing
-  Real css[EPL];
-  Real carry = Real(0);
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) {
-    const Real x = (u[e] == NEG) ? Real(0) : u[e];
-    css[e] = warp_scan_incl(x, lane) + carry;
-    carry = __shfl_sync(0xffffffffu, css[e], 31);
-  }
-  // theta = (css_rho - 1) / (rho + 1) for the LAST index rho with u_rho - (css_rho - 1) / (rho + 1) > 0
-  int best = -1;
-  Real theta = Real(0);
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) {
-    const int idx = lane + 32 * e;
-    const Real t = (css[e] - Real(1)) / (Real)(idx + 1);
-    const bool ok = (u[e] != NEG) && (u[e] - t > Real(0));
-    if (ok && idx > best) { best = idx; theta = t; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const Real ot = __shfl_xor_sync(0xffffffffu, theta, o);
-    if (ob > best) { best = ob; theta = ot; }
-  }
-#pragma unroll
-  for (int e = 0; e < EPL; ++e)
-    if (lane + 32 * e < k) W[row * kp + lane + 32 * e] = fmax(v[e] - theta, Real(0));
+  w_row_project<Real, EPL>(v, part, k, lane, projection, W + row * kp);
 }
 
 void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nsplit, int64_t m, int64_t n,

@@ -267,7 +267,12 @@ class DeviceProblem:
                                             C.byref(self._ctx)), "nbmf_create")
         self._keep = []          # tensors the context borrows
         self.world = 1
-        self.engine = "tensor" if self.lib.nbmf_engine(self._ctx) == _lib.NBMF_ENGINE_TENSOR else "simt"
+        self.engine = {_lib.NBMF_ENGINE_TENSOR: "tensor", _lib.NBMF_ENGINE_FUSED: "fused"}.get(self.lib.nbmf_engine(self._ctx), "simt")
+
+    @property
+    def fit_is_fused(self) -> bool:
+        """The fit loop of this problem runs inside the persistent small-fit kernel (``nbmf_fit_is_fused``)."""
+        return bool(self.lib.nbmf_fit_is_fused(self._ctx))
 
     # -- lifetime
     def close(self):

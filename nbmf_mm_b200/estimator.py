@@ -82,8 +82,10 @@ class NBMFMM(BaseEstimator, TransformerMixin):
         broadcast, so every rank ends with the same fitted estimator.
     dense_storage : {None, "float16"}: device layout of probabilistic X (values strictly inside (0,1)); None = the
         compute dtype, "float16" halves the bytes each pass reads (float32 arithmetic only).
-    engine : {"auto", "simt", "tensor"}: CUDA-core (packed FFMA2) kernels or the tcgen05/TMEM split-precision (TF32 + bf16)
-        kernels (float32, binary X, K <= 64); "auto" picks tensor when eligible and m, n >= 512.
+    engine : {"auto", "simt", "tensor", "fused"}: CUDA-core (packed FFMA2) kernels, the tcgen05/TMEM split-precision (TF32 +
+        bf16) kernels (float32, binary X, K <= 64), or the persistent small-fit kernel (binary X, K <= 32: whole iterations in
+        one launch).  "auto": a single small fit -> fused; else tensor when eligible and m >= 512, n >= 128; else simt.
+        Restarts (``n_init`` > 1) advance as one batch on tensor / simt; pin an engine to get bit-identical single fits.
     """
 
     def __init__(self, n_components=10, alpha=1.2, beta=1.2, max_iter=2000, tol=1e-5,

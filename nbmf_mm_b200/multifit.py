@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 from .device import require_cuda
-from .solver import _CANON, make_problem, prepare_data
+from .solver import _CANON, make_problem, prepare_data, resolve_engine
 
 
 def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
@@ -138,6 +138,10 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
         the order of ``idxs``."""
         k, _, _, mi, tl = prepared[idxs[0]][:5]
         B = len(idxs)
+        # engine="auto" gives a SINGLE small fit to the persistent small-fit kernel (latency: the GPU is otherwise idle); a
+        # batch fills the GPU, and there the tensor engine wins by 3-5x wherever it is eligible (one launch per kernel for
+        # all fits).  Results then differ from a solver call with engine="auto" by fp32 rounding; pass an engine for bits.
+        beng = resolve_engine(engine, dtype=dtype, vkind=data.vkind, k=k, eps=eps, m_total=m, n=n)
         big = {}
 
         def slice_of(b):
@@ -180,7 +184,7 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                 for b, idx in enumerate(idxs):
                     prob = make_problem(data, k, dtype=dtype, alpha=prepared[idx][1], beta=prepared[idx][2], eps=eps,
                                         mask_semantics=mask_semantics, projection=projection_method, max_iter_cap=mi,
-                                        device=device, engine=engine, workspace=slice_of(b),
+                                        device=device, engine=beng, workspace=slice_of(b),
                                         batch_hint=B if batch_plan == "batch" else 0)
                     probs.append(prob)
                     prob.set_factors(W0s[b], H0s[b], normalize_w=True)

@@ -203,7 +203,8 @@ TENSOR_MAX_K = 64            # largest n_components the tcgen05 engine covers (c
 def resolve_engine(engine, *, dtype, vkind, k, eps, m_total, n):
     """The engine every rank of a row-sharded fit must use, decided from GLOBAL quantities (``m_total``, not the
     local shard): ranks that disagreed would all-reduce differently shaped [C | D] buffers (the tensor engine pads K to
-    its own tile).  Same rule as ``make_plan`` in capi.cu applies to a single GPU."""
+    its own tile).  Also the engine of a BATCH of fits (multifit.py).  ``make_plan`` in capi.cu applies the same rule to a
+    single fit on one GPU, after first giving small problems to the persistent small-fit kernel ("fused")."""
     if engine != "auto":
         return engine
     eligible = np.dtype(dtype) == np.float32 and vkind == "bits" and k <= TENSOR_MAX_K and eps >= 1e-9
@@ -285,8 +286,9 @@ def nbmf_mm_solver(Y, n_components, max_iter=500, tol=1e-5, alpha=1.2, beta=1.2,
     every rank passes the FULL ``Y`` and gets the full result), ``shard=(row0, m_total)`` (with
     ``distributed``: ``Y``/``mask`` are already this rank's row block of an ``m_total``-row
     problem in internal orientation; the returned W is the local block, H is global),
-    ``engine`` ("auto" | "simt" | "tensor": packed-FFMA2 CUDA-core kernels or the tcgen05/TMEM
-    split-precision kernels; the tensor engine needs float32, binary V, K <= 64), ``dense_storage`` ("float16":
+    ``engine`` ("auto" | "simt" | "tensor" | "fused": packed-FFMA2 CUDA-core kernels, the tcgen05/TMEM
+    split-precision kernels (float32, binary V, K <= 64) or the persistent small-fit kernel (binary V, K <= 32, one GPU:
+    whole iterations inside one launch; what "auto" gives a small problem), ``dense_storage`` ("float16":
     probabilistic V is stored as fp16 on the device, float32 arithmetic; default = the compute dtype),
     ``check_range`` (raise the estimator's ``ValueError("X must be binary")``, ``_base.py:90-91``, when a dense ``Y``
     holds a value outside [0, 1]: the test runs on the device, in the pass that packs ``Y``).

@@ -111,15 +111,23 @@ def test_stop_rule_and_determinism_on_tensor_engine():
 
 
 def test_auto_engine_selection_and_ineligible_requests():
-    Y, mask, W, H = problem(600, 700, 8, seed=1)
+    Y, mask, W, H = problem(1800, 1500, 8, seed=1)
     data = prepare_data(Y, mask, transpose=False, dtype="float32", device=None)
     kw = dict(alpha=1.2, beta=1.2, eps=1e-8, projection="normalize", max_iter_cap=1, device=None)
     with make_problem(data, 8, dtype="float32", mask_semantics="reference", **kw) as p:
-        assert p.engine == "tensor"
+        assert p.engine == "tensor" and not p.fit_is_fused
     with make_problem(data, 8, dtype="float32", mask_semantics="strict", **kw) as p:
         assert p.engine == "tensor"                                  # strict H pass variant reads the mask plane too
     with make_problem(data, 40, dtype="float32", mask_semantics="reference", **kw) as p:
         assert p.engine == "tensor"                                  # K <= 64: the 3-pipeline instantiation
+    Y, mask = Y[:600, :700].copy(), mask[:600, :700].copy()
+    data = prepare_data(Y, mask, transpose=False, dtype="float32", device=None)
+    with make_problem(data, 8, dtype="float32", mask_semantics="reference", **kw) as p:
+        assert p.engine == "simt" and p.fit_is_fused                 # a single small fit: the persistent small-fit kernel
+    with make_problem(data, 8, dtype="float32", mask_semantics="reference", engine="tensor", **kw) as p:
+        assert p.engine == "tensor" and not p.fit_is_fused           # ... unless asked (batches of fits: multifit.py)
+    with make_problem(data, 40, dtype="float32", mask_semantics="reference", **kw) as p:
+        assert p.engine == "tensor"                                  # K > 32: not covered by the small-fit kernel
     d64 = prepare_data(Y, mask, transpose=False, dtype="float64", device=None)
     with make_problem(d64, 8, dtype="float64", mask_semantics="reference", **kw) as p:
         assert p.engine == "simt"
