@@ -123,16 +123,24 @@ def test_auto_engine_selection_and_ineligible_requests():
     Y, mask = Y[:600, :700].copy(), mask[:600, :700].copy()
     data = prepare_data(Y, mask, transpose=False, dtype="float32", device=None)
     with make_problem(data, 8, dtype="float32", mask_semantics="reference", **kw) as p:
-        assert p.engine == "simt" and p.fit_is_fused                 # a single small fit: the persistent small-fit kernel
+        assert p.engine == "fused" and p.fit_is_fused                # a single small fit: the persistent small-fit kernel
     with make_problem(data, 8, dtype="float32", mask_semantics="reference", engine="tensor", **kw) as p:
         assert p.engine == "tensor" and not p.fit_is_fused           # ... unless asked (batches of fits: multifit.py)
     with make_problem(data, 40, dtype="float32", mask_semantics="reference", **kw) as p:
         assert p.engine == "tensor"                                  # K > 32: not covered by the small-fit kernel
     d64 = prepare_data(Y, mask, transpose=False, dtype="float64", device=None)
     with make_problem(d64, 8, dtype="float64", mask_semantics="reference", **kw) as p:
-        assert p.engine == "simt"
+        assert p.engine == "fused"
+    with make_problem(d64, 8, dtype="float64", mask_semantics="reference", engine="simt", **kw) as p:
+        assert p.engine == "simt" and not p.fit_is_fused
+    with make_problem(d64, 40, dtype="float64", mask_semantics="reference", **kw) as p:
+        assert p.engine == "simt"                                    # fp64, K > 32: the pass kernels
     with pytest.raises(RuntimeError, match="tensor engine"):
         make_problem(d64, 8, dtype="float64", mask_semantics="reference", engine="tensor", **kw)
+    with pytest.raises(RuntimeError, match="fused engine"):
+        make_problem(d64, 40, dtype="float64", mask_semantics="reference", engine="fused", **kw)
     small = prepare_data(Y[:100, :100], None, transpose=False, dtype="float32", device=None)
     with make_problem(small, 8, dtype="float32", mask_semantics="reference", **kw) as p:
+        assert p.engine == "fused"
+    with make_problem(small, 8, dtype="float32", mask_semantics="reference", engine="simt", **kw) as p:
         assert p.engine == "simt"
