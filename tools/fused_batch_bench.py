@@ -14,12 +14,10 @@ for (m, n, dtype) in [(1226, 285, "float64"), (253, 902, "float64"), (100, 500, 
             jobs = [dict(n_components=k, random_state=r) for r in range(B)]
             line = f"{m}x{n} {dtype} K={k:2d} batch of {B:2d}:"
             for fused in (True, False):
-                if fused: os.environ.pop("NBMF_NO_FUSED", None)
-                else: os.environ["NBMF_NO_FUSED"] = "1"
                 best = None
                 for rep in range(3):
                     torch.cuda.synchronize(); t0 = time.perf_counter()
-                    res = nbmf_mm_multifit(X, jobs, max_iter=200, tol=0.0, dtype=dtype)
+                    res = nbmf_mm_multifit(X, jobs, max_iter=200, tol=0.0, dtype=dtype, engine="fused" if fused else "simt")
                     torch.cuda.synchronize(); dt = time.perf_counter() - t0
                     if rep: best = dt if best is None else min(best, dt)
                 line += f"  {'fused' if fused else 'regular'} {best * 1e3:7.1f} ms"

@@ -9,9 +9,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
 from nbmf_mm_b200 import nbmf_mm_solver
 
-def per_iter(X, k, dtype, engine, fused):
-    if fused: os.environ.pop("NBMF_NO_FUSED", None)
-    else: os.environ["NBMF_NO_FUSED"] = "1"
+def per_iter(X, k, dtype, engine):
     ts = {}
     for iters in (60, 260):
         best = None
@@ -23,16 +21,15 @@ def per_iter(X, k, dtype, engine, fused):
         ts[iters] = best
     return (ts[260] - ts[60]) / 200 * 1e6
 
-os.environ["NBMF_FUSED_MAX_WORK"] = str(1 << 32)
 shapes = [(50, 85), (100, 500), (253, 902), (1226, 285), (600, 600), (1000, 1000), (1500, 1500), (2000, 2000), (3000, 3000), (4000, 1000)]
 for dtype in ("float64", "float32"):
     for k in (6, 16, 32):
         for (m, n) in shapes:
             X = (np.random.default_rng(0).random((m, n)) < 0.1).astype(np.float64)
-            f = per_iter(X, k, dtype, "simt", True)
-            r = per_iter(X, k, dtype, "simt", False)
+            f = per_iter(X, k, dtype, "fused")
+            r = per_iter(X, k, dtype, "simt")
             line = f"{dtype} K={k:2d} {m}x{n} ({m*n/1e6:.2f}M entries): fused {f:7.1f} us/it, regular simt {r:7.1f} us/it"
             if dtype == "float32" and m >= 512 and n >= 128:
-                t = per_iter(X, k, dtype, "tensor", False)
+                t = per_iter(X, k, dtype, "tensor")
                 line += f", tensor {t:7.1f} us/it"
             print(line, flush=True)
