@@ -192,6 +192,10 @@ int nbmf_fit_poll(nbmf_ctx* ctx, int wait, int32_t* done_host, int32_t* n_iter_h
  * context as usual.  SIMT engine, single GPU. */
 int nbmf_batch_bind(nbmf_ctx* leader, int32_t n, int64_t stride_bytes);
 int nbmf_batch_poll(nbmf_ctx* leader, int32_t* all_done_host, int32_t* n_iter_host);
+/* the tail of the solver (_solver.py:178-213) for every fit of the batch with one synchronisation: loss histories
+ * (hist_stride doubles per fit), converged flags and max |row sum of W - 1| (NaN if a row sum is not finite) */
+int nbmf_batch_tail(nbmf_ctx* leader, double* history_host, int32_t hist_stride, int32_t* converged_host,
+                    double* deviation_host);
 int nbmf_fit_history(nbmf_ctx* ctx, double* history_host, int32_t count, int32_t* converged_host);
 
 /* ---- transform (replaces the 50 fixed-H W steps of NBMFMM.transform, _base.py:178-198) ----

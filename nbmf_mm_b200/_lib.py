@@ -70,6 +70,7 @@ SIGNATURES = {
     "nbmf_fit_begin": (_INT, [_P, _I32, _DBL]),
     "nbmf_batch_bind": (_INT, [_P, _I32, _I64]),
     "nbmf_batch_poll": (_INT, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
+    "nbmf_batch_tail": (_INT, [_P, C.POINTER(_DBL), _I32, C.POINTER(_I32), C.POINTER(_DBL)]),
     "nbmf_fit_enqueue": (_INT, [_P, _I32]),
     "nbmf_fit_poll": (_INT, [_P, _INT, C.POINTER(_I32), C.POINTER(_I32)]),
     "nbmf_fit_history": (_INT, [_P, C.POINTER(_DBL), _I32, C.POINTER(_I32)]),

@@ -1037,6 +1037,38 @@ extern "C" int nbmf_batch_bind(nbmf_ctx* c, int32_t n, int64_t stride_bytes) {
   graph_drop(c);
   return NBMF_OK;
 }
+// Tail of every fit of the leader's batch with ONE synchronisation (per-fit nbmf_fit_history + nbmf_simplex_deviation cost
+// two each: 7 ms for 64 fits): history_host[i * hist_stride ..] = the losses of fit i (hist_stride <= max_iter_cap + 2
+// entries are copied per fit; the caller knows n_iter from nbmf_batch_poll), converged_host[i], deviation_host[i] =
+// max |row sum of W - 1| of fit i (NaN if a row sum is not finite: the test of _solver.py:195-199).
+extern "C" int nbmf_batch_tail(nbmf_ctx* c, double* history_host, int32_t hist_stride, int32_t* converged_host,
+                               double* deviation_host) {
+  if (!c || !history_host || !converged_host || !deviation_host || hist_stride < 1)
+    return fail(NBMF_ERR_ARG, "nbmf_batch_tail: bad arguments");
+  const int n = c->batch_n;
+  const size_t pitch = n > 1 ? (size_t)c->batch_stride : c->p.total;
+  const int count = std::min<int>(hist_stride, std::max(c->cfg.max_iter_cap, 1) + 2);
+  for (int i = 0; i < n; ++i) {                        // deviation of fit i into its own scratch (64 bytes at oLoss)
+    unsigned char* wsi = c->ws + (size_t)i * pitch;
+    launch_simplex_deviation(c->cfg.dtype, wsi + c->p.oW, c->cfg.m, c->cfg.k, c->p.pl.kp,
+                             reinterpret_cast<unsigned long long*>(wsi + c->p.oLoss), c->st);
+    CHECK_LAUNCH(1);
+  }
+  std::vector<FitState> st((size_t)n);
+  std::vector<unsigned long long> dv((size_t)n * 2);
+  CUDA_TRY(cudaMemcpy2DAsync(history_host, (size_t)hist_stride * 8, c->at<double>(c->p.oHist), pitch, (size_t)count * 8, (size_t)n,
+                             cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaMemcpy2DAsync(st.data(), sizeof(FitState), c->state(), pitch, sizeof(FitState), (size_t)n, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaMemcpy2DAsync(dv.data(), 16, c->ws + c->p.oLoss, pitch, 16, (size_t)n, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  for (int i = 0; i < n; ++i) {
+    converged_host[i] = st[(size_t)i].converged;
+    double d;
+    memcpy(&d, &dv[(size_t)2 * i], 8);
+    deviation_host[i] = dv[(size_t)2 * i + 1] ? NAN : d;
+  }
+  return NBMF_OK;
+}
 // states of all fits of the leader's batch: *all_done = every fit has stopped, n_iter_host[i] = losses recorded by fit i
 extern "C" int nbmf_batch_poll(nbmf_ctx* c, int32_t* all_done, int32_t* n_iter_host) {
   if (!c || !all_done) return fail(NBMF_ERR_ARG, "nbmf_batch_poll: null argument");

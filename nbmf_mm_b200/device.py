@@ -89,11 +89,15 @@ def _packable(a):
     return a.astype(np.float64)
 
 
-def pack_host_dense_checked(X, mask, device, chunk_bytes=256 << 20):
+def pack_host_dense_checked(X, mask, device, chunk_bytes=16 << 20, n_threads=None, pinned_from=64 << 20):
     """Dense HOST X (m x n) [+ dense host mask] -> device bit planes (P = X != 0 & mask, M = mask != 0) and the value
     flags of ``nbmf_pack_bits_checked``, without a NumPy pass over the data: row chunks are uploaded as they are
     (fp64 / fp32 / u8) and checked + packed on the device.  At 20 000 x 5 000 the host front end it replaces (range
-    test, binary test, mask test, ``np.packbits``) costs 3.4 s; this costs the PCIe time of the raw arrays."""
+    test, binary test, mask test, ``np.packbits``) costs 3.4 s; this costs the PCIe time of the raw arrays.
+
+    Large inputs go through page-locked staging: a few threads copy chunk i + 1 into a pinned buffer (NumPy copies release
+    the GIL) while chunk i crosses PCIe by DMA and is packed; a plain ``.to(device)`` of pageable memory is a synchronous
+    copy through the driver's own staging at a third of the rate (1.6 GB of fp64 X + mask: 0.24 s -> see DESIGN 6b)."""
     torch = _torch()
     lib = _lib.load()
     dev = require_cuda(device)
@@ -104,16 +108,53 @@ def pack_host_dense_checked(X, mask, device, chunk_bytes=256 << 20):
     P = torch.empty((m, wpr), dtype=torch.int32, device=dev)
     M = None if mask is None else torch.empty((m, wpr), dtype=torch.int32, device=dev)
     flags = torch.zeros(1, dtype=torch.int32, device=dev)
-    rows = max(1, int(chunk_bytes) // max(1, n * X.dtype.itemsize))
-    with torch.cuda.device(dev):
-        for r0 in range(0, m, rows):
-            r1 = min(m, r0 + rows)
-            Xc = torch.from_numpy(np.ascontiguousarray(X[r0:r1])).to(dev)
-            Mc = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask[r0:r1])).to(dev)
-            _lib.check(lib.nbmf_pack_bits_checked(_ptr(Xc), _elem_code(Xc), n, _ptr(Mc), _elem_code(Mc) if Mc is not None else 0,
-                                                  n, r1 - r0, n, _ptr(P[r0:r1]), _ptr(None if M is None else M[r0:r1]),
-                                                  _ptr(flags), _stream(dev)), "nbmf_pack_bits_checked")
     h2d = X.nbytes + (0 if mask is None else mask.nbytes)
+
+    def pack(Xc, Mc, r0, r1):
+        _lib.check(lib.nbmf_pack_bits_checked(_ptr(Xc), _elem_code(Xc), n, _ptr(Mc), _elem_code(Mc) if Mc is not None else 0,
+                                              n, r1 - r0, n, _ptr(P[r0:r1]), _ptr(None if M is None else M[r0:r1]),
+                                              _ptr(flags), _stream(dev)), "nbmf_pack_bits_checked")
+
+    rows = max(1, int(chunk_bytes) // max(1, n * max(X.dtype.itemsize, 1 if mask is None else mask.dtype.itemsize)))
+    with torch.cuda.device(dev):
+        if h2d < pinned_from or m <= rows:                     # small: not worth page-locking anything
+            for r0 in range(0, m, rows):
+                r1 = min(m, r0 + rows)
+                Xc = torch.from_numpy(np.ascontiguousarray(X[r0:r1])).to(dev)
+                Mc = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask[r0:r1])).to(dev)
+                pack(Xc, Mc, r0, r1)
+            return BitMatrix(P, (m, n)), (None if M is None else BitMatrix(M, (m, n))), int(flags.item()), h2d
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        nt = n_threads or max(1, min(8, (os.cpu_count() or 2) // 2))
+        srcs = [X] + ([] if mask is None else [mask])
+        tdt = [getattr(torch, a.dtype.name) for a in srcs]
+        stage = [[torch.empty((rows, n), dtype=t, pin_memory=True) for t in tdt] for _ in range(2)]
+        stage_np = [[t.numpy() for t in pair] for pair in stage]
+        devbuf = [[torch.empty((rows, n), dtype=t, device=dev) for t in tdt] for _ in range(2)]
+        done = [None, None]                                     # DMA out of staging pair b has finished
+
+        def fill(b, r0, r1):
+            step = -(-(r1 - r0) // nt)
+            jobs = []
+            for si, a in enumerate(srcs):
+                for q0 in range(r0, r1, step):
+                    q1 = min(r1, q0 + step)
+                    jobs.append(pool.submit(np.copyto, stage_np[b][si][q0 - r0:q1 - r0], a[q0:q1]))
+            for j in jobs:
+                j.result()
+
+        with ThreadPoolExecutor(max_workers=nt) as pool:
+            for i, r0 in enumerate(range(0, m, rows)):
+                r1, b = min(m, r0 + rows), i % 2
+                if done[b] is not None:
+                    done[b].synchronize()
+                fill(b, r0, r1)
+                for si in range(len(srcs)):
+                    devbuf[b][si][: r1 - r0].copy_(stage[b][si][: r1 - r0], non_blocking=True)
+                done[b] = torch.cuda.Event()
+                done[b].record()
+                pack(devbuf[b][0][: r1 - r0], devbuf[b][1][: r1 - r0] if mask is not None else None, r0, r1)
     return BitMatrix(P, (m, n)), (None if M is None else BitMatrix(M, (m, n))), int(flags.item()), h2d
 
 
@@ -506,6 +547,17 @@ class DeviceProblem:
         iters = (C.c_int32 * n)()
         self._call("nbmf_batch_poll", C.byref(done), iters)
         return bool(done.value), [int(v) for v in iters]
+
+    def batch_tail(self, hist_len):
+        """(loss histories [n, hist_len], converged [n], simplex deviations [n]) of the batch this context leads, with one
+        synchronisation (``nbmf_batch_tail``)."""
+        n = getattr(self, "_batch_n", 1)
+        hist = np.zeros((n, max(int(hist_len), 1)), dtype=np.float64)
+        conv = (C.c_int32 * n)()
+        dev = np.zeros(n, dtype=np.float64)
+        self._call("nbmf_batch_tail", hist.ctypes.data_as(C.POINTER(C.c_double)), hist.shape[1], conv,
+                   dev.ctypes.data_as(C.POINTER(C.c_double)))
+        return hist, [bool(v) for v in conv], dev
 
     def transform(self, n_steps=50):
         self._call("nbmf_transform", int(n_steps))

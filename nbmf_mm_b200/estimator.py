@@ -124,7 +124,11 @@ class NBMFMM(BaseEstimator, TransformerMixin):
     def _validate_X(X):
         if isinstance(X, BitMatrix):
             return X
-        return check_array(X, accept_sparse="csr", dtype=np.float64)  # _base.py:83; CSR stays CSR (packed on the device)
+        # _base.py:83; CSR stays CSR (packed on the device).  Large dense X: sklearn's finiteness test is a host pass of
+        # 70 ms per 10^8 entries; NaN and inf fail the range test of the device pass that packs X instead (fit() then
+        # re-runs the host test to raise sklearn's message, as the reference would have)
+        big = isinstance(X, np.ndarray) and X.size >= (1 << 22)
+        return check_array(X, accept_sparse="csr", dtype=np.float64, ensure_all_finite=not big)
 
     # ------------------------------------------------------------------ fit
     def fit(self, X, y=None, mask=None):
@@ -159,6 +163,14 @@ class NBMFMM(BaseEstimator, TransformerMixin):
                 rank, world = dist.get_rank(), dist.get_world_size()
         row_sharded = self.distributed in (True, "rows")
 
+        try:
+            return self._fit_checked(X, mask, orientation, n_init, by_restart, row_sharded, rank, world)
+        except ValueError as e:
+            if str(e) == "X must be binary" and isinstance(X, np.ndarray) and not host_check:
+                check_array(X, dtype=np.float64)                       # NaN / inf: sklearn's error comes first (_base.py:83)
+            raise
+
+    def _fit_checked(self, X, mask, orientation, n_init, by_restart, row_sharded, rank, world):
         best = None
         mine = partition_restarts(n_init, rank, world) if by_restart else list(range(n_init))
         if n_init > 1 and not row_sharded:

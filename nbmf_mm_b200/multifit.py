@@ -30,6 +30,30 @@ def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
     return np.asarray(W_init, dtype=np.float64), np.asarray(H_init, dtype=np.float64)
 
 
+_BATCH_STREAMS = {}
+
+
+def _batch_stream(dev):
+    import torch
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _BATCH_STREAMS:
+        _BATCH_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _BATCH_STREAMS[key]
+
+
+_WORKER_STREAMS = {}
+
+
+def _worker_streams(dev, n):
+    """n streams for the worker threads of one call, the same ones every call."""
+    import torch
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    pool = _WORKER_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return list(pool[:n])
+
+
 def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500, tol=1e-5, eps=1e-8,
                      projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
                      engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False, batch=True,
@@ -111,11 +135,12 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     ready = torch.cuda.Event()
     ready.record(main_stream)                                # the data planes were produced on this stream
     local = threading.local()
+    free_streams = _worker_streams(dev, n_streams)           # cached per device: see _batch_stream
 
     def run(idx):
         k, alpha, beta, mi, tl, W0, H0 = prepared[idx]
         if not hasattr(local, "stream"):
-            local.stream = torch.cuda.Stream(device=dev)
+            local.stream = free_streams.pop()                # one per worker thread of this call (list.pop is atomic)
         with torch.cuda.stream(local.stream):
             local.stream.wait_event(ready)
             prob = make_problem(data, k, dtype=dtype, alpha=alpha, beta=beta, eps=eps, mask_semantics=mask_semantics,
@@ -152,7 +177,10 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                 return big["t"][b * big["S"]: b * big["S"] + nbytes]
             return provide
 
-        stream = torch.cuda.Stream(device=dev)               # not the default stream: the loop is replayed from a graph
+        # not the default stream (the loop is replayed from a graph), and the SAME stream on every call: torch's caching
+        # allocator keeps one pool per stream, so a fresh stream per call finds none of the blocks earlier calls released
+        # and goes back to cudaMalloc for half a gigabyte of workspaces (sporadic 100 ms stalls in any phase)
+        stream = _batch_stream(dev)
         probs, out = [], []
         tdt = getattr(torch, np.dtype(dtype).name)
         import os, time
@@ -201,27 +229,36 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                     chunk = min(chunk * 2, 256)
                 else:
                     raise RuntimeError("batched fit loop did not terminate")
-                leader.batch_bind(1, 0)
                 mark("loop")
+                hist, conv, devs = leader.batch_tail(max(n_iters))   # one synchronisation for all fits
+                leader.batch_bind(1, 0)
                 Wd = torch.empty((B, m, k), dtype=torch.float64, device=dev)
                 Hd = torch.empty((B, k, n), dtype=torch.float64, device=dev)
                 meta = []
                 for b, (prob, n_iter) in enumerate(zip(probs, n_iters)):
-                    losses_arr, converged = prob.fit_history(n_iter)
-                    dv = prob.simplex_deviation()            # solver tail, _solver.py:192-213
+                    dv = devs[b]                             # solver tail, _solver.py:192-213
                     prob.get_factors_f64_device(Wd[b], Hd[b], normalize_w=bool(np.isfinite(dv) and dv > 1e-9))
-                    meta.append(([np.float64(v) for v in losses_arr], n_iter, converged, prob.engine))
+                    meta.append(([np.float64(v) for v in hist[b, :n_iter]], n_iter, conv[b], prob.engine))
                 mark("tails")
                 if transpose:                                # _solver.py:182-184, on the device
                     Wd, Hd = Hd.transpose(1, 2).contiguous(), Wd.transpose(1, 2).contiguous()
-                # the results are views of two pinned blocks (fresh pageable arrays page-fault for longer than the copy
-                # takes: 19 ms at K = 64); torch's host allocator recycles the blocks once the caller drops the results
+                # one DMA each into pinned staging, then a threaded copy into the arrays the caller keeps.  (A plain .cpu()
+                # of 50 MB at K = 64 costs 19 ms: pageable D2H + page faults on one thread.  Handing out views of the pinned
+                # blocks instead ties their lifetime to the caller's, and every call then page-locks fresh memory: 10-100 ms,
+                # highly variable.  The staging blocks go back to torch's pinned cache when this function returns.)
                 Wp = torch.empty(Wd.shape, dtype=torch.float64, pin_memory=True)
                 Hp = torch.empty(Hd.shape, dtype=torch.float64, pin_memory=True)
                 Wp.copy_(Wd, non_blocking=True)
                 Hp.copy_(Hd, non_blocking=True)
+                Wh, Hh = np.empty(tuple(Wd.shape)), np.empty(tuple(Hd.shape))
                 stream.synchronize()
-                Wh, Hh = Wp.numpy(), Hp.numpy()
+                Wpn, Hpn = Wp.numpy(), Hp.numpy()
+
+                def unstage(b):
+                    np.copyto(Wh[b], Wpn[b])
+                    np.copyto(Hh[b], Hpn[b])
+                with ThreadPoolExecutor(max_workers=min(B, 8)) as pool:
+                    list(pool.map(unstage, range(B)))
                 mark("results downloaded")
                 for b, (losses, n_iter, converged, eng) in enumerate(meta):
                     out.append((Wh[b], Hh[b], losses, 0.0, n_iter, converged, eng))

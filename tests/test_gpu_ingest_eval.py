@@ -177,14 +177,19 @@ def test_dense_front_end_on_the_device_is_bit_exact(xdt, mdt):
     X, mask = _xy(301, 1100, seed=5)
     Xa = X.astype(xdt)
     Ma = None if mdt is None else mask.astype(mdt)
-    P, M, flags, h2d = pack_host_dense_checked(Xa, Ma, None, chunk_bytes=64 * 1100 * Xa.dtype.itemsize)   # 5 chunks
     want_p = BitMatrix.from_dense((X != 0) & ((mask != 0) if Ma is not None else True))
-    assert flags == 0 and h2d == Xa.nbytes + (0 if Ma is None else Ma.nbytes)
-    assert np.array_equal(P.words.cpu().numpy().view(np.uint32), want_p.words)
-    if Ma is not None:
-        assert np.array_equal(M.words.cpu().numpy().view(np.uint32), BitMatrix.from_dense(mask).words)
-    else:
-        assert M is None
+    # pageable chunks (small inputs) and the pinned, threaded staging pipeline large inputs take (forced here)
+    for kw in (dict(), dict(pinned_from=0, n_threads=3)):
+        P, M, flags, h2d = pack_host_dense_checked(Xa, Ma, None, chunk_bytes=64 * 1100 * 8, **kw)   # 5 chunks, the last ragged
+        assert flags == 0 and h2d == Xa.nbytes + (0 if Ma is None else Ma.nbytes)
+        assert np.array_equal(P.words.cpu().numpy().view(np.uint32), want_p.words)
+        if Ma is not None:
+            assert np.array_equal(M.words.cpu().numpy().view(np.uint32), BitMatrix.from_dense(mask).words)
+        else:
+            assert M is None
+    assert pack_host_dense_checked(np.asfortranarray(X), mask, None, chunk_bytes=64 * 1100 * 8, pinned_from=0)[0] is not None
+    Pf = pack_host_dense_checked(np.asfortranarray(X), mask, None, chunk_bytes=64 * 1100 * 8, pinned_from=0)[0]
+    assert np.array_equal(Pf.words.cpu().numpy().view(np.uint32), BitMatrix.from_dense((X != 0) & (mask != 0)).words)   # any strides
     # flags: probabilistic values, out-of-range values, NaN, weighted mask
     Xp = X.copy(); Xp[7, 3] = 0.25
     assert pack_host_dense_checked(Xp, mask, None)[2] == 1
@@ -212,3 +217,11 @@ def test_dense_front_end_errors_and_large_x_range_check():
         NBMF(n_components=2, max_iter=2, dtype="float32").fit(big)
     with pytest.raises(ValueError, match="X must be binary"):            # reference order: X before orientation
         NBMF(n_components=2, max_iter=2, orientation="nope").fit(big)
+    # NaN / inf in a large X: found by the device pass too (no host finiteness pass), reported with sklearn's message,
+    # which the reference's check_array raises before anything else (_base.py:83)
+    big[1000, 1000] = np.nan
+    with pytest.raises(ValueError, match="contains NaN"):
+        NBMF(n_components=2, max_iter=2, dtype="float32").fit(big)
+    big[1000, 1000] = np.inf
+    with pytest.raises(ValueError, match="infinity"):
+        NBMF(n_components=2, max_iter=2, n_init=2).fit(big)
