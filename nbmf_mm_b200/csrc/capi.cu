@@ -318,6 +318,8 @@ static int make_plan(const nbmf_config& c, Plan* p) {
         p->oBar = take(64);
         p->oFPrior2 = take((size_t)p->n_prior * 16);
         // W phase: warps that share a row, so that a problem with few rows still uses every warp of the (nominal) grid
+        // (more warps per row also when the rows exceed the grid's warps -- 1226 rows: 3 trips of 5 words instead of 2 of
+        // 9 -- measured slower: every trip pays two CTA barriers)
         int ws = 1;
         while (ws < 8 && (int64_t)ws * 2 * c.m <= 148 * 8 && ws * 2 <= nwords) ws *= 2;
         p->f_wsplit = ws;

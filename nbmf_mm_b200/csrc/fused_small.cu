@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_fit_kernel(const FusedArgs a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Real* const smem = reinterpret_cast<Real*>(smem_raw);
   __shared__ FitState ls;
-  __shared__ double red[FNW];
+  __shared__ double red[FNW], red2[FNW];
   __shared__ double sG[FNW][33];                       // W phase: partial gradients of the warps that share a row
 
   if (tid == 0) ls = *state;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_fit_kernel(const FusedArgs a0) {
         Real px = Real(1), ll = Real(0);
         bool neg = false;
         double lld = 0.0;
-        #pragma unroll 1
+        #pragma unroll 1                              // (two rows in flight: measured slower, the register file is full)
         for (int r = 0; r < nrows; ++r) {
           const Real* wr = sWw + r * KP;
           Real theta = Real(0);
@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(FNT, 1) fused_fit_kernel(const FusedArgs a0) {
     if (warp == 0) {
       const double* __restrict__ prior = (trace_it & 1) ? prior_b1 : prior_b0;
       double v = 0.0, pa = 0.0, pb = 0.0;
-      #pragma unroll 1
+      #pragma unroll 8                                // independent L2 loads in flight, fixed order of the adds
       for (int i = lane; i < nunits; i += 32) v += __ldcg(LLp + i);
-      #pragma unroll 1
+      #pragma unroll 4
       for (int i = lane; i < a0.n_prior; i += 32) {
         pa += __ldcg(prior + 2 * i);
         pb += __ldcg(prior + 2 * i + 1);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(FNT, 1) fused_fit_kernel(const FusedArgs a0) {
         double la = 0.0, lb = 0.0;
         if (kk < k && j < n) {
           Real cs = ldcg_(CDp + (int64_t)kk * ldw + j), ds = ldcg_(CDp + ((int64_t)kp + kk) * ldw + j);
-          #pragma unroll 4
+          #pragma unroll 8
           for (int s = 1; s < nsuper; ++s) {
             cs += ldcg_(CDp + ((int64_t)(s * 2) * kp + kk) * ldw + j);
             ds += ldcg_(CDp + ((int64_t)(s * 2 + 1) * kp + kk) * ldw + j);
@@ -288,9 +288,16 @@ __global__ void __launch_bounds__(FNT, 1) fused_fit_kernel(const FusedArgs a0) {
           la = log((double)(hn + eps));
           lb = log((double)((Real(1) - hn) + eps));
         }
-        const double sa = block_sum<FNT>(la, red);
-        const double sb = block_sum<FNT>(lb, red);
+        // both sums with one pair of barriers: fixed shuffle tree, then the warps in order (as block_sum does)
+        la = warp_sum(la);
+        lb = warp_sum(lb);
+        __syncthreads();
+        if (lane == 0) { red[warp] = la; red2[warp] = lb; }
+        __syncthreads();
         if (tid == 0) {
+          double sa = 0.0, sb = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < FNW; ++w8) { sa += red[w8]; sb += red2[w8]; }
           prior[2 * vb] = sa;
           prior[2 * vb + 1] = sb;
         }
