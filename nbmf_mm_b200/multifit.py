@@ -30,6 +30,51 @@ def _draw_inits(random_state, m, n, k, W_init, H_init, transpose):
     return np.asarray(W_init, dtype=np.float64), np.asarray(H_init, dtype=np.float64)
 
 
+def draw_all_inits(jobs, m, n, transpose, n_threads=None):
+    """Inits of every job, as the loop of solver calls would draw them (``_draw_inits`` per job, in order), including the
+    state it leaves the global NumPy stream in.  When every job is seeded (the usual case: restart r uses random_state +
+    r) the jobs are independent streams and are drawn concurrently from private generators -- NumPy releases the GIL, and
+    64 x (1226 x 32 + 32 x 285) doubles cost 30 ms on one thread, as much as the fits themselves on the tensor engine.
+    Unseeded jobs continue the global stream and keep the sequential loop."""
+    need = [i for i, j in enumerate(jobs) if j.get("W_init") is None or j.get("H_init") is None]
+    if len(need) < 2 or any(j.get("random_state") is None for j in jobs):
+        return [_draw_inits(j.get("random_state"), m, n, int(j["n_components"]), j.get("W_init"), j.get("H_init"), transpose)
+                for j in jobs]
+
+    def draw(i):
+        j = jobs[i]
+        rs = np.random.RandomState(j["random_state"])
+        k = int(j["n_components"])
+        W_i, H_i = j.get("W_init"), j.get("H_init")
+        if W_i is None:
+            W_i = rs.uniform(0.1, 0.9, (m, k))
+        if H_i is None:
+            H_i = rs.uniform(0.1, 0.9, (k, n))
+        return np.asarray(W_i, dtype=np.float64), np.asarray(H_i, dtype=np.float64), rs
+
+    import os
+    out = [None] * len(jobs)
+    last_rs = None
+    workers = n_threads or max(1, (os.cpu_count() or 2) // 2)
+    with ThreadPoolExecutor(max_workers=min(len(need), workers)) as pool:
+        for i, (W_i, H_i, rs) in zip(need, pool.map(draw, need)):
+            out[i] = (W_i, H_i)
+            if i == len(jobs) - 1:
+                last_rs = rs
+    for i, j in enumerate(jobs):
+        if out[i] is None:                                   # both inits given: no draw (the swap of _solver.py:122-125)
+            W_i, H_i = j["W_init"], j["H_init"]
+            if transpose:
+                W_i, H_i = np.asarray(H_i).T, np.asarray(W_i).T
+            out[i] = (np.asarray(W_i, dtype=np.float64), np.asarray(H_i, dtype=np.float64))
+    # the global stream ends where the LAST job leaves it: seeded, then its draws (if it drew)
+    if last_rs is not None:
+        np.random.set_state(last_rs.get_state())
+    else:
+        np.random.seed(jobs[-1]["random_state"])
+    return out
+
+
 _BATCH_STREAMS = {}
 
 
@@ -94,42 +139,14 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
             queues = 8
         n_streams = max(8, min(queues, 32)) if m * n <= (1 << 24) else 1
     n_streams = max(1, min(int(n_streams), len(jobs)))
-    # Every job must see the init stream the reference would give it.  Seeded jobs (the usual case: restart r uses
-    # random_state + r) are independent streams, drawn concurrently from private generators (NumPy releases the GIL;
-    # 64 x (1226 x 32 + 32 x 285) doubles cost 30 ms on one thread, as much as the fits themselves on the tensor engine);
-    # the global stream is left where the last seeded job would leave it.  Unseeded jobs use the global stream, in order.
     for j in jobs:
         if int(j.get("max_iter", max_iter)) < 1:
             raise UnboundLocalError("max_iter must be >= 1")
-    inits = [None] * len(jobs)
-    seeded = [i for i, j in enumerate(jobs) if j.get("random_state") is not None
-              and (j.get("W_init") is None or j.get("H_init") is None)]
-    if len(seeded) > 1 and all(jobs[i].get("random_state") is not None for i in range(len(jobs))):
-        def draw(i):
-            j = jobs[i]
-            rs = np.random.RandomState(j["random_state"])
-            W_i, H_i = j.get("W_init"), j.get("H_init")
-            k_i = int(j["n_components"])
-            if transpose and W_i is not None and H_i is not None:
-                W_i, H_i = np.asarray(H_i).T, np.asarray(W_i).T
-            if W_i is None:
-                W_i = rs.uniform(0.1, 0.9, (m, k_i))
-            if H_i is None:
-                H_i = rs.uniform(0.1, 0.9, (k_i, n))
-            return np.asarray(W_i, dtype=np.float64), np.asarray(H_i, dtype=np.float64), rs
-        import os
-        with ThreadPoolExecutor(max_workers=min(len(seeded), max(1, (os.cpu_count() or 2) // 2))) as pool:
-            for i, (W_i, H_i, rs) in zip(seeded, pool.map(draw, seeded)):
-                inits[i] = (W_i, H_i)
-                last_state = rs.get_state() if i == seeded[-1] else None
-        np.random.set_state(last_state)                      # as np.random.seed(last seed) + its draws would leave it
+    inits = draw_all_inits(jobs, m, n, transpose)
     prepared = []
-    for i, j in enumerate(jobs):
-        k = int(j["n_components"])
-        mi = int(j.get("max_iter", max_iter))
-        W0, H0 = inits[i] if inits[i] is not None else _draw_inits(j.get("random_state"), m, n, k, j.get("W_init"),
-                                                                   j.get("H_init"), transpose)
-        prepared.append((k, float(j.get("alpha", 1.2)), float(j.get("beta", 1.2)), mi, float(j.get("tol", tol)), W0, H0))
+    for j, (W0, H0) in zip(jobs, inits):
+        prepared.append((int(j["n_components"]), float(j.get("alpha", 1.2)), float(j.get("beta", 1.2)),
+                         int(j.get("max_iter", max_iter)), float(j.get("tol", tol)), W0, H0))
 
     main_stream = torch.cuda.current_stream(dev)
     ready = torch.cuda.Event()

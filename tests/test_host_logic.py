@@ -187,3 +187,36 @@ def test_dataset_reader_and_splits(datasets):
         assert np.array_equal(trm + vam + tem, np.ones_like(Y))
         Yl, a, b, c = load_dataset_and_splits("lastfm", ref)
         assert np.array_equal(Yl, datasets["lastfm"]) and np.array_equal(a + b + c, np.ones_like(Yl))
+
+
+def test_concurrent_init_draws_equal_the_sequential_loop():
+    """nbmf_mm_multifit draws the inits of seeded jobs concurrently from private generators; the arrays and the state the
+    global NumPy stream is left in must be those of the reference's loop of solver calls (_solver.py:102-103,122-129)."""
+    from nbmf_mm_b200.multifit import _draw_inits, draw_all_inits
+    rng = np.random.default_rng(0)
+    m, n = 37, 29
+    for transpose in (False, True):
+        for trial in range(6):
+            jobs = []
+            for r in range(7):
+                k = int(rng.integers(2, 6))
+                j = dict(n_components=k, random_state=int(rng.integers(0, 1000)))
+                em, en = (n, m) if transpose else (m, n)                  # given inits are in the caller's orientation
+                if rng.integers(0, 4) == 1:
+                    j["W_init"], j["H_init"] = rng.random((em, k)), rng.random((k, en))
+                jobs.append(j)
+            if trial == 4:
+                jobs[-1]["W_init"], jobs[-1]["H_init"] = rng.random((n if transpose else m, jobs[-1]["n_components"])), \
+                    rng.random((jobs[-1]["n_components"], m if transpose else n))  # the last job draws nothing
+            if trial == 5:
+                jobs[3]["random_state"] = None                            # an unseeded job: the sequential loop is kept
+            np.random.seed(123)
+            seq = [_draw_inits(j.get("random_state"), m, n, int(j["n_components"]), j.get("W_init"), j.get("H_init"), transpose)
+                   for j in jobs]
+            after_seq = np.random.uniform()
+            np.random.seed(123)
+            par = draw_all_inits(jobs, m, n, transpose, n_threads=3)
+            after_par = np.random.uniform()
+            assert after_seq == after_par
+            for (Ws, Hs), (Wp, Hp) in zip(seq, par):
+                assert np.array_equal(Ws, Wp) and np.array_equal(Hs, Hp)
