@@ -15,7 +15,7 @@ from .bits import BitMatrix  # noqa: E402
 from .estimator import NBMF, NBMFMM  # noqa: E402
 from .multifit import nbmf_mm_multifit  # noqa: E402
 from .solver import nbmf_mm_solver, nbmf_mm_update_beta_dir  # noqa: E402
-from . import datasets  # noqa: E402,F401
+from . import datasets, experiment  # noqa: E402,F401
 
 __version__ = "0.1.0"
 __all__ = ["NBMFMM", "NBMF", "nbmf_mm_solver", "nbmf_mm_update_beta_dir", "nbmf_mm_multifit", "BitMatrix"]

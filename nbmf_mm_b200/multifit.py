@@ -99,10 +99,53 @@ def _worker_streams(dev, n):
     return list(pool[:n])
 
 
+class HeldOut:
+    """Held-out evaluation of fitted factors without leaving the device: the properly masked
+    mean negative log-likelihood per selected entry and its exponential under each of ``eval_masks`` (name -> 0/1 mask
+    of Y's shape) -- ``compute_perplexity(Y, W @ H, mask)`` of the reference's experiment driver
+    (``examples/reproduce_magron2022.py:40-47``, eps = 1e-8) -- through the fused objective kernel with strict mask
+    semantics and a flat prior; Theta is never materialised.  The planes (Y & mask, mask) of every evaluation mask are
+    packed and uploaded once per call, in the fits' internal orientation, so that the factors go from the fit's context
+    to the evaluation context as device tensors."""
+
+    def __init__(self, Y, eval_masks, *, transpose, dtype, device):
+        self.dtype, self.device = dtype, device
+        self.sets = {}
+        for name, em in dict(eval_masks).items():
+            if em is None:
+                raise ValueError(f"eval_masks[{name!r}] is None: an evaluation mask selects the held-out entries")
+            d = prepare_data(Y, em, transpose=transpose, dtype=dtype, device=device)
+            if d.vkind != "bits":
+                raise ValueError("held-out evaluation needs binary Y and 0/1 evaluation masks")
+            self.sets[name] = d
+
+    def contexts(self, k):
+        """One evaluation context per mask for factors with ``k`` components (on the current stream); the caller closes
+        them (``close``)."""
+        return {name: make_problem(d, k, dtype=self.dtype, alpha=1.0, beta=1.0, eps=1e-8, mask_semantics="strict",
+                                   projection="normalize", max_iter_cap=1, device=self.device, engine="simt")
+                for name, d in self.sets.items()}
+
+    def score(self, ctxs, Wd, Hd):
+        """``{name: {"nll", "perplexity", "n_entries"}}`` of the internal-orientation factors ``Wd`` (m x k), ``Hd``
+        (k x n) -- device tensors."""
+        out = {}
+        for name, prob in ctxs.items():
+            prob.set_factors(Wd, Hd, normalize_w=False)
+            nll = float(prob.objective())
+            out[name] = {"nll": nll, "perplexity": float(np.exp(nll)), "n_entries": int(self.sets[name].n_obs)}
+        return out
+
+    @staticmethod
+    def close(ctxs):
+        for prob in ctxs.values():
+            prob.close()
+
+
 def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500, tol=1e-5, eps=1e-8,
                      projection_method="normalize", mask_semantics="reference", dtype="float64", device=None,
                      engine="auto", dense_storage=None, n_streams=None, stats=None, check_range=False, batch=True,
-                     batch_plan="fit", verbose=0):
+                     batch_plan="fit", verbose=0, eval_masks=None):
     """Fit ``len(jobs)`` models to the same ``Y`` / ``mask``.
 
     ``jobs``: sequence of dicts with ``n_components`` and optionally ``alpha``, ``beta`` (default 1.2),
@@ -117,7 +160,12 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     partials are then summed in a different order, so results agree with the solver call to rounding (fp64 ~1e-15, fp32
     ~1e-7) instead of bit for bit.
     ``n_streams``: concurrent fits for the remaining jobs
-    (default: one per hardware queue, 8..32, for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own)."""
+    (default: one per hardware queue, 8..32, for problems up to 2^24 entries, else 1: a large fit fills the GPU on its own).
+    ``eval_masks``: ``{name: mask}`` of held-out entry sets (validation / test splits; ``mask`` itself may be listed to
+    get the training perplexity).  Every result then carries a sixth element ``{name: {"nll", "perplexity",
+    "n_entries"}}``: the properly masked perplexity of the job's returned factors (``HeldOut``), computed on the device
+    right after the fit -- the train -> validate loop of ``examples/reproduce_magron2022.py:87-117`` without a host
+    round trip of the factors or an M x N reconstruction."""
     import torch
     if orientation not in _CANON:
         raise ValueError(f"Unknown orientation: {orientation}. Must be one of {list(_CANON)}")
@@ -131,6 +179,7 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     data = prepare_data(Y, mask, transpose=transpose, dtype=dtype, device=device, dense_storage=dense_storage,
                         check_range=check_range)
     m, n = data.m, data.n
+    held = HeldOut(Y, eval_masks, transpose=transpose, dtype=dtype, device=device) if eval_masks else None
     if n_streams is None:                                    # one stream per hardware queue, see __init__.py
         import os
         try:
@@ -166,13 +215,26 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                 prob.set_factors(W0, H0, normalize_w=True)
                 losses_arr, n_iter, converged = prob.fit(mi, tl)
                 dv = prob.simplex_deviation()                # solver tail, _solver.py:192-213
-                W, H = prob.get_factors_f64(normalize_w=bool(np.isfinite(dv) and dv > 1e-9))
+                renorm = bool(np.isfinite(dv) and dv > 1e-9)
+                ho = None
+                if held is None:
+                    W, H = prob.get_factors_f64(normalize_w=renorm)
+                else:                                        # the returned factors, scored where they are
+                    Wd = torch.empty((m, k), dtype=torch.float64, device=dev)
+                    Hd = torch.empty((k, n), dtype=torch.float64, device=dev)
+                    prob.get_factors_f64_device(Wd, Hd, normalize_w=renorm)
+                    ctxs = held.contexts(k)
+                    try:
+                        ho = held.score(ctxs, Wd, Hd)
+                    finally:
+                        held.close(ctxs)
+                    W, H = Wd.cpu().numpy(), Hd.cpu().numpy()
                 eng = prob.engine
             finally:
                 prob.close()
         if transpose:                                        # _solver.py:182-184
             W, H = np.ascontiguousarray(H.T), np.ascontiguousarray(W.T)
-        return W, H, [np.float64(v) for v in losses_arr], 0.0, n_iter, converged, eng
+        return W, H, [np.float64(v) for v in losses_arr], 0.0, n_iter, converged, eng, ho
 
     def run_batch(idxs):
         """Fits with the same K and hyper-parameters advance TOGETHER: contexts with workspaces at a uniform stride in one
@@ -257,6 +319,14 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                     prob.get_factors_f64_device(Wd[b], Hd[b], normalize_w=bool(np.isfinite(dv) and dv > 1e-9))
                     meta.append(([np.float64(v) for v in hist[b, :n_iter]], n_iter, conv[b], prob.engine))
                 mark("tails")
+                held_out = [None] * B
+                if held is not None:                         # one evaluation context per mask for the whole group
+                    ctxs = held.contexts(k)
+                    try:
+                        held_out = [held.score(ctxs, Wd[b], Hd[b]) for b in range(B)]
+                    finally:
+                        held.close(ctxs)
+                    mark("held-out")
                 if transpose:                                # _solver.py:182-184, on the device
                     Wd, Hd = Hd.transpose(1, 2).contiguous(), Wd.transpose(1, 2).contiguous()
                 # one DMA each into pinned staging, then a threaded copy into the arrays the caller keeps.  (A plain .cpu()
@@ -278,7 +348,7 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
                     list(pool.map(unstage, range(B)))
                 mark("results downloaded")
                 for b, (losses, n_iter, converged, eng) in enumerate(meta):
-                    out.append((Wh[b], Hh[b], losses, 0.0, n_iter, converged, eng))
+                    out.append((Wh[b], Hh[b], losses, 0.0, n_iter, converged, eng, held_out[b]))
             finally:
                 for prob in probs:
                     prob.close()
@@ -326,4 +396,6 @@ def nbmf_mm_multifit(Y, jobs, *, mask=None, orientation="beta-dir", max_iter=500
     if stats is not None:
         stats.update(h2d_bytes=data.h2d_bytes, n_streams=n_streams, engine=results[0][6], batched=batched,
                      converged=[r[5] for r in results])
+    if held is not None:
+        return [r[:5] + (r[7],) for r in results]
     return [r[:5] for r in results]

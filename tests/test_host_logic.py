@@ -220,3 +220,35 @@ def test_concurrent_init_draws_equal_the_sequential_loop():
             assert after_seq == after_par
             for (Ws, Hs), (Wp, Hp) in zip(seq, par):
                 assert np.array_equal(Ws, Wp) and np.array_equal(Hs, Hp)
+
+
+def test_experiment_driver_builds_the_loops_of_the_reference_script(monkeypatch):
+    """Host side of nbmf_mm_b200.experiment (examples/reproduce_magron2022.py:74-152,242-329): job order (alpha outer,
+    beta inner), the driver's seed, record fields, first arg-min of the validation perplexity -- with the device call
+    replaced by a stub that returns a perplexity computed from the job."""
+    from nbmf_mm_b200 import experiment
+    seen = {}
+
+    def stub(Y, jobs, *, mask=None, eval_masks=None, **kw):
+        seen["jobs"], seen["kw"], seen["masks"] = jobs, kw, eval_masks
+        out = []
+        for j in jobs:
+            val = abs(j["alpha"] - 1.5) + abs(j["beta"] - 2.0) + 1.0
+            ho = {name: {"nll": np.log(val), "perplexity": val, "n_entries": 3} for name in eval_masks}
+            out.append((np.zeros((4, j["n_components"])), np.zeros((j["n_components"], 5)), [np.float64(0.7), np.float64(0.6)],
+                        0.0, 2, ho))
+        return out
+    monkeypatch.setattr(experiment, "nbmf_mm_multifit", stub)
+    Y = np.zeros((4, 5))
+    tr, va, te = np.ones((4, 5)), np.ones((4, 5)), np.ones((4, 5))
+    out = experiment.grid_search(Y, tr, va, n_components=3, max_iter=7)
+    assert [(j["alpha"], j["beta"]) for j in seen["jobs"]] == [(a, b) for a in experiment.ALPHA_VALUES for b in experiment.BETA_VALUES]
+    assert all(j["random_state"] == 12345 and j["n_components"] == 3 for j in seen["jobs"])
+    assert set(seen["masks"]) == {"train", "val"} and seen["kw"]["max_iter"] == 7 and seen["kw"]["orientation"] == "beta-dir"
+    assert len(out["records"]) == 36 and (out["best"]["alpha"], out["best"]["beta"]) == (1.5, 2.0)
+    assert set(out["best"]) == {"alpha", "beta", "k", "train_perplexity", "val_perplexity", "n_iter", "final_loss", "time"}
+    assert out["best"]["n_iter"] == 2 and out["best"]["final_loss"] == 0.6
+    recs = experiment.components_sweep(Y, tr, va, te, alpha=2.0, beta=2.0)
+    assert [r["k"] for r in recs] == list(experiment.K_RANGE) and all("test_perplexity" in r for r in recs)
+    one = experiment.fit_and_test(Y, tr, te, n_components=4, alpha=1.0, beta=1.0)
+    assert seen["kw"]["max_iter"] == 1000 and one["W"].shape == (4, 4) and "val_perplexity" not in one
