@@ -53,7 +53,7 @@ extern "C" {
 #define NBMF_PROJ_DUCHI 1     /* multiplicative step / n_obs(row), Euclidean simplex projection; unpinned */
 
 #define NBMF_ENGINE_AUTO 0   /* a single small fit: FUSED; else TENSOR when eligible and m >= 512, n >= 128; else SIMT */
-#define NBMF_ENGINE_SIMT 1   /* packed-FFMA2 CUDA-core kernels: every dtype / K <= 64 / layout */
+#define NBMF_ENGINE_SIMT 1   /* packed-FFMA2 CUDA-core kernels: every dtype / K <= 128 / layout */
 #define NBMF_ENGINE_TENSOR 2 /* tcgen05 + TMEM kernels, TF32 + bf16 split precision: float32, bit-packed V, K <= 64, eps >= 1e-9 */
 #define NBMF_ENGINE_FUSED 3  /* SIMT arithmetic, but the fit loop (nbmf_fit / nbmf_fit_enqueue) runs whole iterations inside one
                               * persistent cooperative kernel: bit-packed V, K <= 32, single GPU.  AUTO picks it while
@@ -66,7 +66,7 @@ typedef struct nbmf_ctx nbmf_ctx;
 typedef struct nbmf_config {
   int64_t m;             /* local rows of this shard (internal orientation) */
   int64_t n;             /* columns */
-  int32_t k;             /* n_components, 1..64 */
+  int32_t k;             /* n_components, 1..128 (tensor engine: <= 64, persistent small-fit kernel: <= 32) */
   int32_t dtype;         /* NBMF_F32 | NBMF_F64 */
   int32_t vkind;         /* NBMF_V_BITS | NBMF_V_DENSE | NBMF_V_DENSE_F16 */
   int32_t mask_semantics;

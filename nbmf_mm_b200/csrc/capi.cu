@@ -188,7 +188,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int make_plan(const nbmf_config& c, Plan* p) {
   if (c.m < 1 || c.n < 1) return fail(NBMF_ERR_ARG, "m and n must be positive");
-  if (c.k < 1 || c.k > 64) return fail(NBMF_ERR_UNSUPPORTED, "n_components must be in 1..64");
+  if (c.k < 1 || c.k > 128) return fail(NBMF_ERR_UNSUPPORTED, "n_components must be in 1..128");
   if (c.dtype != NBMF_F32 && c.dtype != NBMF_F64) return fail(NBMF_ERR_ARG, "dtype must be NBMF_F32 or NBMF_F64");
   if (c.vkind != NBMF_V_BITS && c.vkind != NBMF_V_DENSE && c.vkind != NBMF_V_DENSE_F16) return fail(NBMF_ERR_ARG, "bad vkind");
   if (c.vkind == NBMF_V_DENSE_F16 && c.dtype != NBMF_F32)
@@ -406,7 +406,7 @@ extern "C" int nbmf_pack_csr(const int64_t* indptr, const int32_t* indices, cons
   return NBMF_OK;
 }
 extern "C" int nbmf_reconstruct(int dtype, const void* w, const void* h, int64_t m, int64_t n, int32_t k, void* out, void* stream) {
-  if (!w || !h || !out || m < 1 || n < 1 || k < 1 || k > 64) return fail(NBMF_ERR_ARG, "nbmf_reconstruct: bad arguments (k in 1..64)");
+  if (!w || !h || !out || m < 1 || n < 1 || k < 1 || k > 128) return fail(NBMF_ERR_ARG, "nbmf_reconstruct: bad arguments (k in 1..128)");
   if (dtype != NBMF_F32 && dtype != NBMF_F64) return fail(NBMF_ERR_ARG, "dtype must be NBMF_F32 or NBMF_F64");
   launch_reconstruct(dtype, w, h, m, n, k, out, (cudaStream_t)stream);
   CHECK_LAUNCH(1);

@@ -61,13 +61,14 @@ __device__ __forceinline__ Real warp_scan_incl(Real v, int lane) {
   return v;
 }
 
-// ---- simplex projection of one row held across a warp (lane = component k; EPL = 2: components lane and lane + 32) and
-// the store of the row.  v = the multiplicative step W*G/denom, part = this lane's share of its sum.  projection 0 =
-// "normalize" (L1 renormalisation, _solver.py:55-57), 1 = "duchi" (Euclidean projection, Duchi et al. 2008): descending
-// bitonic sort of the row across the warp's registers, inclusive prefix sums in sorted order, rho = last index whose
-// value exceeds the running threshold, then w = max(v - theta, 0).  Every reduction is a fixed shuffle tree.
+// ---- simplex projection of one row held across a warp (lane = component k; EPL = 1, 2 or 4 components per lane: lane,
+// lane + 32, ..) and the store of the row.  v = the multiplicative step W*G/denom, part = this lane's share of its sum.
+// projection 0 = "normalize" (L1 renormalisation, _solver.py:55-57), 1 = "duchi" (Euclidean projection, Duchi et al.
+// 2008): descending bitonic sort of the row across the warp's registers, inclusive prefix sums in sorted order, rho = last
+// index whose value exceeds the running threshold, then w = max(v - theta, 0).  Every reduction is a fixed shuffle tree.
 template <typename Real, int EPL>
 __device__ __forceinline__ void w_row_project(Real (&v)[EPL], Real part, int k, int lane, int projection, Real* __restrict__ Wrow) {
+  static_assert(EPL == 1 || EPL == 2 || EPL == 4, "components per lane");
   if (projection == 0) {
     const Real sum = warp_sum(part);
 #pragma unroll
@@ -75,7 +76,7 @@ __device__ __forceinline__ void w_row_project(Real (&v)[EPL], Real part, int k, 
       if (lane + 32 * e < k) Wrow[lane + 32 * e] = v[e] / sum;
     return;
   }
-  // ---- Duchi: bitonic sort (descending) of the 32 * EPL values held one (two) per lane; padding sorts last
+  // ---- Duchi: bitonic sort (descending) of the 32 * EPL values, element index = lane + 32 e; padding sorts last
   const Real NEG = -INFINITY;
   Real u[EPL];
 #pragma unroll
@@ -85,13 +86,17 @@ __device__ __forceinline__ void w_row_project(Real (&v)[EPL], Real part, int k, 
   for (int size = 2; size <= NEL; size <<= 1) {
 #pragma unroll
     for (int j = size >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {                               // partner is this lane's other register (EPL == 2, j == 32)
-        if constexpr (EPL == 2) {
-          // element indices lane and lane + 32; direction of the merge: descending when (index & size) == 0
-          const bool desc = ((lane & size) == 0);   // size == 64 here: always descending
-          const Real lo = fmin(u[0], u[1]), hi = fmax(u[0], u[1]);
-          u[0] = desc ? hi : lo;
-          u[1] = desc ? lo : hi;
+      if (j >= 32) {                               // partner is another register of this lane: e ^ (j / 32)
+        const int je = j >> 5;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          if ((e & je) == 0 && (e | je) < EPL) {
+            const int f = e | je;                   // indices lane + 32 e (lower) and lane + 32 f
+            const bool desc = (((32 * e) & size) == 0);   // direction of the merge: descending when (index & size) == 0
+            const Real lo = fmin(u[e], u[f]), hi = fmax(u[e], u[f]);
+            u[e] = desc ? hi : lo;
+            u[f] = desc ? lo : hi;
+          }
         }
       } else {
 #pragma unroll

@@ -223,7 +223,7 @@ void launch_prior_sums(int dtype, const void* H, int64_t n, int k, int kp, int64
 // projection 0 = "normalize": (W*G)/n then L1 renormalisation;  1 = "duchi": (W*G)/n_obs(row)
 // then Euclidean projection onto the simplex (Duchi et al. 2008 sort/threshold; unpinned).
 // ------------------------------------------------------------------------------------
-// One WARP per row, lane = component k (two components per lane for 32 < K <= 64): row reads and writes are single
+// One WARP per row, lane = component k (two components per lane for 32 < K <= 64, four for K <= 128): row reads and writes are single
 // coalesced lines and every reduction is a fixed shuffle tree (deterministic).  Round 1 ran one thread per row with
 // two 64-element local arrays and stride-K global access: on small problems (config 5) it cost as much as the H pass.
 // Duchi: descending bitonic sort of the row across the warp's registers, inclusive prefix sums in sorted order, rho =
@@ -267,8 +267,8 @@ void launch_w_epilogue(int dtype, const void* Gpart, const void* Qpart, int nspl
 #define NBMF_WEPI(Real, EPL)                                                                                               \
   w_epilogue_kernel<Real, EPL><<<grid, 256, 0, st>>>((const Real*)Gpart, (const Real*)Qpart, nsplit, m, n, k, kp, projection, \
                                                      (const Real*)rowcount, (Real*)W, state, bstride)
-  if (dtype == 0) { if (k <= 32) NBMF_WEPI(float, 1); else NBMF_WEPI(float, 2); }
-  else { if (k <= 32) NBMF_WEPI(double, 1); else NBMF_WEPI(double, 2); }
+  if (dtype == 0) { if (k <= 32) NBMF_WEPI(float, 1); else if (k <= 64) NBMF_WEPI(float, 2); else NBMF_WEPI(float, 4); }
+  else { if (k <= 32) NBMF_WEPI(double, 1); else if (k <= 64) NBMF_WEPI(double, 2); else NBMF_WEPI(double, 4); }
 #undef NBMF_WEPI
 }
 
@@ -502,7 +502,7 @@ void launch_pack_csr(const int64_t* indptr, const int32_t* indices, const void* 
 template <typename Real>
 __global__ void reconstruct_kernel(const Real* __restrict__ W, const Real* __restrict__ H, int64_t m, int64_t n, int k,
                                    Real* __restrict__ out) {
-  __shared__ Real sw[8][64];
+  __shared__ Real sw[8][128];
   const int64_t r0 = (int64_t)blockIdx.y * 8;
   for (int t = threadIdx.x; t < 8 * k; t += blockDim.x) {
     const int r = t / k, kk = t % k;

@@ -84,7 +84,8 @@ struct HCfg {
   static constexpr int SMEM = NSTAGE * STAGE_BYTES;
   static_assert(KP % S == 0 && KH % 2 == 0, "K slice per lane must be even");
   static_assert((KP * sizeof(Real)) % 16 == 0, "W rows must be 16-byte multiples");
-  static_assert(BN % 128 == 0 && 1024 % BN == 0, "column tile must divide the 1024-column pitch");
+  static_assert(BN % 64 == 0 && 1024 % BN == 0, "column tile must divide the 1024-column pitch");
+  static constexpr int BIT_CB = WPT >= 4 ? 16 : 8;   // bytes per cp.async of a bit-plane tile row (BN = 64: two words)
   static_assert(32 % C == 0, "a thread's bits must not straddle a word");
 };
 
@@ -144,24 +145,18 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     const int wchunks = nrows * (KP * (int)sizeof(Real) / 16);
     const unsigned char* wsrc = Wg + (size_t)rb * KP * sizeof(Real);
     for (int c = tid; c < wchunks; c += NT) cp_async16(st + 16 * c, wsrc + 16 * (size_t)c);
-    if constexpr (!DENSE) {
-      constexpr int CPR = WPT / 4;                               // 16-byte chunks per tile row
+    auto bit_rows = [&](unsigned char* dst, const uint32_t* __restrict__ plane) {   // nrows x WPT words of a bit plane
+      constexpr int CB = Cfg::BIT_CB, CPR = WPT * 4 / CB;         // chunks of CB bytes per tile row
       const int bchunks = nrows * CPR;
       for (int c = tid; c < bchunks; c += NT) {
         const int r = c / CPR, q = c % CPR;
-        cp_async16(st + Cfg::W_BYTES + 16 * c,
-                   a.P + (size_t)(rb + r) * a.wpr + (size_t)blockIdx.x * WPT + 4 * q);
+        const uint32_t* src = plane + (size_t)(rb + r) * a.wpr + (size_t)blockIdx.x * WPT + (CB / 4) * q;
+        if constexpr (CB == 16) cp_async16(dst + CB * c, src);
+        else cp_async8(dst + CB * c, src);
       }
-    }
-    if constexpr (STRICT) {
-      constexpr int CPR = WPT / 4;
-      const int bchunks = nrows * CPR;
-      for (int c = tid; c < bchunks; c += NT) {
-        const int r = c / CPR, q = c % CPR;
-        cp_async16(st + Cfg::W_BYTES + Cfg::P_BYTES + 16 * c,
-                   a.M + (size_t)(rb + r) * a.wpr + (size_t)blockIdx.x * WPT + 4 * q);
-      }
-    }
+    };
+    if constexpr (!DENSE) bit_rows(st + Cfg::W_BYTES, a.P);
+    if constexpr (STRICT) bit_rows(st + Cfg::W_BYTES + Cfg::P_BYTES, a.M);
     if constexpr (DENSE) {
       // the V*mask tile: rows of BN elements, NSTAGE - 1 tiles (2 x 16 rows) ahead of the arithmetic -- a register
       // prefetch one row ahead left the DRAM latency exposed (52 % of the stall samples on the load's first use)
@@ -366,12 +361,14 @@ struct WCfg {
   static constexpr int BMR = NW * RW;       // rows per CTA
   static constexpr int BNT = 128;           // columns per stage
   static constexpr int NWORD = BNT / 32;
-  static constexpr int NSTAGE = 2;
   static constexpr int NT = NW * 32;
   static constexpr int HT_BYTES = BNT * KP * (int)sizeof(Real);
   static constexpr int P_BYTES = DENSE ? 0 : BMR * NWORD * 4;
   static constexpr int M_BYTES = BMR * NWORD * 4;
   static constexpr int STAGE_BYTES = HT_BYTES + P_BYTES + M_BYTES;
+  // two stages (the next Ht tile loads while this one is worked on) unless they exceed the SM's shared memory: fp64 at
+  // K > 96 (128 x 128 x 8 = 128 KB per tile) runs single-staged
+  static constexpr int NSTAGE = 2 * STAGE_BYTES <= 200 * 1024 ? 2 : 1;
   static constexpr int SMEM = NSTAGE * STAGE_BYTES;
   static_assert(KP % S == 0 && KH % 2 == 0, "K slice per lane must be even");
   static_assert((KP * sizeof(Real)) % 16 == 0, "Ht rows must be 16-byte multiples");
@@ -445,13 +442,21 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
     for (int rr = 0; rr < C; ++rr)
       load_v<VT, Real, 8>(Vg + (size_t)min(ib + il + rr, a.m - 1) * a.ldv + min(c0, a.ldv - 8), vnext[rr]);
   }
-  if (ntiles > 0) issue_tile(0);
-  cp_async_commit();
+  if constexpr (NSTAGE > 1) {
+    if (ntiles > 0) issue_tile(0);
+    cp_async_commit();
+  }
 
   for (int64_t t = 0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) issue_tile(t + 1);
-    cp_async_commit();
-    cp_async_wait<1>();
+    if constexpr (NSTAGE > 1) {
+      if (t + 1 < ntiles) issue_tile(t + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {                                                       // single stage: load, then work (see WCfg)
+      issue_tile(t);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
     __syncthreads();
 
     const unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;

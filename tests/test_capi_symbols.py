@@ -42,10 +42,11 @@ def test_pure_host_entry_points():
     assert lib.nbmf_words_per_row(1025) == 64 and lib.nbmf_words_per_row(100000) == 3136
     assert lib.nbmf_padded_cols(500) == 1024
     h, w, kp = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
-    for k, want in [(1, 4), (4, 4), (6, 8), (10, 12), (16, 16), (20, 20), (32, 32), (33, 48), (64, 64)]:
+    for k, want in [(1, 4), (4, 4), (6, 8), (10, 12), (16, 16), (20, 20), (32, 32), (33, 48), (64, 64), (65, 96), (97, 128), (128, 128)]:
         assert lib.nbmf_variant_info(0, 0, k, ctypes.byref(h), ctypes.byref(w), ctypes.byref(kp)) == 0
         assert kp.value == want and 1024 % h.value == 0 and w.value % 32 == 0
-    assert lib.nbmf_variant_info(0, 0, 65, None, None, None) != 0
+    assert lib.nbmf_variant_info(1, 0, 128, ctypes.byref(h), ctypes.byref(w), ctypes.byref(kp)) == 0 and h.value == 64    # fp64: 64-column tiles
+    assert lib.nbmf_variant_info(0, 0, 129, None, None, None) != 0
     assert b"variant" in lib.nbmf_last_error()
 
 

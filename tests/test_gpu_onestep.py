@@ -54,9 +54,9 @@ def test_objective_matches_reference_loss(golden_onestep, name, dtype, tol):
     assert abs(loss - float(c["loss1"])) <= tol * abs(float(c["loss1"])), (name, loss, float(c["loss1"]))
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 9, 12, 13, 16, 17, 20, 21, 24, 25, 31, 32, 33, 40, 48, 49, 64])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 9, 12, 13, 16, 17, 20, 21, 24, 25, 31, 32, 33, 40, 48, 49, 64, 65, 80, 96, 97, 128])
 def test_every_k_variant_against_oracle(k):
-    """All padded-K kernel variants (4..64) in both dtypes, masked, ragged shapes."""
+    """All padded-K kernel variants (4..128) in both dtypes, masked, ragged shapes."""
     rng = np.random.default_rng(k)
     m, n = 150 + 3 * k, 1100 + k                  # n crosses the 1024-column pitch, m is not a tile multiple
     Y = (rng.random((m, n)) < 0.2).astype(np.float64)
@@ -119,3 +119,40 @@ def test_empty_and_degenerate_inputs():
     assert np.array_equal(np.isnan(W1), np.isnan(Wo)) and np.isnan(W1[:, 9]).all()
     ok = ~np.isnan(Wo)
     assert rel_err(W1[ok], Wo[ok]) < 1e-9 and rel_err(H1, Ho) < 1e-9
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 5e-5)])
+def test_more_than_64_components(dtype, tol):
+    """64 < K <= 128 (the K axis split over 8 lanes; 64-column H-pass tiles and a single-staged W pass in fp64; four
+    components per lane in the W epilogue): Duchi projection, strict mask semantics, probabilistic X and a short
+    trajectory against the oracle; beyond 128 the C-ABI says so."""
+    rng = np.random.default_rng(21)
+    m, n, k = 210, 1300, 100
+    Y = (rng.random((m, n)) < 0.2).astype(np.float64)
+    mask = (rng.random((m, n)) < 0.85).astype(np.float64)
+    W = rng.uniform(0.1, 0.9, (k, m)); W /= W.sum(axis=0, keepdims=True)
+    H = rng.uniform(0.05, 0.95, (k, n))
+    Wo, Ho = orc.mm_step(Y, W, H, mask, 1.2, 1.2, projection="duchi")
+    W1, H1 = nbmf_mm_update_beta_dir(Y, W, H, mask, 1.2, 1.2, projection_method="duchi", dtype=dtype)
+    assert rel_err(H1, Ho) < tol and rel_err(W1, Wo) < tol
+    assert np.all(W1 >= 0) and np.allclose(W1.sum(axis=0), 1.0, atol=1e-6)
+    Wo, Ho = orc.mm_step(Y, W, H, mask, 1.4, 1.1, mask_semantics="strict")
+    W1, H1 = nbmf_mm_update_beta_dir(Y, W, H, mask, 1.4, 1.1, mask_semantics="strict", dtype=dtype)
+    assert rel_err(H1, Ho) < tol and rel_err(W1, Wo) < tol
+    Yp = rng.random((90, 140))                                   # probabilistic X: the dense layout, K = 72 and 128
+    for kk in (72, 128):
+        Wp = rng.uniform(0.1, 0.9, (kk, 90)); Wp /= Wp.sum(axis=0, keepdims=True)
+        Hp = rng.uniform(0.05, 0.95, (kk, 140))
+        Wo, Ho = orc.mm_step(Yp, Wp, Hp, mask[:90, :140], 1.2, 1.3)
+        W1, H1 = nbmf_mm_update_beta_dir(Yp, Wp, Hp, mask[:90, :140], 1.2, 1.3, dtype=dtype)
+        assert rel_err(H1, Ho) < tol and rel_err(W1, Wo) < tol
+    from nbmf_mm_b200 import nbmf_mm_solver
+    for orientation in ("beta-dir", "dir-beta"):
+        want = orc.fit(Y, 90, max_iter=12, tol=0.0, mask=mask, random_state=3, orientation=orientation)
+        got = nbmf_mm_solver(Y, 90, max_iter=12, tol=0.0, mask=mask, random_state=3, orientation=orientation, dtype=dtype)
+        assert got[4] == want[3] == 12
+        assert rel_err(got[2], want[2]) < (1e-9 if dtype == "float64" else 1e-4)
+        if dtype == "float64":
+            assert rel_err(got[0], want[0]) < 1e-8 and rel_err(got[1], want[1]) < 1e-8
+    with pytest.raises(RuntimeError, match="1..128"):
+        nbmf_mm_update_beta_dir(Y, np.full((129, m), 1 / 129), rng.uniform(0.1, 0.9, (129, n)), mask, 1.2, 1.2, dtype=dtype)
