@@ -60,7 +60,19 @@ __device__ __forceinline__ float  rcp_(float x)  {   // bare MUFU.RCP: x >= eps 
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+// fp64: `1.0 / x` compiles to MUFU.RCP64H, the five-DFMA Newton chain below AND a range test that branches to a slow
+// path for operands outside the normal range; the branch cuts the row loop of the pass kernels into basic blocks that
+// ptxas cannot interleave.  x = (Theta | 1 - Theta) + eps is always a normal number here, so the chain alone is enough:
+// faithfully rounded (<= 1 ulp; the parity bar is 1e-9), no branch.
+__device__ __forceinline__ double rcp_(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 __device__ __forceinline__ float  div_(float a, float b)  { return a * rcp_(b); }
 __device__ __forceinline__ double div_(double a, double b) { return a / b; }
 __device__ __forceinline__ float  logu_(float x)  {   // bare MUFU.LG2 (log2 units)

@@ -13,6 +13,8 @@
 // that fp32 issues packed FFMA2 (one issue slot per two FMAs).
 #pragma once
 #include <cuda_fp16.h>
+
+#include <type_traits>
 #include "args.h"
 #include "common.cuh"
 
@@ -177,6 +179,11 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     cp_async_commit();
   }
 
+  // the tile loop, once per value of a.compute_cd: as a run-time test inside the row loop the flag is a (uniform) branch
+  // that cuts the loop body into basic blocks, and ptxas then cannot interleave the Theta dots, the reciprocal chain and
+  // the accumulations of the two unrolled rows
+  auto tile_loop = [&](auto cd_tag) {
+  constexpr bool CD = decltype(cd_tag)::value;
   for (int64_t t = 0; t < ntiles; ++t) {
     if (t + NSTAGE - 1 < ntiles) issue_tile(t + NSTAGE - 1);
     cp_async_commit();
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
           rn_ = div_(neg, xn);
           ll[cc] += v * logu_(xp) + neg * logu_(xn);
         }
-        if (a.compute_cd) {
+        if constexpr (CD) {
           const V2 rp2 = make2(rp, rp), rn2 = make2(rn_, rn_);
 #pragma unroll
           for (int q = 0; q < KH / 2; ++q) {
@@ -303,6 +310,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     for (int cc = 0; cc < C; ++cc) lld[cc] += (double)ll[cc];
     __syncthreads();
   }
+  };
+  if (a.compute_cd) tile_loop(std::true_type{});
+  else tile_loop(std::false_type{});
   cp_async_wait<0>();
 
   // ---- partial C, D for this row split
