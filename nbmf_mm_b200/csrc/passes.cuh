@@ -57,6 +57,37 @@ __device__ __forceinline__ void load_v(const VT* __restrict__ p, Real (&out)[N])
   for (int i = 0; i < N; ++i) out[i] = (Real)tmp[i];
 }
 
+// Factor rows in shared memory: lane kp of a group reads its K slice (KH elements) of a row with 16-byte loads, and the
+// 8 lanes of one shared-memory phase hold min(S, 8) different slices.  Slices that lie a multiple of 128 bytes apart fall
+// on the same banks (ncu: 5e8 bank conflicts per pass in fp64, where two slices of 16 doubles are exactly 128 bytes apart;
+// 8-way at K = 128), so such tilings get 16 bytes of padding after every slice: slice kp starts at kp * (slice + 16).
+// MINS: pad only tilings with at least this many slices per row.  The W pass pads every conflicting tiling (fp64 K <= 32,
+// two slices: 75.5 -> 71.6 ms), the H pass from four slices on (fp32 K = 64: 181.6 -> 174.8 ms): its two-slice fp64 case
+// is not bound by shared memory and lost 3 % to the longer address arithmetic.
+template <typename Real, int KH, int S, int MINS>
+struct SlicePad {
+  static constexpr int SLICE_B = KH * (int)sizeof(Real);
+  static constexpr int ways() {
+    int w = 0;
+    for (int d = 0; d < (S < 8 ? S : 8); ++d)
+      if ((d * SLICE_B) % 128 == 0) ++w;
+    return w;
+  }
+  static constexpr int PAD_B = (ways() >= 2 && S >= MINS) ? 16 : 0;
+  static constexpr int STRIDE_B = SLICE_B + PAD_B;          // bytes from one slice of a row to the next
+  static constexpr int ROW_B = S * STRIDE_B;                // bytes per factor row in shared memory
+  static constexpr int CPR = S * SLICE_B / 16;              // 16-byte chunks per row of the contiguous global layout
+  static_assert((S * SLICE_B) % 16 == 0, "factor rows must be 16-byte multiples");
+  static_assert(PAD_B == 0 || SLICE_B % 16 == 0, "padded slices must be 16-byte multiples");
+  // byte offset inside the tile of chunk c of the contiguous global layout (row-major, K elements per row)
+  __device__ static __forceinline__ int chunk_offset(int c) {
+    if constexpr (PAD_B == 0) return 16 * c;
+    constexpr int CH = SLICE_B / 16;                        // chunks per slice
+    const int r = c / CPR, q = c - r * CPR;
+    return r * ROW_B + q * 16 + (q / CH) * PAD_B;
+  }
+};
+
 // =====================================================================================
 // H pass:  C[k][j] = sum_i W[i][k] * pos[i][j] / (Theta[i][j] + eps)
 //          D[k][j] = sum_i W[i][k] * neg[i][j] / ((1 - Theta[i][j]) + eps)
@@ -78,14 +109,14 @@ struct HCfg {
   static constexpr int BM = DENSE ? 16 : 32;   // rows per stage (dense: the V tile rides in the stage too)
   static constexpr int NSTAGE = 3;
   static constexpr int NT = NW * 32;
-  static constexpr int W_BYTES = BM * KP * (int)sizeof(Real);
+  using Pad = SlicePad<Real, KP / S, S, 4>;
+  static constexpr int W_BYTES = BM * Pad::ROW_B;
   static constexpr int P_BYTES = DENSE ? 0 : BM * WPT * 4;
   static constexpr int M_BYTES = STRICT ? BM * WPT * 4 : 0;
   static constexpr int V_BYTES = DENSE ? BM * BN * (int)sizeof(VT) : 0;   // dense V*mask tile, staged by cp.async
   static constexpr int STAGE_BYTES = W_BYTES + P_BYTES + M_BYTES + V_BYTES;
   static constexpr int SMEM = NSTAGE * STAGE_BYTES;
   static_assert(KP % S == 0 && KH % 2 == 0, "K slice per lane must be even");
-  static_assert((KP * sizeof(Real)) % 16 == 0, "W rows must be 16-byte multiples");
   static_assert(BN % 64 == 0 && 1024 % BN == 0, "column tile must divide the 1024-column pitch");
   static constexpr int BIT_CB = WPT >= 4 ? 16 : 8;   // bytes per cp.async of a bit-plane tile row (BN = 64: two words)
   static_assert(32 % C == 0, "a thread's bits must not straddle a word");
@@ -146,7 +177,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     const int nrows = (int)min((int64_t)BM, r1 - rb);
     const int wchunks = nrows * (KP * (int)sizeof(Real) / 16);
     const unsigned char* wsrc = Wg + (size_t)rb * KP * sizeof(Real);
-    for (int c = tid; c < wchunks; c += NT) cp_async16(st + 16 * c, wsrc + 16 * (size_t)c);
+    for (int c = tid; c < wchunks; c += NT) cp_async16(st + Cfg::Pad::chunk_offset(c), wsrc + 16 * (size_t)c);
     auto bit_rows = [&](unsigned char* dst, const uint32_t* __restrict__ plane) {   // nrows x WPT words of a bit plane
       constexpr int CB = Cfg::BIT_CB, CPR = WPT * 4 / CB;         // chunks of CB bytes per tile row
       const int bchunks = nrows * CPR;
@@ -191,7 +222,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
     __syncthreads();
 
     const unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;
-    const Real* Wt = reinterpret_cast<const Real*>(st);
+    const unsigned char* Wt = st + kp * Cfg::Pad::STRIDE_B;      // this lane's K slice of row 0
     const uint32_t* Pb = reinterpret_cast<const uint32_t*>(st + Cfg::W_BYTES);
     const uint32_t* Mb = reinterpret_cast<const uint32_t*>(st + Cfg::W_BYTES + Cfg::P_BYTES);
     const int64_t rb = r0 + t * BM;
@@ -227,7 +258,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) h_pass_kernel(const HPassA
 #pragma unroll 2
     for (int r = 0; r < nrows; ++r) {
       V2 wp[KH / 2];
-      load_pairs<Real, KH>(Wt + r * KP + kp * KH, wp);
+      load_pairs<Real, KH>(reinterpret_cast<const Real*>(Wt + r * Cfg::Pad::ROW_B), wp);
 
       // ---- Theta[i][j] for the C owned columns
       V2 th[C];
@@ -372,7 +403,8 @@ struct WCfg {
   static constexpr int BNT = 128;           // columns per stage
   static constexpr int NWORD = BNT / 32;
   static constexpr int NT = NW * 32;
-  static constexpr int HT_BYTES = BNT * KP * (int)sizeof(Real);
+  using Pad = SlicePad<Real, KP / S, S, 2>;
+  static constexpr int HT_BYTES = BNT * Pad::ROW_B;
   static constexpr int P_BYTES = DENSE ? 0 : BMR * NWORD * 4;
   static constexpr int M_BYTES = BMR * NWORD * 4;
   static constexpr int STAGE_BYTES = HT_BYTES + P_BYTES + M_BYTES;
@@ -381,7 +413,6 @@ struct WCfg {
   static constexpr int NSTAGE = 2 * STAGE_BYTES <= 200 * 1024 ? 2 : 1;
   static constexpr int SMEM = NSTAGE * STAGE_BYTES;
   static_assert(KP % S == 0 && KH % 2 == 0, "K slice per lane must be even");
-  static_assert((KP * sizeof(Real)) % 16 == 0, "Ht rows must be 16-byte multiples");
 };
 
 template <typename Cfg>
@@ -434,9 +465,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
   auto issue_tile = [&](int64_t t) {
     unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;
     const int64_t cb = c0 + t * BNT;
-    constexpr int HCH = Cfg::HT_BYTES / 16;
+    constexpr int HCH = BNT * Cfg::Pad::CPR;
     const unsigned char* hsrc = Htg + (size_t)cb * KP * sizeof(Real);
-    for (int c = tid; c < HCH; c += NT) cp_async16(st + 16 * c, hsrc + 16 * (size_t)c);
+    for (int c = tid; c < HCH; c += NT) cp_async16(st + Cfg::Pad::chunk_offset(c), hsrc + 16 * (size_t)c);
     const int64_t wb = cb >> 5;                                   // first bit word of this tile
     for (int r = tid; r < BMR; r += NT) {
       const int64_t row = min(ib + r, a.m - 1);
@@ -470,7 +501,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
     __syncthreads();
 
     const unsigned char* st = smem + (size_t)(t % NSTAGE) * Cfg::STAGE_BYTES;
-    const Real* Hts = reinterpret_cast<const Real*>(st);
+    const unsigned char* Hts = st + kp * Cfg::Pad::STRIDE_B;    // this lane's K slice of column 0 of the tile
     const uint32_t* Pb = reinterpret_cast<const uint32_t*>(st + Cfg::HT_BYTES);
     const uint32_t* Mb = reinterpret_cast<const uint32_t*>(st + Cfg::HT_BYTES + Cfg::P_BYTES);
     const int64_t cb = c0 + t * BNT;
@@ -510,7 +541,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB) w_pass_kernel(const WPassA
         for (int e = 0; e < 8; ++e) {
           const int jj = 8 * u + e;
           V2 hq[KH / 2];
-          load_pairs<Real, KH>(Hts + (32 * w + jj) * KP + kp * KH, hq);
+          load_pairs<Real, KH>(reinterpret_cast<const Real*>(Hts + (32 * w + jj) * Cfg::Pad::ROW_B), hq);
           V2 th[C];
 #pragma unroll
           for (int rr = 0; rr < C; ++rr) th[rr] = make2(Real(0), Real(0));
