@@ -696,7 +696,9 @@ static int format_w(nbmf_ctx* c, bool guarded) {
 }
 static int format_h(nbmf_ctx* c, bool guarded) {
   if (!c->p.tensor) return NBMF_OK;
-  launch_format_h(c->H(), c->p.ldh, c->p.pl.kp, c->ws + c->p.oHf, guarded ? c->state() : nullptr, c->st,
+  // K <= 32 kernels: MMA1 of the W pass yields Theta + eps (see format_h_kernel); the K <= 64 kernels add eps themselves
+  const float theta_bias = c->p.pl.kp == 32 ? (float)c->cfg.eps : 0.0f;
+  launch_format_h(c->H(), c->p.ldh, c->p.pl.kp, theta_bias, c->ws + c->p.oHf, guarded ? c->state() : nullptr, c->st,
                   guarded ? c->batch_n : 1, guarded ? c->batch_stride : 0);
   CHECK_LAUNCH(1);
   return NBMF_OK;

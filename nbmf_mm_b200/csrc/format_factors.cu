@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) format_w_kernel(const float* __restrict__
 
 template <int KT>
 __global__ void __launch_bounds__(256) format_h_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ Hf,
-                                                       const FitState* __restrict__ state, int64_t bstride) {
+                                                       const FitState* __restrict__ state, int64_t bstride, float theta_bias) {
   if (bstride) {
     const size_t sh = (size_t)blockIdx.z * (size_t)bstride;
     H = batch_shift(H, sh); Hf = batch_shift(Hf, sh);
@@ -113,12 +113,14 @@ __global__ void __launch_bounds__(256) format_h_kernel(const float* __restrict__
       int r, c, w;
       unswizzle((uint32_t)(d & 2047) * 4u, r, c, w);
       const int slab = d >> 11;
-      blk[d] = __float_as_uint(tc::tf32_trunc(tile[32 * slab + 4 * c + (w >> 2)][r]));
+      // theta_bias: W's rows sum to one, so Theta + eps = sum_k W_ik (H_kj + eps) -- the MMA1 operand of the K <= 32 W
+      // pass is formatted from H + eps and the ones' x is the MMA output itself (one FADD per entry less, w_entry)
+      blk[d] = __float_as_uint(tc::tf32_trunc(tile[32 * slab + 4 * c + (w >> 2)][r] + theta_bias));
       uint32_t word = 0;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int idx = 64 * slab + 8 * c + (w >> 1) + q;
-        const float x = tile[idx < KT ? idx : idx - KT][r];
+        const float x = tile[idx < KT ? idx : idx - KT][r] + theta_bias;
         const float hi = tc::tf32_trunc(x);
         word |= tc::bf16_bits(idx < KT ? x - hi : hi) << (16 * q);
       }
@@ -142,11 +144,11 @@ void launch_format_w(const void* W, int64_t m, int64_t mpad, int kt, void* Wf, c
   if (kt == 64) format_w_kernel<64><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state, bstride);
   else format_w_kernel<32><<<grid, 256, 0, st>>>((const float*)W, m, mpad, (float*)Wf, state, bstride);
 }
-void launch_format_h(const void* H, int64_t ldh, int kt, void* Hf, const FitState* state, cudaStream_t st,
+void launch_format_h(const void* H, int64_t ldh, int kt, float theta_bias, void* Hf, const FitState* state, cudaStream_t st,
                      int batch_n, int64_t bstride) {
   dim3 grid((unsigned)(ldh / 64), 1, (unsigned)batch_n);              // one block per 64-column block of H
-  if (kt == 64) format_h_kernel<64><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state, bstride);
-  else format_h_kernel<32><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state, bstride);
+  if (kt == 64) format_h_kernel<64><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state, bstride, theta_bias);
+  else format_h_kernel<32><<<grid, 256, 0, st>>>((const float*)H, ldh, (float*)Hf, state, bstride, theta_bias);
 }
 
 // Ones per column of a re-tiled plane (Pc layout), accumulated over the row blocks [rb0, rb1): the H pass uses the

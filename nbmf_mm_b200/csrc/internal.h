@@ -59,7 +59,7 @@ void launch_clip_rows(int dtype, void* W, int64_t m, int k, int kp, double lo, d
 // ---- tensor-core engine (K <= 64, fp32, bit-packed V): operand formatting + pass launchers
 void launch_format_w(const void* W, int64_t m, int64_t mpad, int kt, void* Wf, const FitState* state, cudaStream_t st,
                      int batch_n = 1, int64_t batch_stride = 0);
-void launch_format_h(const void* H, int64_t ldh, int kt, void* Hf, const FitState* state, cudaStream_t st,
+void launch_format_h(const void* H, int64_t ldh, int kt, float theta_bias, void* Hf, const FitState* state, cudaStream_t st,
                      int batch_n = 1, int64_t batch_stride = 0);
 void launch_colcount(const uint32_t* Pc, int64_t nrb, int64_t rb0, int64_t rb1, int64_t ldh, uint32_t* colcnt, cudaStream_t st);
 void launch_tile_planes(const uint32_t* P, const uint32_t* M, int64_t m, int64_t n, int64_t wpr, int64_t mpad,

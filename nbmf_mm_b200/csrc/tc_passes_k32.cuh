@@ -144,20 +144,22 @@ __device__ __forceinline__ float h_x_strict(float theta, uint32_t bits, uint32_t
   return x;
 }
 //   W pass: signed ratio s = 1/(theta + eps) on ones, -1/((1 - theta) + eps) on observed zeros, 0 on unobserved
-//   entries; q accumulates the zeros' 1/x (= -s) with one predicated subtract.
-__device__ __forceinline__ void w_entry(float theta, uint32_t pbits, uint32_t obits, uint32_t bit, float eps, float& s,
+//   entries; q accumulates the zeros' 1/x (= -s) with one predicated subtract.  `te` is Theta + eps as MMA1 delivers it
+//   (its H operand is formatted from H + eps and W's rows sum to one: format_h_kernel), so the ones' x costs nothing and
+//   the zeros' x = (te - 1) - 2 eps = -((1 - Theta) + eps) two predicated FADDs; eps2 = 2 eps.
+__device__ __forceinline__ void w_entry(float te, uint32_t pbits, uint32_t obits, uint32_t bit, float eps2, float& s,
                                         float& q) {
   asm("{\n\t.reg .pred p, o;\n\t.reg .b32 t;\n\t.reg .f32 y;\n\t"
       "and.b32 t, %3, %5;\n\tsetp.ne.b32 p, t, 0;\n\t"
       "and.b32 t, %4, %5;\n\tsetp.ne.b32 o, t, 0;\n\t"
-      "add.f32 y, %2, %6;\n\t"
+      "mov.f32 y, %2;\n\t"
       "@!p add.f32 y, %2, 0fBF800000;\n\t"
       "@!p sub.f32 y, y, %6;\n\t"
       "rcp.approx.ftz.f32 y, y;\n\t"
       "selp.f32 %0, y, 0f00000000, o;\n\t"
       "@!p sub.f32 %1, %1, %0;\n\t}\n"
       : "=f"(s), "+f"(q)
-      : "f"(theta), "r"(pbits), "r"(obits), "r"(bit), "f"(eps));
+      : "f"(te), "r"(pbits), "r"(obits), "r"(bit), "f"(eps2));
 }
 
 constexpr int TC_SIMT_WARPS = 16;
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int tl = q * 32 + lane;
     const int64_t row = ib + tl;
-    const float eps = a.eps;
+    const float eps2 = 2.0f * a.eps;                                   // Theta arrives with eps added: see w_entry
     {  // resident A operand: this thread's row of W, k = 8 w4 .. 8 w4 + 7 (zero beyond m)
       float x[8];
       if (row < a.m) {
@@ -704,7 +706,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w_pass_tc_kernel(const WTcArgs 
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             float sv;
-            w_entry(__uint_as_float(v[8 * w + e]), bits.x, bits.y, 1u << (16 * u + 8 * w + e), eps, sv, qb);
+            w_entry(__uint_as_float(v[8 * w + e]), bits.x, bits.y, 1u << (16 * u + 8 * w + e), eps2, sv, qb);
             const float hi = tf32_trunc(sv);
             out[e] = __float_as_uint(hi);
             out[8 + e] = pack_bf16x2(hi, sv - hi);                       // (hi, lo) of s in one column
