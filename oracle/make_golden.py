@@ -78,6 +78,7 @@ def onestep_cases():
         ("bin_alpha_lt1", 50, 30, 5, 0.4, None, 0.5, 2.0),
         ("bin_k1", 17, 19, 1, 0.5, 0.9, 1.2, 1.2),
         ("bin_wide", 5, 300, 3, 0.2, 0.85, 1.2, 1.2),
+        ("bin_mask_k100", 48, 130, 100, 0.15, 0.9, 1.2, 1.3),      # 64 < K <= 128: the 8-lane K split of the CUDA-core engine
     ]
     for idx, (name, m, n, k, dens, mfrac, a, b) in enumerate(specs):
         rng = np.random.default_rng(1000 + idx)
@@ -153,6 +154,13 @@ def trajectories(data, animals_train):
     out["k40/X_bits"] = np.packbits(Xk.astype(bool), axis=1, bitorder="little")
     out["k40/mask_bits"] = np.packbits(Mk.astype(bool), axis=1, bitorder="little")
     run("k40", Xk, 40, orientation="beta-dir", max_iter=40, tol=0.0, random_state=1, mask=Mk)
+    # K = 70: the 64 < K <= 128 kernels (K padded to 96), both dtypes on the CUDA-core engine
+    rng = np.random.default_rng(10)
+    X70 = (rng.random((120, 100)) < 0.12).astype(float)
+    M70 = (rng.random(X70.shape) < 0.9).astype(float)
+    out["k70/X_bits"] = np.packbits(X70.astype(bool), axis=1, bitorder="little")
+    out["k70/mask_bits"] = np.packbits(M70.astype(bool), axis=1, bitorder="little")
+    run("k70", X70, 70, orientation="beta-dir", max_iter=30, tol=0.0, alpha=1.1, beta=1.3, random_state=4, mask=M70)
     # probabilistic X through the estimator
     Xp = np.random.default_rng(5).random((45, 60))
     out["prob/X"] = Xp

@@ -13,7 +13,8 @@ from nbmf_mm_b200.solver import make_problem, prepare_data
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["bin_nomask", "bin_mask", "bin_mask_k32", "prob_nomask", "prob_mask", "bin_alpha_lt1", "bin_k1", "bin_wide"]
+CASES = ["bin_nomask", "bin_mask", "bin_mask_k32", "prob_nomask", "prob_mask", "bin_alpha_lt1", "bin_k1", "bin_wide",
+         "bin_mask_k100"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -31,6 +31,8 @@ def _cases(datasets, golden_traj):
                           dict(n_components=6, orientation="dir-beta", max_iter=60, tol=1e-8, alpha=1.2, beta=1.4, random_state=2)),
         "k40": (_bits(g["k40"]["X_bits"], 600), _bits(g["k40"]["mask_bits"], 600),
                 dict(n_components=40, max_iter=40, tol=0.0, random_state=1)),
+        "k70": (_bits(g["k70"]["X_bits"], 100), _bits(g["k70"]["mask_bits"], 100),
+                dict(n_components=70, max_iter=30, tol=0.0, alpha=1.1, beta=1.3, random_state=4)),
         "cfg1": (cfg1_matrix(), None, dict(n_components=6, alpha=1.2, beta=1.2, random_state=0)),
         "cfg2_animals": (datasets["animals"], None, dict(n_components=10, max_iter=500, tol=1e-5, random_state=0)),
         "cfg2_lastfm": (datasets["lastfm"], None, dict(n_components=10, max_iter=500, tol=1e-5, random_state=0)),
@@ -45,7 +47,7 @@ def _cases(datasets, golden_traj):
 
 
 NAMES = ["cfg1", "cfg2_animals", "cfg2_lastfm", "cfg2_paleo", "cfg2_animals_train", "cfg3s", "prob",
-         "cfg2_lastfm_train", "cfg2_paleo_train", "wmask", "wmask_dirbeta", "k40"]
+         "cfg2_lastfm_train", "cfg2_paleo_train", "wmask", "wmask_dirbeta", "k40", "k70"]
 
 
 @pytest.mark.parametrize("name", NAMES)

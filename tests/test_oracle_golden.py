@@ -125,3 +125,16 @@ def test_weighted_mask_train_splits_and_k40(golden_traj, datasets):
     gk = golden_traj["k40"]
     _, _, losses, _ = orc.fit(unbits(gk["X_bits"], 600), 40, max_iter=6, tol=0.0, random_state=1, mask=unbits(gk["mask_bits"], 600))
     assert np.array_equal(np.asarray(losses), gk["losses"][:6])
+
+
+def test_more_than_64_components_against_the_reference(golden_onestep, golden_traj):
+    """Golden cases from the real reference for the 64 < K <= 128 kernels: one step at K = 100, 30 iterations at K = 70."""
+    c = golden_onestep["bin_mask_k100"]
+    Wo, Ho = orc.mm_step(c["Y"], c["W"], c["H"], c["mask"], float(c["alpha"]), float(c["beta"]))
+    assert c["W"].shape[0] == 100 and np.array_equal(Wo, c["W1"]) and np.array_equal(Ho, c["H1"])
+    unbits = lambda a, n: np.unpackbits(a, axis=1, bitorder="little")[:, :n].astype(np.float64)
+    g = golden_traj["k70"]
+    W, H, losses, n_iter = orc.fit(unbits(g["X_bits"], 100), 70, max_iter=30, tol=0.0, alpha=1.1, beta=1.3, random_state=4,
+                                   mask=unbits(g["mask_bits"], 100))
+    assert n_iter == int(g["n_iter"]) == 30 and np.array_equal(np.asarray(losses), g["losses"])
+    assert np.array_equal(W, g["W"]) and np.array_equal(H, g["H"])
